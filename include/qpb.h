@@ -1,0 +1,180 @@
+/*
+ * qpb.h — C ABI of the B200-native qpsim time-stepping hot path ("qpb" = quasiparticle-B200).
+ *
+ * The reference (Soren-O/Quasiparticle-Physics-Simulation, pure Python) has no FFI layer; its
+ * boundary for this path is the Python function qpsim.solver.run_2d_crank_nicolson
+ * (qpsim/solver.py:999-1036) and the in-place helpers apply_collision_step_fischer_catelani_uniform /
+ * _nonuniform (qpsim/solver.py:794-875).  This header declares what a ctypes binding placed behind those
+ * functions calls (see INTEGRATION.md for the binding).  Every entry point cites the reference lines whose
+ * work it takes over.
+ *
+ * Conventions
+ *  - plain C, caller-owned HOST buffers, library-owned DEVICE buffers, no exceptions across the boundary;
+ *  - every function returns QPB_OK (0) or a negative QPB_E_* code; qpb_last_error() gives the message of the
+ *    last failure on the calling thread;
+ *  - host arrays use the reference's layouts: quasiparticle state  n[NE][N]  and phonon state  n_ph[Nw][N],
+ *    C-contiguous float64, N = number of mask cells in np.argwhere(mask) (row-major) order
+ *    (qpsim/solver.py:53-58); geometry arrays are dense [ny][nx];
+ *  - there is NO CPU fallback: qpb_create fails when no sm_100 device is usable.
+ */
+#ifndef QPB_H
+#define QPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPB_ABI_VERSION 1
+
+/* status codes */
+#define QPB_OK            0
+#define QPB_E_INVALID    -1   /* bad argument / call order            */
+#define QPB_E_CUDA       -2   /* CUDA runtime error (message has it)  */
+#define QPB_E_NOMEM      -3
+#define QPB_E_NODEVICE   -4   /* no usable CUDA device                */
+#define QPB_E_NOCONV     -5   /* diffusion iteration did not converge */
+
+/* qpb_config.flags */
+#define QPB_F_DIFFUSION      (1u << 0)  /* enable_diffusion                      */
+#define QPB_F_SCATTERING     (1u << 1)  /* enable_scattering                     */
+#define QPB_F_RECOMBINATION  (1u << 2)  /* enable_recombination                  */
+#define QPB_F_FREEZE_PHONONS (1u << 3)  /* freeze_phonon_dynamics (solver.py:1406) */
+#define QPB_F_VARIABLE_D     (1u << 4)  /* per-cell D(E,x): solver.py:1145-1164   */
+#define QPB_F_PAULI          (1u << 5)  /* record occupancy diagnostics each step (solver.py:967-996) */
+#define QPB_F_SCALAR         (1u << 6)  /* legacy scalar mode, NE == 1, no dE factor (solver.py:1517-1571) */
+
+typedef struct qpb_ctx qpb_ctx; /* opaque */
+
+typedef struct qpb_config {
+    int32_t abi_version;  /* QPB_ABI_VERSION */
+    int32_t device;       /* CUDA ordinal */
+    int32_t ny, nx;       /* mask shape */
+    int32_t ne;           /* energy bins on this context (all bins on one GPU) */
+    int32_t nw;           /* phonon bins (0 when collisions are off) */
+    int32_t ncell;        /* N = mask cells */
+    int32_t ngap;         /* number of distinct gap tables (1 = uniform gap) */
+    uint32_t flags;       /* QPB_F_* */
+    int32_t reserved;
+    double dx;            /* mesh size */
+    double dE;            /* energy bin width (1.0 for a single bin, solver.py:75-78) */
+    double diff_tol;      /* relative max-norm residual tolerance of the CN solve (<=0: default 1e-12) */
+    double pauli_floor;   /* pauli_density_floor of solver.py:1031 (forbidden-state test)          */
+} qpb_config;
+
+/* diagnostics of the most recent qpb_advance */
+typedef struct qpb_diag {
+    int64_t steps_done;
+    int64_t sweeps;          /* directional tridiagonal sweeps executed (all bins count as one sweep) */
+    int64_t bin_sweeps;      /* sum over bins of sweeps actually applied to that bin                    */
+    int64_t pr_iterations;   /* Peaceman-Rachford double-sweeps (max over bins), summed over steps      */
+    double  last_delta;      /* largest relative update of the last PR iteration                       */
+    int32_t direct_mode;     /* 1: one-cell-thick geometry, CN solved by one direct sweep              */
+    int32_t commuting;       /* 1: Lx,Ly commute (planned Wachspress sequence), 0: cyclic shifts        */
+    int64_t kernel_launches; /* CUDA kernels launched by the library since creation                     */
+} qpb_diag;
+
+/* one record per time step, mirrors _pauli_occupancy_stats (solver.py:967-996) */
+typedef struct qpb_pauli_rec {
+    double  max_occ;     /* max n/rho over cells with rho > 1e-30 (0 elsewhere)          */
+    int64_t max_index;   /* flat index i*N + cell of the first maximum (np.argmax order)  */
+    int64_t forbidden;   /* flat index of the first forbidden-state cell, or -1           */
+} qpb_pauli_rec;
+
+const char *qpb_last_error(void);
+int qpb_abi_version(void);
+/* number of usable sm_100 devices, or a negative code */
+int qpb_device_count(void);
+
+int qpb_create(const qpb_config *cfg, qpb_ctx **out);
+void qpb_destroy(qpb_ctx *ctx);
+
+/*
+ * Geometry and boundary terms — replaces build_laplacian_with_boundaries /_apply_boundary_contribution
+ * (solver.py:112-212).  All arrays dense [ny*nx]:
+ *   mask   1 = cell in the domain
+ *   bcx    sum over the cell's boundary faces in x (left/right) of the face's diagonal term in 1/dx^2
+ *          units (absorbing/dirichlet: 2, robin: beta*dx, reflective/neumann: 0); bcy likewise for up/down
+ *   source s of  rhs = B u + dt*D*s  (dirichlet 2g/dx^2, neumann q/dx, robin gamma/dx), solver.py:130-148
+ */
+int qpb_upload_geometry(qpb_ctx *ctx, const uint8_t *mask, const double *bcx, const double *bcy,
+                        const double *source);
+
+/*
+ * Diffusion coefficients — D[ne] (uniform gap, solver.py:1135,1167) or, with QPB_F_VARIABLE_D, D[ne][N]
+ * (precomputed["D_array"], solver.py:1132, harmonic-mean faces solver.py:283).
+ */
+int qpb_upload_diffusion(qpb_ctx *ctx, const double *D);
+
+/*
+ * Prepare the Crank-Nicolson solve for a step length (slot 0 = dt, slot 1 = remainder_dt): replaces the
+ * per-bin operator build + splu of solver.py:1143-1174.  Chooses direct / planned / cyclic mode and builds
+ * the pivot tables of the tridiagonal sweeps.
+ */
+int qpb_prepare_diffusion(qpb_ctx *ctx, int slot, double dt);
+
+/*
+ * Collision tables (solver.py:1203-1238, 668-683).  K_r0/K_s0: [ngap][ne][ne] (NULL when that process is
+ * off), rho: [ngap][ne], gap_id: [N] (NULL = all zero), idx_diff/idx_sum: [ne][ne] phonon-bin index maps,
+ * sign: [ne][ne] int8 sign(E_i - E_j).
+ */
+int qpb_upload_collision(qpb_ctx *ctx, const double *K_r0, const double *K_s0, const double *rho,
+                         const int32_t *gap_id, const int32_t *idx_diff, const int32_t *idx_sum,
+                         const int8_t *sign);
+
+/* state in the reference layouts; n_ph may be NULL when nw == 0 */
+int qpb_set_state(qpb_ctx *ctx, const double *n, const double *n_ph);
+int qpb_get_state(qpb_ctx *ctx, double *n, double *n_ph);
+/* energy-integrated field  sum_i n[i][cell]*dE  (solver.py:1480), [N] */
+int qpb_get_integrated(qpb_ctx *ctx, double *out);
+
+/* external generation (solver.py:878-964, 1459-1464) */
+#define QPB_GEN_NONE     0
+#define QPB_GEN_CONSTANT 1   /* rate                                  */
+#define QPB_GEN_PULSE    2   /* rate while t0 <= t < t0 + duration    */
+#define QPB_GEN_ARRAY    3   /* host-evaluated g[ne][N], nsteps must be 1 */
+
+typedef struct qpb_generation {
+    int32_t mode;
+    int32_t reserved;
+    double  rate;
+    double  pulse_start;
+    double  pulse_duration;
+    const double *array;   /* QPB_GEN_ARRAY only */
+} qpb_generation;
+
+/*
+ * Advance nsteps time steps of length dt starting at time t_start — the loop body of
+ * solver.py:1454-1478: generation, then C(dt/2) D(dt) C(dt/2) when both collisions and diffusion are on,
+ * otherwise C(dt) D(dt); Pauli record per step when QPB_F_PAULI.  `slot` selects the prepared diffusion
+ * operator.  pauli_out (may be NULL) receives nsteps records.
+ */
+int qpb_advance(qpb_ctx *ctx, int32_t nsteps, double dt, int32_t slot, double t_start,
+                const qpb_generation *gen, qpb_pauli_rec *pauli_out);
+
+/* single stages, used by the multi-GPU driver and by the in-place collision helpers (solver.py:794-875) */
+int qpb_collide(qpb_ctx *ctx, double dt);
+int qpb_diffuse(qpb_ctx *ctx, int32_t slot);
+int qpb_pauli(qpb_ctx *ctx, qpb_pauli_rec *out);
+
+int qpb_get_diag(qpb_ctx *ctx, qpb_diag *out);
+int qpb_synchronize(qpb_ctx *ctx);
+
+/*
+ * Device-side timing of the dominant kernels since the last qpb_reset_timers (CUDA events on the library's
+ * stream): ms spent and launches, for bench.py's roofline.  which: 0 = x sweeps, 1 = y sweeps, 2 = collision.
+ * Timers are off by default (they serialise); qpb_enable_timers(ctx, 1) turns them on.
+ */
+int qpb_enable_timers(qpb_ctx *ctx, int on);
+int qpb_reset_timers(qpb_ctx *ctx);
+int qpb_get_timer(qpb_ctx *ctx, int which, double *ms, int64_t *launches);
+
+/* raw device pointers for NCCL plumbing (torch wraps them): which 0 = dense QP state [ne][ny*nx],
+ * 1 = phonon state [nw][N]; *bytes receives the allocation size */
+int qpb_device_ptr(qpb_ctx *ctx, int which, void **ptr, int64_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPB_H */

@@ -1,0 +1,306 @@
+"""ctypes binding of ``libqpb.so`` (C ABI declared in ``include/qpb.h``).
+
+The library is built in-tree by :func:`build_library` (``nvcc`` for sm_100a only).  There is no Python or CPU
+fallback: if the shared object is missing or no B200 is visible every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+REPO_DIR = os.path.dirname(PKG_DIR)
+CSRC_DIR = os.path.join(PKG_DIR, "csrc")
+LIB_DIR = os.path.join(PKG_DIR, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libqpb.so")
+INCLUDE_DIR = os.path.join(REPO_DIR, "include")
+
+ABI_VERSION = 1
+
+F_DIFFUSION = 1 << 0
+F_SCATTERING = 1 << 1
+F_RECOMBINATION = 1 << 2
+F_FREEZE_PHONONS = 1 << 3
+F_VARIABLE_D = 1 << 4
+F_PAULI = 1 << 5
+F_SCALAR = 1 << 6
+
+GEN_NONE, GEN_CONSTANT, GEN_PULSE, GEN_ARRAY = 0, 1, 2, 3
+
+E_NOCONV = -5
+
+
+class QpbError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libqpb error {code}: {message}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_int32), ("device", C.c_int32), ("ny", C.c_int32), ("nx", C.c_int32),
+        ("ne", C.c_int32), ("nw", C.c_int32), ("ncell", C.c_int32), ("ngap", C.c_int32),
+        ("flags", C.c_uint32), ("reserved", C.c_int32),
+        ("dx", C.c_double), ("dE", C.c_double), ("diff_tol", C.c_double), ("pauli_floor", C.c_double),
+    ]
+
+
+class Diag(C.Structure):
+    _fields_ = [
+        ("steps_done", C.c_int64), ("sweeps", C.c_int64), ("bin_sweeps", C.c_int64),
+        ("pr_iterations", C.c_int64), ("last_delta", C.c_double), ("direct_mode", C.c_int32),
+        ("commuting", C.c_int32), ("kernel_launches", C.c_int64),
+    ]
+
+
+class PauliRec(C.Structure):
+    _fields_ = [("max_occ", C.c_double), ("max_index", C.c_int64), ("forbidden", C.c_int64)]
+
+
+class Generation(C.Structure):
+    _fields_ = [
+        ("mode", C.c_int32), ("reserved", C.c_int32), ("rate", C.c_double), ("pulse_start", C.c_double),
+        ("pulse_duration", C.c_double), ("array", C.c_void_p),
+    ]
+
+
+SOURCES = ["qpb_api.cu", "qpb_diffusion.cu", "qpb_sweep_fast.cu", "qpb_collision.cu", "qpb_aux.cu"]
+
+# every symbol include/qpb.h declares; tests check that the built library exports all of them
+EXPORTED = [
+    "qpb_last_error", "qpb_abi_version", "qpb_device_count", "qpb_create", "qpb_destroy",
+    "qpb_upload_geometry", "qpb_upload_diffusion", "qpb_prepare_diffusion", "qpb_upload_collision",
+    "qpb_set_state", "qpb_get_state", "qpb_get_integrated", "qpb_advance", "qpb_collide", "qpb_diffuse",
+    "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
+    "qpb_device_ptr",
+]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; libqpb cannot be built")
+
+
+def library_is_current() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return False
+    built = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR)] + [os.path.join(INCLUDE_DIR, "qpb.h")]
+    return all(os.path.getmtime(d) <= built for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source of the package for sm_100a into lib/libqpb.so (cross-compiles without a GPU)."""
+    if not force and library_is_current():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    cmd = [
+        _nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+        "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE_DIR, "-I", CSRC_DIR,
+    ]
+    if verbose:
+        cmd += ["-Xptxas", "-v"]
+    cmd += [os.path.join(CSRC_DIR, s) for s in SOURCES] + ["-o", LIB_PATH]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libqpb.so and declare the prototypes.  Raises when the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for this path)"
+        )
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+    lib.qpb_last_error.restype = C.c_char_p
+    lib.qpb_last_error.argtypes = []
+    lib.qpb_abi_version.restype = C.c_int
+    lib.qpb_device_count.restype = C.c_int
+    lib.qpb_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.qpb_destroy.argtypes = [vp]
+    lib.qpb_destroy.restype = None
+    lib.qpb_upload_geometry.argtypes = [vp, vp, vp, vp, vp]
+    lib.qpb_upload_diffusion.argtypes = [vp, vp]
+    lib.qpb_prepare_diffusion.argtypes = [vp, C.c_int, dbl]
+    lib.qpb_upload_collision.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.qpb_set_state.argtypes = [vp, vp, vp]
+    lib.qpb_get_state.argtypes = [vp, vp, vp]
+    lib.qpb_get_integrated.argtypes = [vp, vp]
+    lib.qpb_advance.argtypes = [vp, i32, dbl, i32, dbl, C.POINTER(Generation), vp]
+    lib.qpb_collide.argtypes = [vp, dbl]
+    lib.qpb_diffuse.argtypes = [vp, i32]
+    lib.qpb_pauli.argtypes = [vp, C.POINTER(PauliRec)]
+    lib.qpb_get_diag.argtypes = [vp, C.POINTER(Diag)]
+    lib.qpb_synchronize.argtypes = [vp]
+    lib.qpb_enable_timers.argtypes = [vp, C.c_int]
+    lib.qpb_reset_timers.argtypes = [vp]
+    lib.qpb_get_timer.argtypes = [vp, C.c_int, C.POINTER(dbl), C.POINTER(i64)]
+    lib.qpb_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    for name in EXPORTED:
+        fn = getattr(lib, name)
+        if name not in ("qpb_last_error", "qpb_destroy"):
+            fn.restype = C.c_int
+    if lib.qpb_abi_version() != ABI_VERSION:
+        raise RuntimeError("libqpb.so ABI version does not match the Python binding; rebuild the library")
+    _lib = lib
+    return lib
+
+
+def _ptr(arr):
+    return None if arr is None else arr.ctypes.data_as(C.c_void_p)
+
+
+def _f64(a, shape=None):
+    out = np.ascontiguousarray(a, dtype=np.float64)
+    if shape is not None and out.shape != tuple(shape):
+        raise ValueError(f"expected array of shape {tuple(shape)}, got {out.shape}")
+    return out
+
+
+class Context:
+    """RAII wrapper of a qpb_ctx handle."""
+
+    def __init__(self, *, ny, nx, ne, nw, ncell, ngap=1, flags=0, dx=1.0, dE=1.0, device=0, diff_tol=0.0,
+                 pauli_floor=1e-18):
+        self.lib = load_library()
+        self.cfg = Config(ABI_VERSION, int(device), int(ny), int(nx), int(ne), int(nw), int(ncell), int(ngap),
+                          int(flags), 0, float(dx), float(dE), float(diff_tol), float(pauli_floor))
+        self.handle = C.c_void_p()
+        self._check(self.lib.qpb_create(C.byref(self.cfg), C.byref(self.handle)))
+        self.ne, self.nw, self.ncell, self.ny, self.nx = int(ne), int(nw), int(ncell), int(ny), int(nx)
+        self.flags = int(flags)
+
+    def _check(self, rc: int) -> None:
+        if rc != 0:
+            raise QpbError(rc, self.lib.qpb_last_error().decode("utf-8", "replace"))
+
+    def close(self) -> None:
+        if getattr(self, "handle", None) is not None and self.handle:
+            self.lib.qpb_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- uploads -------------------------------------------------------------------------------------
+    def upload_geometry(self, mask, bcx=None, bcy=None, source=None):
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        if m.shape != (self.ny, self.nx):
+            raise ValueError("mask shape does not match the context")
+        arrs = [None if a is None else _f64(a, (self.ny, self.nx)) for a in (bcx, bcy, source)]
+        self._check(self.lib.qpb_upload_geometry(self.handle, _ptr(m), *[_ptr(a) for a in arrs]))
+
+    def upload_diffusion(self, D):
+        shape = (self.ne, self.ncell) if self.flags & F_VARIABLE_D else (self.ne,)
+        d = _f64(D, shape)
+        self._check(self.lib.qpb_upload_diffusion(self.handle, _ptr(d)))
+
+    def prepare_diffusion(self, slot: int, dt: float):
+        self._check(self.lib.qpb_prepare_diffusion(self.handle, int(slot), float(dt)))
+
+    def upload_collision(self, K_r0, K_s0, rho, gap_id, idx_diff, idx_sum, sign):
+        ng, ne = self.cfg.ngap, self.ne
+        kr = None if K_r0 is None else _f64(K_r0).reshape(ng, ne, ne)
+        ks = None if K_s0 is None else _f64(K_s0).reshape(ng, ne, ne)
+        rh = _f64(rho).reshape(ng, ne)
+        gid = None if gap_id is None else np.ascontiguousarray(gap_id, dtype=np.int32).reshape(self.ncell)
+        idd = None if idx_diff is None else np.ascontiguousarray(idx_diff, dtype=np.int32).reshape(ne, ne)
+        ids = None if idx_sum is None else np.ascontiguousarray(idx_sum, dtype=np.int32).reshape(ne, ne)
+        sg = None if sign is None else np.ascontiguousarray(sign, dtype=np.int8).reshape(ne, ne)
+        self._check(self.lib.qpb_upload_collision(self.handle, _ptr(kr), _ptr(ks), _ptr(rh), _ptr(gid), _ptr(idd),
+                                                  _ptr(ids), _ptr(sg)))
+
+    # ---- state ---------------------------------------------------------------------------------------
+    def set_state(self, n, n_ph=None):
+        a = _f64(n, (self.ne, self.ncell))
+        p = None if (n_ph is None or self.nw == 0) else _f64(n_ph, (self.nw, self.ncell))
+        self._check(self.lib.qpb_set_state(self.handle, _ptr(a), _ptr(p)))
+
+    def get_state(self, want_phonons=True):
+        n = np.empty((self.ne, self.ncell))
+        p = np.empty((self.nw, self.ncell)) if (want_phonons and self.nw > 0) else None
+        self._check(self.lib.qpb_get_state(self.handle, _ptr(n), _ptr(p)))
+        return n, p
+
+    def get_integrated(self):
+        out = np.empty(self.ncell)
+        self._check(self.lib.qpb_get_integrated(self.handle, _ptr(out)))
+        return out
+
+    # ---- stepping ------------------------------------------------------------------------------------
+    def advance(self, nsteps, dt, slot=0, t_start=0.0, gen_mode=GEN_NONE, rate=0.0, pulse_start=0.0,
+                pulse_duration=0.0, gen_array=None, want_pauli=False):
+        g = Generation(int(gen_mode), 0, float(rate), float(pulse_start), float(pulse_duration), None)
+        keep = None
+        if gen_mode == GEN_ARRAY:
+            keep = _f64(gen_array, (self.ne, self.ncell))
+            g.array = keep.ctypes.data
+        recs = (PauliRec * max(1, int(nsteps)))() if want_pauli else None
+        rc = self.lib.qpb_advance(self.handle, int(nsteps), float(dt), int(slot), float(t_start), C.byref(g),
+                                  C.cast(recs, C.c_void_p) if recs is not None else None)
+        self._check(rc)
+        if recs is None:
+            return None
+        return [(recs[k].max_occ, recs[k].max_index, recs[k].forbidden) for k in range(int(nsteps))]
+
+    def collide(self, dt):
+        self._check(self.lib.qpb_collide(self.handle, float(dt)))
+
+    def diffuse(self, slot=0):
+        self._check(self.lib.qpb_diffuse(self.handle, int(slot)))
+
+    def pauli(self):
+        r = PauliRec()
+        self._check(self.lib.qpb_pauli(self.handle, C.byref(r)))
+        return r.max_occ, r.max_index, r.forbidden
+
+    def diag(self) -> dict:
+        d = Diag()
+        self._check(self.lib.qpb_get_diag(self.handle, C.byref(d)))
+        return {name: getattr(d, name) for name, _ in Diag._fields_}
+
+    def synchronize(self):
+        self._check(self.lib.qpb_synchronize(self.handle))
+
+    def enable_timers(self, on=True):
+        self._check(self.lib.qpb_enable_timers(self.handle, 1 if on else 0))
+
+    def reset_timers(self):
+        self._check(self.lib.qpb_reset_timers(self.handle))
+
+    def timer(self, which: int):
+        ms, n = C.c_double(), C.c_int64()
+        self._check(self.lib.qpb_get_timer(self.handle, int(which), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def device_ptr(self, which: int):
+        p, n = C.c_void_p(), C.c_int64()
+        self._check(self.lib.qpb_device_ptr(self.handle, int(which), C.byref(p), C.byref(n)))
+        return p.value, n.value

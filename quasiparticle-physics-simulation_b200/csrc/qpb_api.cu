@@ -1,0 +1,830 @@
+// C ABI of libqpb: context, uploads, the time-step loop.  See include/qpb.h for the contract.
+#include "qpb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <random>
+
+static thread_local std::string g_err;
+
+void qpb_set_error(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+extern "C" const char *qpb_last_error(void) { return g_err.c_str(); }
+extern "C" int qpb_abi_version(void) { return QPB_ABI_VERSION; }
+
+extern "C" int qpb_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        qpb_set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+        return QPB_E_NODEVICE;
+    }
+    int usable = 0;
+    for (int d = 0; d < n; ++d) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) usable++;
+    }
+    return usable;
+}
+
+template <class T>
+static int dev_alloc(T **p, size_t count) {
+    *p = nullptr;
+    if (count == 0) return QPB_OK;
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        qpb_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        return QPB_E_NOMEM;
+    }
+    return QPB_OK;
+}
+
+#define QPB_ALLOC(ptr, count)                              \
+    do {                                                   \
+        int _rc = dev_alloc(&(ptr), (size_t)(count));      \
+        if (_rc != QPB_OK) return _rc;                     \
+    } while (0)
+
+template <class T>
+static void dev_free(T *&p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+void qpbk_free_slot(DiffSlot &s) {
+    dev_free(s.d_a);
+    dev_free(s.d_shift);
+    dev_free(s.d_jlen);
+    dev_free(s.d_ex);
+    dev_free(s.d_ey);
+    dev_free(s.d_gbx);
+    dev_free(s.d_gby);
+    dev_free(s.d_src);
+    dev_free(s.fx.d_cls);
+    dev_free(s.fx.d_tab);
+    dev_free(s.fy.d_cls);
+    dev_free(s.fy.d_tab);
+    s.ready = false;
+    s.fast = false;
+}
+
+extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
+    if (!cfg || !out) {
+        qpb_set_error("qpb_create: null argument");
+        return QPB_E_INVALID;
+    }
+    *out = nullptr;
+    if (cfg->abi_version != QPB_ABI_VERSION) {
+        qpb_set_error("qpb_create: ABI version mismatch (caller %d, library %d)", cfg->abi_version, QPB_ABI_VERSION);
+        return QPB_E_INVALID;
+    }
+    if (cfg->ny <= 0 || cfg->nx <= 0 || cfg->ne <= 0 || cfg->ncell <= 0 || cfg->ncell > (int64_t)cfg->ny * cfg->nx ||
+        cfg->nw < 0 || cfg->ngap < 1 || !(cfg->dx > 0.0)) {
+        qpb_set_error("qpb_create: invalid dimensions ny=%d nx=%d ne=%d nw=%d ncell=%d ngap=%d dx=%g", cfg->ny, cfg->nx,
+                      cfg->ne, cfg->nw, cfg->ncell, cfg->ngap, cfg->dx);
+        return QPB_E_INVALID;
+    }
+    if ((int64_t)cfg->ny * cfg->nx >= (int64_t)1 << 31) {
+        qpb_set_error("qpb_create: grid too large for 32-bit cell indices");
+        return QPB_E_INVALID;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        qpb_set_error("qpb_create: no CUDA device is visible; this library has no CPU fallback");
+        return QPB_E_NODEVICE;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) {
+        qpb_set_error("qpb_create: device %d out of range (0..%d)", cfg->device, ndev - 1);
+        return QPB_E_NODEVICE;
+    }
+    cudaDeviceProp prop;
+    QPB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) {
+        qpb_set_error("qpb_create: device %d is sm_%d%d; libqpb is built for sm_100a only", cfg->device, prop.major,
+                      prop.minor);
+        return QPB_E_NODEVICE;
+    }
+    QPB_CUDA(cudaSetDevice(cfg->device));
+    qpb_ctx *c = new qpb_ctx();
+    c->cfg = *cfg;
+    if (!(c->cfg.diff_tol > 0.0)) c->cfg.diff_tol = 1e-12;
+    c->ncd = cfg->ny * cfg->nx;
+    c->maxit = 512;
+    auto fail = [&](int rc) {
+        qpb_destroy(c);
+        return rc;
+    };
+#define TRY(x)                          \
+    do {                                \
+        int _r = (x);                   \
+        if (_r != QPB_OK) return fail(_r); \
+    } while (0)
+#define TRYCUDA(expr)                                                                                  \
+    do {                                                                                               \
+        cudaError_t _e = (expr);                                                                       \
+        if (_e != cudaSuccess) {                                                                       \
+            qpb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, __LINE__,     \
+                          cudaGetErrorString(_e));                                                     \
+            return fail(QPB_E_CUDA);                                                                   \
+        }                                                                                              \
+    } while (0)
+    TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaEventCreate(&c->ev0));
+    TRYCUDA(cudaEventCreate(&c->ev1));
+    const size_t nstate = (size_t)cfg->ne * c->ncd;
+    TRY(dev_alloc(&c->d_S, nstate));
+    TRYCUDA(cudaMemsetAsync(c->d_S, 0, nstate * sizeof(double), c->stream));
+    TRY(dev_alloc(&c->d_flags, (size_t)c->ncd));
+    TRY(dev_alloc(&c->d_cell2dense, (size_t)cfg->ncell));
+    TRY(dev_alloc(&c->d_integrated, (size_t)cfg->ncell));
+    // T1 doubles as the staging buffer for state upload/download even when diffusion is off
+    TRY(dev_alloc(&c->d_T1, nstate));
+    if (cfg->flags & QPB_F_DIFFUSION) {
+        TRY(dev_alloc(&c->d_B, nstate));
+        TRY(dev_alloc(&c->d_T2, nstate));
+        TRY(dev_alloc(&c->d_bcx, (size_t)c->ncd));
+        TRY(dev_alloc(&c->d_bcy, (size_t)c->ncd));
+        TRY(dev_alloc(&c->d_srcgeom, (size_t)c->ncd));
+        TRY(dev_alloc(&c->d_res, (size_t)c->maxit * cfg->ne));
+        TRY(dev_alloc(&c->d_unorm, (size_t)c->maxit * cfg->ne));
+        TRY(dev_alloc(&c->d_done, 2 * (size_t)cfg->ne));
+        if (cfg->flags & QPB_F_VARIABLE_D) TRY(dev_alloc(&c->d_Dcell, nstate));
+    }
+    if (cfg->nw > 0) {
+        TRY(dev_alloc(&c->d_P, (size_t)cfg->nw * cfg->ncell));
+        TRYCUDA(cudaMemsetAsync(c->d_P, 0, (size_t)cfg->nw * cfg->ncell * sizeof(double), c->stream));
+    }
+    c->pauli_cap = 1024;
+    TRY(dev_alloc(&c->d_pauli, (size_t)c->pauli_cap));
+    TRYCUDA(cudaStreamSynchronize(c->stream));
+#undef TRY
+#undef TRYCUDA
+    *out = c;
+    return QPB_OK;
+}
+
+extern "C" void qpb_destroy(qpb_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    qpbk_free_slot(c->slot[0]);
+    qpbk_free_slot(c->slot[1]);
+    dev_free(c->d_flags); dev_free(c->d_bcx); dev_free(c->d_bcy); dev_free(c->d_srcgeom);
+    dev_free(c->d_cell2dense); dev_free(c->d_Dcell); dev_free(c->d_S); dev_free(c->d_B);
+    dev_free(c->d_T1); dev_free(c->d_T2); dev_free(c->d_res); dev_free(c->d_unorm); dev_free(c->d_done);
+    dev_free(c->d_Kr); dev_free(c->d_Ks); dev_free(c->d_KrT); dev_free(c->d_KsT); dev_free(c->d_rho);
+    dev_free(c->d_gapid); dev_free(c->d_idxd); dev_free(c->d_idxs); dev_free(c->d_idxdT);
+    dev_free(c->d_sign); dev_free(c->d_signT); dev_free(c->d_dmap); dev_free(c->d_smap);
+    dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_scratch); dev_free(c->d_gen);
+    dev_free(c->d_integrated); dev_free(c->d_pauli);
+    if (c->d_pauli_part) cudaFree(c->d_pauli_part);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+#define QPB_ENTER(c)                                   \
+    do {                                               \
+        if (!(c)) {                                    \
+            qpb_set_error("null context");             \
+            return QPB_E_INVALID;                      \
+        }                                              \
+        QPB_CUDA(cudaSetDevice((c)->cfg.device));      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qpb_upload_geometry(qpb_ctx *c, const uint8_t *mask, const double *bcx, const double *bcy,
+                                   const double *source) {
+    QPB_ENTER(c);
+    const int ny = c->cfg.ny, nx = c->cfg.nx, ncd = c->ncd;
+    if (!mask) {
+        qpb_set_error("qpb_upload_geometry: mask is null");
+        return QPB_E_INVALID;
+    }
+    c->h_flags.assign(ncd, 0);
+    c->h_cell2dense.clear();
+    c->h_cell2dense.reserve(c->cfg.ncell);
+    bool anyx = false, anyy = false;
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) {
+            const int p = y * nx + x;
+            if (!mask[p]) continue;
+            unsigned f = QPB_IN;
+            if (x > 0 && mask[p - 1]) f |= QPB_LK_L;
+            if (x + 1 < nx && mask[p + 1]) f |= QPB_LK_R;
+            if (y > 0 && mask[p - nx]) f |= QPB_LK_U;
+            if (y + 1 < ny && mask[p + nx]) f |= QPB_LK_D;
+            if (f & (QPB_LK_L | QPB_LK_R)) anyx = true;
+            if (f & (QPB_LK_U | QPB_LK_D)) anyy = true;
+            c->h_flags[p] = (uint8_t)f;
+            c->h_cell2dense.push_back(p);
+        }
+    if ((int)c->h_cell2dense.size() != c->cfg.ncell) {
+        qpb_set_error("qpb_upload_geometry: mask has %zu cells, config says %d", c->h_cell2dense.size(), c->cfg.ncell);
+        return QPB_E_INVALID;
+    }
+    c->thin_x = !anyy;  // no vertical links: every row is an independent 1-D problem along x
+    c->thin_y = !anyx;
+    QPB_CUDA(cudaMemcpyAsync(c->d_flags, c->h_flags.data(), ncd, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaMemcpyAsync(c->d_cell2dense, c->h_cell2dense.data(), sizeof(int32_t) * c->cfg.ncell,
+                             cudaMemcpyHostToDevice, c->stream));
+    if (c->cfg.flags & QPB_F_DIFFUSION) {
+        if (!bcx || !bcy || !source) {
+            qpb_set_error("qpb_upload_geometry: boundary arrays are required when diffusion is enabled");
+            return QPB_E_INVALID;
+        }
+        c->h_bcx.assign(bcx, bcx + ncd);
+        c->h_bcy.assign(bcy, bcy + ncd);
+        c->h_src.assign(source, source + ncd);
+        QPB_CUDA(cudaMemcpyAsync(c->d_bcx, bcx, sizeof(double) * ncd, cudaMemcpyHostToDevice, c->stream));
+        QPB_CUDA(cudaMemcpyAsync(c->d_bcy, bcy, sizeof(double) * ncd, cudaMemcpyHostToDevice, c->stream));
+        QPB_CUDA(cudaMemcpyAsync(c->d_srcgeom, source, sizeof(double) * ncd, cudaMemcpyHostToDevice, c->stream));
+        // Gershgorin bounds and a commutator probe of Gx, Gy (unit coefficient)
+        double gx = 0.0, gy = 0.0;
+        for (int p = 0; p < ncd; ++p) {
+            const unsigned f = c->h_flags[p];
+            if (!(f & QPB_IN)) continue;
+            const int dxl = ((f & QPB_LK_L) ? 1 : 0) + ((f & QPB_LK_R) ? 1 : 0);
+            const int dyl = ((f & QPB_LK_U) ? 1 : 0) + ((f & QPB_LK_D) ? 1 : 0);
+            gx = std::max(gx, 2.0 * dxl + std::fabs(bcx[p]));
+            gy = std::max(gy, 2.0 * dyl + std::fabs(bcy[p]));
+        }
+        c->gmax_x = gx;
+        c->gmax_y = gy;
+        std::mt19937_64 rng(12345);
+        std::uniform_real_distribution<double> U(0.5, 1.5);
+        std::vector<double> r(ncd, 0.0), t1(ncd), t2(ncd), t3(ncd), t4(ncd);
+        for (int p = 0; p < ncd; ++p)
+            if (c->h_flags[p] & QPB_IN) r[p] = U(rng);
+        auto apply = [&](const std::vector<double> &in, std::vector<double> &o, bool xdir) {
+            for (int p = 0; p < ncd; ++p) {
+                const unsigned f = c->h_flags[p];
+                double v = 0.0;
+                if (f & QPB_IN) {
+                    if (xdir) {
+                        v = bcx[p] * in[p];
+                        if (f & QPB_LK_L) v += in[p] - in[p - 1];
+                        if (f & QPB_LK_R) v += in[p] - in[p + 1];
+                    } else {
+                        v = bcy[p] * in[p];
+                        if (f & QPB_LK_U) v += in[p] - in[p - nx];
+                        if (f & QPB_LK_D) v += in[p] - in[p + nx];
+                    }
+                }
+                o[p] = v;
+            }
+        };
+        apply(r, t1, true);
+        apply(t1, t2, false);  // Gy Gx r
+        apply(r, t3, false);
+        apply(t3, t4, true);   // Gx Gy r
+        double dmax = 0.0, vmax = 0.0;
+        for (int p = 0; p < ncd; ++p) {
+            dmax = std::max(dmax, std::fabs(t2[p] - t4[p]));
+            vmax = std::max(vmax, std::max(std::fabs(t2[p]), std::fabs(t4[p])));
+        }
+        c->commuting = dmax <= 1e-12 * std::max(vmax, 1.0);
+    }
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_geom = true;
+    qpbk_free_slot(c->slot[0]);
+    qpbk_free_slot(c->slot[1]);
+    return QPB_OK;
+}
+
+extern "C" int qpb_upload_diffusion(qpb_ctx *c, const double *D) {
+    QPB_ENTER(c);
+    if (!(c->cfg.flags & QPB_F_DIFFUSION) || !D) {
+        qpb_set_error("qpb_upload_diffusion: diffusion is disabled on this context or D is null");
+        return QPB_E_INVALID;
+    }
+    const bool vard = c->cfg.flags & QPB_F_VARIABLE_D;
+    const size_t n = vard ? (size_t)c->cfg.ne * c->cfg.ncell : (size_t)c->cfg.ne;
+    c->h_D.assign(D, D + n);
+    for (size_t i = 0; i < n; ++i)
+        if (!(c->h_D[i] >= 0.0) || !std::isfinite(c->h_D[i])) {
+            qpb_set_error("qpb_upload_diffusion: D must be finite and non-negative");
+            return QPB_E_INVALID;
+        }
+    c->have_D = true;
+    qpbk_free_slot(c->slot[0]);
+    qpbk_free_slot(c->slot[1]);
+    return QPB_OK;
+}
+
+// ---- shift parameters -----------------------------------------------------------------------------------
+// Jacobi dn(u|m) and K(m) by the arithmetic-geometric mean (Abramowitz & Stegun 16.4, 17.6).
+static void agm_dn(double m, const std::vector<double> &frac, std::vector<double> &dn_out) {
+    double a[32], cc[32];
+    a[0] = 1.0;
+    double b = std::sqrt(std::max(1.0 - m, 0.0));
+    cc[0] = std::sqrt(m);
+    int N = 0;
+    while (N < 30 && std::fabs(cc[N]) > 1e-16 * a[N]) {
+        const double an = 0.5 * (a[N] + b);
+        cc[N + 1] = 0.5 * (a[N] - b);
+        b = std::sqrt(a[N] * b);
+        a[N + 1] = an;
+        ++N;
+    }
+    const double K = M_PI / (2.0 * a[N]);
+    dn_out.resize(frac.size());
+    for (size_t i = 0; i < frac.size(); ++i) {
+        const double u = frac[i] * K;
+        double phi = std::ldexp(a[N] * u, N);
+        double phi_prev = phi;
+        for (int n = N; n >= 1; --n) {
+            phi_prev = phi;
+            phi = 0.5 * (phi + std::asin(cc[n] / a[n] * std::sin(phi)));
+        }
+        const double den = std::cos(phi_prev - phi);
+        dn_out[i] = (N == 0 || std::fabs(den) < 1e-300) ? 1.0 : std::cos(phi) / den;
+    }
+}
+
+// Optimal J-parameter ADI shifts on [lo,hi] (Wachspress): r_j = hi * dn((2j-1)K/(2J), 1-(lo/hi)^2).
+static std::vector<double> wachspress(double lo, double hi, int J) {
+    std::vector<double> out(J);
+    if (hi <= lo * (1.0 + 1e-12)) {
+        std::fill(out.begin(), out.end(), std::sqrt(lo * hi));
+        return out;
+    }
+    const double kp = lo / hi;
+    std::vector<double> frac(J), dn;
+    for (int j = 0; j < J; ++j) frac[j] = (2.0 * j + 1.0) / (2.0 * J);
+    agm_dn(1.0 - kp * kp, frac, dn);
+    for (int j = 0; j < J; ++j) out[j] = std::min(hi, std::max(lo, hi * dn[j]));
+    return out;
+}
+
+static double adi_bound(double lo, double hi, const std::vector<double> &sh) {
+    const int NP = 600;
+    double worst = 0.0;
+    for (int i = 0; i <= NP; ++i) {
+        const double h = lo * std::pow(hi / lo, (double)i / NP);
+        double f = 1.0;
+        for (double r : sh) f *= std::fabs((r - h) / (r + h));
+        worst = std::max(worst, f);
+    }
+    return worst * worst;
+}
+
+static std::vector<double> plan_shifts(double lo, double hi, double target, int jcap) {
+    if (hi <= lo * (1.0 + 1e-9)) return {std::sqrt(lo * hi)};
+    int J = (int)std::ceil(std::log(4.0 / target) * std::log(4.0 * hi / lo) / (M_PI * M_PI));
+    J = std::max(1, std::min(J, jcap));
+    while (J > 1 && adi_bound(lo, hi, wachspress(lo, hi, J - 1)) <= target) --J;
+    while (J < jcap && adi_bound(lo, hi, wachspress(lo, hi, J)) > target) ++J;
+    return wachspress(lo, hi, J);
+}
+
+extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
+    QPB_ENTER(c);
+    if (slot < 0 || slot > 1 || !(dt > 0.0)) {
+        qpb_set_error("qpb_prepare_diffusion: bad slot %d or dt %g", slot, dt);
+        return QPB_E_INVALID;
+    }
+    if (!(c->cfg.flags & QPB_F_DIFFUSION) || !c->have_geom || !c->have_D) {
+        qpb_set_error("qpb_prepare_diffusion: geometry and diffusion coefficients must be uploaded first");
+        return QPB_E_INVALID;
+    }
+    DiffSlot &s = c->slot[slot];
+    qpbk_free_slot(s);
+    const auto &cf = c->cfg;
+    const int ne = cf.ne, ncd = c->ncd, nx = cf.nx;
+    const bool vard = cf.flags & QPB_F_VARIABLE_D;
+    const double inv_dx = 1.0 / cf.dx, inv_dx2 = inv_dx * inv_dx;
+    s.dt = dt;
+    s.mode = c->thin_x ? 1 : (c->thin_y ? 2 : 0);
+    s.commuting = c->commuting && !vard;
+    s.a_bin.assign(ne, 0.0);
+    std::vector<double> hi_bin(ne, 0.5);
+    std::vector<double> srccoef(ne, 0.0);
+    if (!vard) {
+        for (int i = 0; i < ne; ++i) {
+            const double a = 0.5 * dt * c->h_D[i] * inv_dx2;
+            s.a_bin[i] = a;
+            hi_bin[i] = 0.5 + a * std::max(c->gmax_x, c->gmax_y);
+            srccoef[i] = dt * c->h_D[i];
+        }
+        QPB_ALLOC(s.d_src, ne);
+        QPB_CUDA(cudaMemcpyAsync(s.d_src, srccoef.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        // dense per-bin coefficient fields (solver.py:275-318): harmonic-mean faces, D-scaled boundary terms
+        const size_t nst = (size_t)ne * ncd;
+        std::vector<double> ex(nst, 0.0), ey(nst, 0.0), gbx(nst, 0.0), gby(nst, 0.0), src(nst, 0.0), Dd((size_t)ncd);
+        for (int i = 0; i < ne; ++i) {
+            std::fill(Dd.begin(), Dd.end(), 0.0);
+            for (int q = 0; q < cf.ncell; ++q) Dd[c->h_cell2dense[q]] = c->h_D[(size_t)i * cf.ncell + q];
+            double hx = 0.0, hy = 0.0;
+            const size_t o = (size_t)i * ncd;
+            for (int p = 0; p < ncd; ++p) {
+                const unsigned f = c->h_flags[p];
+                if (!(f & QPB_IN)) continue;
+                const double Dp = Dd[p];
+                if (f & QPB_LK_L) {
+                    const double Dq = Dd[p - 1];
+                    ex[o + p] = 0.5 * dt * (2.0 * Dp * Dq / std::max(Dp + Dq, 1e-30) * inv_dx2);
+                }
+                if (f & QPB_LK_U) {
+                    const double Dq = Dd[p - nx];
+                    ey[o + p] = 0.5 * dt * (2.0 * Dp * Dq / std::max(Dp + Dq, 1e-30) * inv_dx2);
+                }
+                gbx[o + p] = 0.5 * dt * (Dp * c->h_bcx[p] * inv_dx2);
+                gby[o + p] = 0.5 * dt * (Dp * c->h_bcy[p] * inv_dx2);
+                src[o + p] = dt * (Dp * c->h_src[p]);
+            }
+            for (int p = 0; p < ncd; ++p) {
+                const unsigned f = c->h_flags[p];
+                if (!(f & QPB_IN)) continue;
+                const double eL = ex[o + p], eR = (f & QPB_LK_R) ? ex[o + p + 1] : 0.0;
+                const double eU = ey[o + p], eD = (f & QPB_LK_D) ? ey[o + p + nx] : 0.0;
+                hx = std::max(hx, 2.0 * (eL + eR) + std::fabs(gbx[o + p]));
+                hy = std::max(hy, 2.0 * (eU + eD) + std::fabs(gby[o + p]));
+            }
+            hi_bin[i] = 0.5 + std::max(hx, hy);
+        }
+        QPB_ALLOC(s.d_ex, nst);
+        QPB_ALLOC(s.d_ey, nst);
+        QPB_ALLOC(s.d_gbx, nst);
+        QPB_ALLOC(s.d_gby, nst);
+        QPB_ALLOC(s.d_src, nst);
+        QPB_CUDA(cudaMemcpy(s.d_ex, ex.data(), sizeof(double) * nst, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(s.d_ey, ey.data(), sizeof(double) * nst, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(s.d_gbx, gbx.data(), sizeof(double) * nst, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(s.d_gby, gby.data(), sizeof(double) * nst, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(s.d_src, src.data(), sizeof(double) * nst, cudaMemcpyHostToDevice));
+    }
+    // shift tables
+    std::vector<std::vector<double>> sh(ne);
+    s.jlen.assign(ne, 1);
+    int jmax = 1;
+    const double target = std::min(1e-2, std::max(cf.diff_tol * 0.1, 1e-15));
+    for (int i = 0; i < ne; ++i) {
+        const double lo = 0.5, hi = std::max(hi_bin[i], 0.5);
+        if (s.mode != 0) sh[i] = {0.0};
+        else if (s.commuting) sh[i] = plan_shifts(lo, hi, target, 48);
+        else {
+            const int J = 4;  // cyclic geometric set (box D)
+            sh[i].resize(J);
+            for (int k = 1; k <= J; ++k) sh[i][k - 1] = hi * std::pow(lo / hi, (2.0 * k - 1.0) / (2.0 * J));
+        }
+        s.jlen[i] = (int)sh[i].size();
+        jmax = std::max(jmax, s.jlen[i]);
+    }
+    s.jmax = jmax;
+    std::vector<double> flat((size_t)ne * jmax, 0.5);
+    for (int i = 0; i < ne; ++i)
+        for (int k = 0; k < s.jlen[i]; ++k) flat[(size_t)i * jmax + k] = sh[i][k];
+    QPB_ALLOC(s.d_a, ne);
+    QPB_ALLOC(s.d_shift, (size_t)ne * jmax);
+    QPB_ALLOC(s.d_jlen, ne);
+    QPB_CUDA(cudaMemcpyAsync(s.d_a, s.a_bin.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaMemcpyAsync(s.d_shift, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaMemcpyAsync(s.d_jlen, s.jlen.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    s.launch_iters = s.commuting ? std::min(jmax, 16) : 8;
+    s.ready = true;
+    s.fast = false;
+    if (!vard) {
+        int rc = qpbk_prepare_fast(c, s);
+        if (rc != QPB_OK) return rc;
+    }
+    c->diag.direct_mode = s.mode != 0;
+    c->diag.commuting = s.commuting;
+    return QPB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qpb_upload_collision(qpb_ctx *c, const double *K_r0, const double *K_s0, const double *rho,
+                                    const int32_t *gap_id, const int32_t *idx_diff, const int32_t *idx_sum,
+                                    const int8_t *sign) {
+    QPB_ENTER(c);
+    const auto &cf = c->cfg;
+    const int ne = cf.ne, ng = cf.ngap;
+    if (!rho) {
+        qpb_set_error("qpb_upload_collision: rho is required");
+        return QPB_E_INVALID;
+    }
+    const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
+    if ((scat || rec) && (cf.nw <= 0 || !idx_diff || !idx_sum || !sign)) {
+        qpb_set_error("qpb_upload_collision: phonon index maps are required when collisions are enabled");
+        return QPB_E_INVALID;
+    }
+    if ((scat && !K_s0) || (rec && !K_r0)) {
+        qpb_set_error("qpb_upload_collision: kernel matrix missing for an enabled process");
+        return QPB_E_INVALID;
+    }
+    const size_t nk = (size_t)ng * ne * ne;
+    auto up_mat = [&](const double *src, double *&d, double *&dT) -> int {
+        if (!src) return QPB_OK;
+        std::vector<double> T(nk);
+        for (int g = 0; g < ng; ++g)
+            for (int i = 0; i < ne; ++i)
+                for (int j = 0; j < ne; ++j)
+                    T[((size_t)g * ne + j) * ne + i] = src[((size_t)g * ne + i) * ne + j];
+        dev_free(d);
+        dev_free(dT);
+        QPB_ALLOC(d, nk);
+        QPB_ALLOC(dT, nk);
+        QPB_CUDA(cudaMemcpy(d, src, sizeof(double) * nk, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(dT, T.data(), sizeof(double) * nk, cudaMemcpyHostToDevice));
+        return QPB_OK;
+    };
+    int rc;
+    if ((rc = up_mat(rec ? K_r0 : nullptr, c->d_Kr, c->d_KrT)) != QPB_OK) return rc;
+    if ((rc = up_mat(scat ? K_s0 : nullptr, c->d_Ks, c->d_KsT)) != QPB_OK) return rc;
+    dev_free(c->d_rho);
+    QPB_ALLOC(c->d_rho, (size_t)ng * ne);
+    QPB_CUDA(cudaMemcpy(c->d_rho, rho, sizeof(double) * ng * ne, cudaMemcpyHostToDevice));
+    dev_free(c->d_gapid);
+    if (gap_id && ng > 1) {
+        for (int q = 0; q < cf.ncell; ++q)
+            if (gap_id[q] < 0 || gap_id[q] >= ng) {
+                qpb_set_error("qpb_upload_collision: gap_id[%d]=%d out of range", q, gap_id[q]);
+                return QPB_E_INVALID;
+            }
+        QPB_ALLOC(c->d_gapid, cf.ncell);
+        QPB_CUDA(cudaMemcpy(c->d_gapid, gap_id, sizeof(int32_t) * cf.ncell, cudaMemcpyHostToDevice));
+    }
+    c->structured = false;
+    if (scat || rec) {
+        const size_t nn = (size_t)ne * ne;
+        for (size_t k = 0; k < nn; ++k)
+            if (idx_diff[k] < 0 || idx_diff[k] >= cf.nw || idx_sum[k] < 0 || idx_sum[k] >= cf.nw) {
+                qpb_set_error("qpb_upload_collision: phonon index out of range at pair %zu", k);
+                return QPB_E_INVALID;
+            }
+        std::vector<int32_t> idT(nn);
+        std::vector<int8_t> sgT(nn);
+        for (int i = 0; i < ne; ++i)
+            for (int j = 0; j < ne; ++j) {
+                idT[(size_t)j * ne + i] = idx_diff[(size_t)i * ne + j];
+                sgT[(size_t)j * ne + i] = sign[(size_t)i * ne + j];
+            }
+        dev_free(c->d_idxd); dev_free(c->d_idxs); dev_free(c->d_idxdT); dev_free(c->d_sign); dev_free(c->d_signT);
+        QPB_ALLOC(c->d_idxd, nn);
+        QPB_ALLOC(c->d_idxs, nn);
+        QPB_ALLOC(c->d_idxdT, nn);
+        QPB_ALLOC(c->d_sign, nn);
+        QPB_ALLOC(c->d_signT, nn);
+        QPB_CUDA(cudaMemcpy(c->d_idxd, idx_diff, sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(c->d_idxs, idx_sum, sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(c->d_idxdT, idT.data(), sizeof(int32_t) * nn, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(c->d_sign, sign, sizeof(int8_t) * nn, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(c->d_signT, sgT.data(), sizeof(int8_t) * nn, cudaMemcpyHostToDevice));
+        // Structure probe: idx_diff depends on |i-j| only, idx_sum on i+j only, both injective, sign = sign(i-j),
+        // kernels symmetric, idx_sum symmetric.  True for every uniform energy grid the solver builds.
+        bool ok = true;
+        std::vector<int32_t> dmap(ne, -1), smap(2 * ne - 1, -1);
+        for (int i = 0; i < ne && ok; ++i)
+            for (int j = 0; j < ne && ok; ++j) {
+                const int k = std::abs(i - j), m = i + j;
+                const int32_t d = idx_diff[(size_t)i * ne + j], sidx = idx_sum[(size_t)i * ne + j];
+                if (dmap[k] < 0) dmap[k] = d; else if (dmap[k] != d) ok = false;
+                if (smap[m] < 0) smap[m] = sidx; else if (smap[m] != sidx) ok = false;
+                const int sg = (i > j) - (i < j);
+                if (sign[(size_t)i * ne + j] != sg) ok = false;
+            }
+        std::vector<int32_t> kof(cf.nw, -1), mof(cf.nw, -1);
+        for (int k = 0; k < ne && ok; ++k) {
+            if (kof[dmap[k]] >= 0) ok = false;
+            kof[dmap[k]] = k;
+        }
+        for (int m = 0; m < 2 * ne - 1 && ok; ++m) {
+            if (mof[smap[m]] >= 0) ok = false;
+            mof[smap[m]] = m;
+        }
+        auto symmetric = [&](const double *K) {
+            if (!K) return true;
+            for (int g = 0; g < ng; ++g)
+                for (int i = 0; i < ne; ++i)
+                    for (int j = 0; j < i; ++j)
+                        if (K[((size_t)g * ne + i) * ne + j] != K[((size_t)g * ne + j) * ne + i]) return false;
+            return true;
+        };
+        ok = ok && symmetric(scat ? K_s0 : nullptr) && symmetric(rec ? K_r0 : nullptr);
+        if (ok && scat)
+            for (int g = 0; g < ng && ok; ++g)
+                for (int i = 0; i < ne; ++i)
+                    if (K_s0[((size_t)g * ne + i) * ne + i] != 0.0) ok = false;
+        dev_free(c->d_dmap); dev_free(c->d_smap); dev_free(c->d_kof); dev_free(c->d_mof);
+        if (ok) {
+            QPB_ALLOC(c->d_dmap, ne);
+            QPB_ALLOC(c->d_smap, 2 * ne - 1);
+            QPB_ALLOC(c->d_kof, cf.nw);
+            QPB_ALLOC(c->d_mof, cf.nw);
+            QPB_CUDA(cudaMemcpy(c->d_dmap, dmap.data(), sizeof(int32_t) * ne, cudaMemcpyHostToDevice));
+            QPB_CUDA(cudaMemcpy(c->d_smap, smap.data(), sizeof(int32_t) * (2 * ne - 1), cudaMemcpyHostToDevice));
+            QPB_CUDA(cudaMemcpy(c->d_kof, kof.data(), sizeof(int32_t) * cf.nw, cudaMemcpyHostToDevice));
+            QPB_CUDA(cudaMemcpy(c->d_mof, mof.data(), sizeof(int32_t) * cf.nw, cudaMemcpyHostToDevice));
+            c->structured = true;
+        }
+    }
+    c->have_coll = true;
+    return qpbk_collision_setup(c);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+extern "C" int qpb_set_state(qpb_ctx *c, const double *n, const double *n_ph) {
+    QPB_ENTER(c);
+    if (!c->have_geom || !n) {
+        qpb_set_error("qpb_set_state: upload the geometry first and pass a state");
+        return QPB_E_INVALID;
+    }
+    const auto &cf = c->cfg;
+    QPB_CUDA(cudaMemcpyAsync(c->d_T1, n, sizeof(double) * (size_t)cf.ne * cf.ncell, cudaMemcpyHostToDevice, c->stream));
+    int rc = qpbk_scatter_state(c, c->d_T1);
+    if (rc != QPB_OK) return rc;
+    if (cf.nw > 0 && n_ph)
+        QPB_CUDA(cudaMemcpyAsync(c->d_P, n_ph, sizeof(double) * (size_t)cf.nw * cf.ncell, cudaMemcpyHostToDevice,
+                                 c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_get_state(qpb_ctx *c, double *n, double *n_ph) {
+    QPB_ENTER(c);
+    const auto &cf = c->cfg;
+    if (n) {
+        int rc = qpbk_gather_state(c, c->d_T1);
+        if (rc != QPB_OK) return rc;
+        QPB_CUDA(cudaMemcpyAsync(n, c->d_T1, sizeof(double) * (size_t)cf.ne * cf.ncell, cudaMemcpyDeviceToHost,
+                                 c->stream));
+    }
+    if (n_ph && cf.nw > 0)
+        QPB_CUDA(cudaMemcpyAsync(n_ph, c->d_P, sizeof(double) * (size_t)cf.nw * cf.ncell, cudaMemcpyDeviceToHost,
+                                 c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_get_integrated(qpb_ctx *c, double *out) {
+    QPB_ENTER(c);
+    if (!out) {
+        qpb_set_error("qpb_get_integrated: null output");
+        return QPB_E_INVALID;
+    }
+    int rc = qpbk_integrate(c);
+    if (rc != QPB_OK) return rc;
+    QPB_CUDA(cudaMemcpyAsync(out, c->d_integrated, sizeof(double) * c->cfg.ncell, cudaMemcpyDeviceToHost, c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_collide(qpb_ctx *c, double dt) {
+    QPB_ENTER(c);
+    if (!c->have_coll) {
+        qpb_set_error("qpb_collide: collision tables were not uploaded");
+        return QPB_E_INVALID;
+    }
+    if (!(dt > 0.0)) return QPB_OK;  // solver.py:1385
+    return qpbk_collide(c, dt);
+}
+
+extern "C" int qpb_diffuse(qpb_ctx *c, int32_t slot) {
+    QPB_ENTER(c);
+    if (slot < 0 || slot > 1 || !c->slot[slot].ready) {
+        qpb_set_error("qpb_diffuse: slot %d was not prepared", slot);
+        return QPB_E_INVALID;
+    }
+    return qpbk_diffuse(c, c->slot[slot]);
+}
+
+extern "C" int qpb_pauli(qpb_ctx *c, qpb_pauli_rec *out) {
+    QPB_ENTER(c);
+    if (!c->d_rho || !out) {
+        qpb_set_error("qpb_pauli: density of states not uploaded or null output");
+        return QPB_E_INVALID;
+    }
+    int rc = qpbk_pauli(c, c->d_pauli);
+    if (rc != QPB_OK) return rc;
+    QPB_CUDA(cudaMemcpyAsync(out, c->d_pauli, sizeof(qpb_pauli_rec), cudaMemcpyDeviceToHost, c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, double t_start,
+                           const qpb_generation *gen, qpb_pauli_rec *pauli_out) {
+    QPB_ENTER(c);
+    const auto &cf = c->cfg;
+    if (nsteps < 0 || !(dt > 0.0)) {
+        qpb_set_error("qpb_advance: bad nsteps %d or dt %g", nsteps, dt);
+        return QPB_E_INVALID;
+    }
+    const bool diff = cf.flags & QPB_F_DIFFUSION;
+    const bool coll = cf.flags & (QPB_F_SCATTERING | QPB_F_RECOMBINATION);
+    const bool pauli = (cf.flags & QPB_F_PAULI) && c->d_rho;
+    if (diff && (slot < 0 || slot > 1 || !c->slot[slot].ready)) {
+        qpb_set_error("qpb_advance: diffusion slot %d was not prepared", slot);
+        return QPB_E_INVALID;
+    }
+    if (coll && !c->have_coll) {
+        qpb_set_error("qpb_advance: collision tables were not uploaded");
+        return QPB_E_INVALID;
+    }
+    const int gmode = gen ? gen->mode : QPB_GEN_NONE;
+    if (gmode == QPB_GEN_ARRAY) {
+        if (nsteps > 1 || !gen->array) {
+            qpb_set_error("qpb_advance: array generation needs nsteps == 1 and a non-null array");
+            return QPB_E_INVALID;
+        }
+        const size_t n = (size_t)cf.ne * cf.ncell;
+        if (!c->d_gen) QPB_ALLOC(c->d_gen, n);
+        QPB_CUDA(cudaMemcpyAsync(c->d_gen, gen->array, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (pauli && nsteps > c->pauli_cap) {
+        dev_free(c->d_pauli);
+        c->pauli_cap = nsteps;
+        QPB_ALLOC(c->d_pauli, (size_t)c->pauli_cap);
+    }
+    double t = t_start;
+    int rc;
+    for (int s = 0; s < nsteps; ++s) {
+        if (gmode == QPB_GEN_CONSTANT) {
+            if ((rc = qpbk_add_generation(c, dt, gen->rate, nullptr)) != QPB_OK) return rc;
+        } else if (gmode == QPB_GEN_PULSE) {
+            if (gen->pulse_start <= t && t < gen->pulse_start + gen->pulse_duration)  // solver.py:914
+                if ((rc = qpbk_add_generation(c, dt, gen->rate, nullptr)) != QPB_OK) return rc;
+        } else if (gmode == QPB_GEN_ARRAY) {
+            if ((rc = qpbk_add_generation(c, dt, 0.0, c->d_gen)) != QPB_OK) return rc;
+        }
+        if (coll && diff) {  // solver.py:1469-1472
+            if ((rc = qpbk_collide(c, 0.5 * dt)) != QPB_OK) return rc;
+            if ((rc = qpbk_diffuse(c, c->slot[slot])) != QPB_OK) return rc;
+            if ((rc = qpbk_collide(c, 0.5 * dt)) != QPB_OK) return rc;
+        } else {             // solver.py:1474-1475
+            if (coll && (rc = qpbk_collide(c, dt)) != QPB_OK) return rc;
+            if (diff && (rc = qpbk_diffuse(c, c->slot[slot])) != QPB_OK) return rc;
+        }
+        if (pauli && (rc = qpbk_pauli(c, c->d_pauli + s)) != QPB_OK) return rc;
+        t += dt;
+        c->diag.steps_done++;
+    }
+    if (pauli && pauli_out && nsteps > 0)
+        QPB_CUDA(cudaMemcpyAsync(pauli_out, c->d_pauli, sizeof(qpb_pauli_rec) * nsteps, cudaMemcpyDeviceToHost,
+                                 c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_get_diag(qpb_ctx *c, qpb_diag *out) {
+    if (!c || !out) {
+        qpb_set_error("qpb_get_diag: null argument");
+        return QPB_E_INVALID;
+    }
+    *out = c->diag;
+    return QPB_OK;
+}
+
+extern "C" int qpb_synchronize(qpb_ctx *c) {
+    QPB_ENTER(c);
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_enable_timers(qpb_ctx *c, int on) {
+    if (!c) return QPB_E_INVALID;
+    c->timers_on = on != 0;
+    return QPB_OK;
+}
+
+extern "C" int qpb_reset_timers(qpb_ctx *c) {
+    if (!c) return QPB_E_INVALID;
+    for (auto &t : c->timer) t = Timer();
+    return QPB_OK;
+}
+
+extern "C" int qpb_get_timer(qpb_ctx *c, int which, double *ms, int64_t *launches) {
+    if (!c || which < 0 || which > 2) return QPB_E_INVALID;
+    if (ms) *ms = c->timer[which].ms;
+    if (launches) *launches = c->timer[which].launches;
+    return QPB_OK;
+}
+
+extern "C" int qpb_device_ptr(qpb_ctx *c, int which, void **ptr, int64_t *bytes) {
+    if (!c || !ptr) return QPB_E_INVALID;
+    if (which == 0) {
+        *ptr = c->d_S;
+        if (bytes) *bytes = (int64_t)sizeof(double) * c->cfg.ne * c->ncd;
+    } else if (which == 1) {
+        *ptr = c->d_P;
+        if (bytes) *bytes = (int64_t)sizeof(double) * c->cfg.nw * c->cfg.ncell;
+    } else
+        return QPB_E_INVALID;
+    return QPB_OK;
+}

@@ -1,0 +1,194 @@
+// Layout conversion, external generation, Pauli diagnostics and energy integration.
+//   generation  solver.py:1459-1464        Pauli stats  solver.py:967-996        integration  solver.py:1480
+#include "qpb_internal.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <climits>
+
+namespace {
+
+__global__ void k_scatter_state(int ne, int ncell, int ncd, const double *__restrict__ compact,
+                                double *__restrict__ dense, const int32_t *__restrict__ c2d) {
+    const long long total = (long long)ne * ncell;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(g / ncell);
+        const int q = (int)(g - (long long)i * ncell);
+        dense[(long long)i * ncd + c2d[q]] = compact[g];
+    }
+}
+
+__global__ void k_gather_state(int ne, int ncell, int ncd, double *__restrict__ compact,
+                               const double *__restrict__ dense, const int32_t *__restrict__ c2d) {
+    const long long total = (long long)ne * ncell;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(g / ncell);
+        const int q = (int)(g - (long long)i * ncell);
+        compact[g] = dense[(long long)i * ncd + c2d[q]];
+    }
+}
+
+// state += scale * g   (g: one rate for every bin and cell, or a host-evaluated array [ne][ncell])
+__global__ void k_add_generation(int ne, int ncell, int ncd, double *__restrict__ S,
+                                 const int32_t *__restrict__ c2d, double scale, double rate,
+                                 const double *__restrict__ arr) {
+    const long long total = (long long)ne * ncell;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(g / ncell);
+        const int q = (int)(g - (long long)i * ncell);
+        const double v = arr ? arr[g] : rate;
+        S[(long long)i * ncd + c2d[q]] += scale * v;
+    }
+}
+
+// integrated[q] = (sum_i n[i][q]) * dE, bins added in order like np.sum(state, axis=0)
+__global__ void k_integrate(int ne, int ncell, int ncd, const double *__restrict__ S,
+                            const int32_t *__restrict__ c2d, double dE, double *__restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= ncell) return;
+    const int d = c2d[q];
+    double acc = 0.0;
+    for (int i = 0; i < ne; ++i) acc += S[(long long)i * ncd + d];
+    out[q] = acc * dE;
+}
+
+struct PauliPart {
+    double val;
+    long long idx;
+    long long forb;
+};
+
+__device__ __forceinline__ void pauli_merge(PauliPart &a, const PauliPart &b) {
+    if (b.val > a.val || (b.val == a.val && b.idx < a.idx)) {
+        a.val = b.val;
+        a.idx = b.idx;
+    }
+    if (b.forb < a.forb) a.forb = b.forb;
+}
+
+__device__ void pauli_block_reduce(PauliPart &p) {
+    __shared__ PauliPart sh[32];
+    for (int o = 16; o > 0; o >>= 1) {
+        PauliPart q;
+        q.val = __shfl_down_sync(0xffffffffu, p.val, o);
+        q.idx = __shfl_down_sync(0xffffffffu, p.idx, o);
+        q.forb = __shfl_down_sync(0xffffffffu, p.forb, o);
+        pauli_merge(p, q);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = p;
+    __syncthreads();
+    if (w == 0) {
+        const int nw = (blockDim.x + 31) >> 5;
+        PauliPart q = l < nw ? sh[l] : PauliPart{-DBL_MAX, LLONG_MAX, LLONG_MAX};
+        for (int o = 16; o > 0; o >>= 1) {
+            PauliPart r;
+            r.val = __shfl_down_sync(0xffffffffu, q.val, o);
+            r.idx = __shfl_down_sync(0xffffffffu, q.idx, o);
+            r.forb = __shfl_down_sync(0xffffffffu, q.forb, o);
+            pauli_merge(q, r);
+        }
+        p = q;
+    }
+}
+
+__global__ void k_pauli_stage1(int ne, int ncell, int ncd, const double *__restrict__ S,
+                               const int32_t *__restrict__ c2d, const double *__restrict__ rho,
+                               const int32_t *__restrict__ gapid, double floor_, PauliPart *__restrict__ part) {
+    PauliPart p{-DBL_MAX, LLONG_MAX, LLONG_MAX};
+    const long long total = (long long)ne * ncell;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(g / ncell);
+        const int q = (int)(g - (long long)i * ncell);
+        const double n = S[(long long)i * ncd + c2d[q]];
+        const double r = rho[(gapid ? gapid[q] : 0) * ne + i];
+        const bool ok = r > 1e-30;
+        const double f = ok ? n / fmax(r, 1e-30) : 0.0;
+        if (f > p.val) {  // indices grow along the loop, so ">" keeps the first maximum
+            p.val = f;
+            p.idx = g;
+        }
+        if (!ok && n > floor_ && g < p.forb) p.forb = g;
+    }
+    pauli_block_reduce(p);
+    if (threadIdx.x == 0) part[blockIdx.x] = p;
+}
+
+__global__ void k_pauli_stage2(int nparts, const PauliPart *__restrict__ part, qpb_pauli_rec *__restrict__ out) {
+    PauliPart p{-DBL_MAX, LLONG_MAX, LLONG_MAX};
+    for (int k = threadIdx.x; k < nparts; k += blockDim.x) pauli_merge(p, part[k]);
+    pauli_block_reduce(p);
+    if (threadIdx.x == 0) {
+        out->max_occ = p.val;
+        out->max_index = p.idx;
+        out->forbidden = p.forb == LLONG_MAX ? -1 : p.forb;
+    }
+}
+
+inline int grid_for(long long total, int threads, int cap) {
+    return (int)std::max<long long>(1, std::min<long long>(ceil_div64(total, threads), cap));
+}
+
+}  // namespace
+
+int qpbk_scatter_state(qpb_ctx *c, const double *d_compact) {
+    const auto &cf = c->cfg;
+    const long long total = (long long)cf.ne * cf.ncell;
+    k_scatter_state<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, d_compact, c->d_S,
+                                                                          c->d_cell2dense);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int qpbk_gather_state(qpb_ctx *c, double *d_compact) {
+    const auto &cf = c->cfg;
+    const long long total = (long long)cf.ne * cf.ncell;
+    k_gather_state<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, d_compact, c->d_S,
+                                                                         c->d_cell2dense);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_array) {
+    const auto &cf = c->cfg;
+    const long long total = (long long)cf.ne * cf.ncell;
+    k_add_generation<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S,
+                                                                           c->d_cell2dense, scale, rate, d_array);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int qpbk_integrate(qpb_ctx *c) {
+    const auto &cf = c->cfg;
+    k_integrate<<<(cf.ncell + 127) / 128, 128, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S, c->d_cell2dense, cf.dE,
+                                                               c->d_integrated);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out) {
+    const auto &cf = c->cfg;
+    const long long total = (long long)cf.ne * cf.ncell;
+    const int blocks = grid_for(total, 256, 148 * 8);
+    if (!c->d_pauli_part || c->pauli_blocks < blocks) {
+        if (c->d_pauli_part) cudaFree(c->d_pauli_part);
+        c->d_pauli_part = nullptr;
+        c->pauli_blocks = 148 * 8;
+        QPB_CUDA(cudaMalloc(&c->d_pauli_part, sizeof(PauliPart) * c->pauli_blocks));
+    }
+    k_pauli_stage1<<<blocks, 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S, c->d_cell2dense, c->d_rho,
+                                                  c->d_gapid, cf.pauli_floor, (PauliPart *)c->d_pauli_part);
+    QPB_CHECK_LAUNCH();
+    k_pauli_stage2<<<1, 256, 0, c->stream>>>(blocks, (const PauliPart *)c->d_pauli_part, d_out);
+    QPB_CHECK_LAUNCH();
+    c->diag.kernel_launches += 2;
+    return QPB_OK;
+}

@@ -1,0 +1,596 @@
+// Per-cell coupled quasiparticle + phonon collision update.
+//
+// Replaces qpsim/solver.py:794-875 (the Python loop over pixels) and :703-791, :640-665, :686-700 (the
+// per-pixel arithmetic):
+//   w = max(1 - n/max(rho,1e-30), 0), p = rho*w
+//   scattering   gain_i += dE rho_i w_i sum_j Ks[j,i] Np[j,i] n_j      loss_i += dE sum_j Ks[i,j] Np[i,j] p_j
+//                Np[i,j] = n_ph[idx_diff[i,j]] (+1 when E_i > E_j), zero diagonal
+//   recombination loss_i += 2dE sum_j Kr[i,j] (1+nS[i,j]) n_j          gain_i += 2dE p_i sum_j Kr[i,j] nS[i,j] p_j
+//   n'  = max(e^{-mu dt} n + (1-e^{-mu dt})/mu * max(gain + (mu-loss) n, 0), 0),  mu = max(loss, 0)
+//   phonons (from the OLD n, p):  a,b[idx_diff] += / -= dE n_i Ks[i,j] p_j ;  a,b[idx_sum] += dE n_i Kr n_j ;
+//                b[idx_sum] -= dE p_i Kr p_j ;  n_ph' = max(e^x n_ph + (e^x-1)/b * a, 0), x = clip(b dt, +-80)
+//
+// Two implementations:
+//  * k_collide_struct — uniform energy grid (idx_diff = f(|i-j|), idx_sum = f(i+j)), symmetric kernels, one gap
+//    table.  Lanes of a warp are different CELLS, every thread owns 8 rows (or 8 diagonals / anti-diagonals) and
+//    sweeps the other index in register tiles, so the kernel matrices are warp-uniform loads and the per-cell
+//    vectors are conflict-free shared-memory columns.  Three passes: rows (quasiparticles), diagonals (scattering
+//    phonon source), anti-diagonals (recombination / pair-breaking phonon source).
+//  * k_collide_generic — arbitrary index maps / per-cell gap tables; shared-memory atomics.
+#include "qpb_internal.h"
+
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+namespace {
+
+__device__ __forceinline__ double relax_update(double n, double gain, double loss, double dt) {
+    const double mu = fmax(loss, 0.0);                       // solver.py:655
+    const double P = fmax(gain + (mu - loss) * n, 0.0);      // solver.py:656
+    const double decay = exp(-mu * dt);
+    const double coeff = mu < 1e-14 ? dt : (1.0 - decay) / mu;
+    return fmax(decay * n + coeff * P, 0.0);
+}
+
+__device__ __forceinline__ double affine_growth(double y, double a, double b, double dt) {
+    const double x = fmin(fmax(b * dt, -80.0), 80.0);        // solver.py:693
+    const double ex = exp(x);
+    const double coeff = fabs(b) < 1e-14 ? dt : (ex - 1.0) / b;
+    return fmax(ex * y + coeff * a, 0.0);
+}
+
+// =========================================================================================================
+// generic kernel
+// =========================================================================================================
+struct GenericArgs {
+    int ne, nw, ncell, ncd, ngap;
+    double *S;
+    double *P;
+    const int32_t *c2d;
+    const double *Ks, *KsT, *Kr, *KrT, *rho;
+    const int32_t *gapid;
+    const int32_t *idxd, *idxdT, *idxs;
+    const int8_t *sign, *signT;
+    double dE, dt;
+    int scat, rec, update_ph;
+};
+
+template <int CG>
+__global__ void __launch_bounds__(128) k_collide_generic(GenericArgs A) {
+    extern __shared__ double sm[];
+    const int ne = A.ne, nw = A.nw;
+    const int per = 3 * ne + 3 * nw;
+    const int cell0 = blockIdx.x * CG;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int gid[CG];
+    bool same = true;
+#pragma unroll
+    for (int cc = 0; cc < CG; ++cc) {
+        const int q = min(cell0 + cc, A.ncell - 1);
+        gid[cc] = A.gapid ? A.gapid[q] : 0;
+        same = same && gid[cc] == gid[0];
+    }
+#pragma unroll
+    for (int cc = 0; cc < CG; ++cc) {
+        double *n = sm + cc * per, *w = n + ne, *p = w + ne, *ph = p + ne, *a = ph + nw, *b = a + nw;
+        const int q = cell0 + cc;
+        const bool live = q < A.ncell;
+        const int d = live ? A.c2d[q] : 0;
+        for (int i = tid; i < ne; i += nt) {
+            const double nv = live ? A.S[(long long)i * A.ncd + d] : 0.0;
+            const double r = A.rho[gid[cc] * ne + i];
+            const double wv = fmax(1.0 - nv / fmax(r, 1e-30), 0.0);
+            n[i] = nv;
+            w[i] = wv;
+            p[i] = r * wv;
+        }
+        for (int o = tid; o < nw; o += nt) {
+            ph[o] = live ? A.P[(long long)o * A.ncell + q] : 0.0;
+            a[o] = 0.0;
+            b[o] = 0.0;
+        }
+    }
+    __syncthreads();
+    const size_t nn = (size_t)ne * ne;
+    for (int i = tid; i < ne; i += nt) {
+        double gs[CG], ls[CG], lr[CG], gp[CG];
+#pragma unroll
+        for (int cc = 0; cc < CG; ++cc) gs[cc] = ls[cc] = lr[cc] = gp[cc] = 0.0;
+        for (int j = 0; j < ne; ++j) {
+            const size_t e = (size_t)j * ne + i;  // [j][i] of X == X[j,i];  [j][i] of XT == X[i,j]
+            double ks_ij = 0.0, ks_ji = 0.0, kr_ij = 0.0;
+            int id_ij = 0, id_ji = 0, sg_ij = 0, sg_ji = 0, is_ij = 0;
+            if (A.scat) {
+                id_ij = A.idxdT[e]; id_ji = A.idxd[e]; sg_ij = A.signT[e]; sg_ji = A.sign[e];
+            }
+            if (A.rec) is_ij = A.idxs[(size_t)i * ne + j];
+#pragma unroll
+            for (int cc = 0; cc < CG; ++cc) {
+                double *n = sm + cc * per, *p = n + 2 * ne, *ph = p + ne, *a = ph + nw, *b = a + nw;
+                if (cc == 0 || !same) {
+                    const size_t g = (size_t)gid[cc] * nn;
+                    if (A.scat) { ks_ij = A.KsT[g + e]; ks_ji = A.Ks[g + e]; }
+                    if (A.rec) kr_ij = A.KrT[g + e];
+                }
+                const double nj = n[j], pj = p[j], ni = n[i], pi = p[i];
+                if (A.scat) {
+                    if (i != j) {
+                        const double nd_ij = ph[id_ij], nd_ji = ph[id_ji];
+                        const double np_ij = sg_ij > 0 ? 1.0 + nd_ij : nd_ij;
+                        const double np_ji = sg_ji > 0 ? 1.0 + nd_ji : nd_ji;
+                        gs[cc] += ks_ji * np_ji * nj;
+                        ls[cc] += ks_ij * np_ij * pj;
+                    }
+                    if (A.update_ph && sg_ij != 0) {
+                        const double Sv = A.dE * (ni * ks_ij * pj);
+                        if (sg_ij > 0) { atomicAdd(&a[id_ij], Sv); atomicAdd(&b[id_ij], Sv); }
+                        else atomicAdd(&b[id_ij], -Sv);
+                    }
+                }
+                if (A.rec) {
+                    const double nS = ph[is_ij];
+                    lr[cc] += kr_ij * (1.0 + nS) * nj;
+                    gp[cc] += kr_ij * nS * pj;
+                    if (A.update_ph) {
+                        const double R = A.dE * (ni * kr_ij * nj);
+                        const double Bk = A.dE * (pi * kr_ij * pj);
+                        atomicAdd(&a[is_ij], R);
+                        atomicAdd(&b[is_ij], R - Bk);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < CG; ++cc) {
+            const int q = cell0 + cc;
+            if (q >= A.ncell) continue;
+            double *n = sm + cc * per, *w = n + ne, *p = w + ne;
+            const double r = A.rho[gid[cc] * ne + i];
+            const double gain = A.dE * r * w[i] * gs[cc] + 2.0 * A.dE * p[i] * gp[cc];
+            const double loss = A.dE * ls[cc] + 2.0 * A.dE * lr[cc];
+            A.S[(long long)i * A.ncd + A.c2d[q]] = relax_update(n[i], gain, loss, A.dt);
+        }
+    }
+    if (!A.update_ph || !(A.scat || A.rec)) return;
+    __syncthreads();
+#pragma unroll
+    for (int cc = 0; cc < CG; ++cc) {
+        const int q = cell0 + cc;
+        if (q >= A.ncell) continue;
+        double *ph = sm + cc * per + 3 * ne, *a = ph + nw, *b = a + nw;
+        for (int o = tid; o < nw; o += nt)
+            A.P[(long long)o * A.ncell + q] = affine_growth(ph[o], a[o], b[o], A.dt);
+    }
+}
+
+// =========================================================================================================
+// structured kernel
+// =========================================================================================================
+constexpr int TI = 8;     // rows / diagonals / anti-diagonals per thread
+constexpr int TJ = 4;     // columns per register tile
+constexpr int PADF = 8;   // zero padding in front of the n,p columns in shared memory
+constexpr int PADB = 16;  // and behind
+
+struct StructArgs {
+    int ne, nep, nw, ncell, ncd;
+    double *S;
+    double *P;
+    const int32_t *c2d;
+    const double2 *K2;   // [nep][nep]  (dE*Ks, 2dE*Kr)
+    const double *KsD;   // [nep][nep]  dE*Ks[j+k][j]
+    const double *KrA;   // [2nep][nep] dE*Kr[m-j][j] * (2 if j<m-j, 1 if j==m-j, else 0)
+    const double *rho;   // [nep] zero padded
+    const int32_t *dmap, *smap, *kof, *mof;
+    double dt;
+};
+
+// CC = cells per CTA-row (lanes that differ in cell); 32/CC sub-slots per warp work on different blocks.
+template <int CC, bool SC, bool RC, bool PH>
+__global__ void __launch_bounds__(256) k_collide_struct(StructArgs A) {
+    extern __shared__ double sm[];
+    const int nep = A.nep;
+    const int ncol = nep + PADF + PADB;
+    double *sn = sm;                                   // [ncol][CC]
+    double *sp = sn + (size_t)ncol * CC;               // [ncol][CC]
+    double *snd = sp + (size_t)ncol * CC;              // [nep][CC]      n_ph at |i-j| ; later: stash a (diag family)
+    double *sns = snd + (size_t)nep * CC;              // [2nep][CC]     n_ph at i+j   ; later: stash b (diag family)
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cl = lane % CC, sub = lane / CC;
+    constexpr int SUBS = 32 / CC;
+    const int nslot = (blockDim.x >> 5) * SUBS;
+    const int slot = warp * SUBS + sub;
+    const int cell0 = blockIdx.x * CC;
+    const int ncell = A.ncell;
+
+    // ---- stage the per-cell columns -------------------------------------------------------------------
+    for (int e = tid; e < ncol * CC; e += blockDim.x) {
+        const int col = e / CC, c = e - col * CC;
+        const int i = col - PADF;
+        const int q = cell0 + c;
+        double nv = 0.0, pv = 0.0;
+        if (i >= 0 && i < A.ne && q < ncell) {
+            nv = A.S[(long long)i * A.ncd + A.c2d[q]];
+            const double r = A.rho[i];
+            pv = r * fmax(1.0 - nv / fmax(r, 1e-30), 0.0);
+        }
+        sn[e] = nv;
+        sp[e] = pv;
+    }
+    for (int e = tid; e < 3 * nep * CC; e += blockDim.x) {
+        const int idx = e / CC, c = e - idx * CC;
+        const int q = cell0 + c;
+        double v = 0.0;
+        if (q < ncell) {
+            if (idx < nep) {
+                if (idx < A.ne) v = A.P[(long long)A.dmap[idx] * ncell + q];
+            } else {
+                const int m = idx - nep;
+                if (m < 2 * A.ne - 1) v = A.P[(long long)A.smap[m] * ncell + q];
+            }
+        }
+        snd[e] = v;  // snd and sns are contiguous
+    }
+    __syncthreads();
+    const double *cn = sn + (size_t)PADF * CC + cl;   // cn[idx*CC] = n[idx] of this lane's cell
+    const double *cp = sp + (size_t)PADF * CC + cl;
+    const double *cnd = snd + cl;
+    const double *cns = sns + cl;
+    const int q = cell0 + cl;
+    const bool live = q < ncell;
+
+    // ---- pass 1: rows ------------------------------------------------------------------------------------
+    const int nib = nep / TI;
+    for (int ib = slot; ib < nib; ib += nslot) {
+        const int i0 = ib * TI;
+        double ni[TI], pi[TI], L[TI], G[TI];
+#pragma unroll
+        for (int r = 0; r < TI; ++r) {
+            ni[r] = cn[(i0 + r) * CC];
+            pi[r] = cp[(i0 + r) * CC];
+            L[r] = 0.0;
+            G[r] = 0.0;
+        }
+        for (int j0 = 0; j0 < nep; j0 += TJ) {
+            double nj[TJ], pj[TJ];
+#pragma unroll
+            for (int s = 0; s < TJ; ++s) {
+                nj[s] = cn[(j0 + s) * CC];
+                pj[s] = cp[(j0 + s) * CC];
+            }
+            double nsw[TI + TJ - 1];
+            if (RC) {
+#pragma unroll
+                for (int t = 0; t < TI + TJ - 1; ++t) nsw[t] = cns[(i0 + j0 + t) * CC];
+            }
+            const int kb = i0 - j0;
+            if (kb >= TJ || kb <= -TI) {
+                // whole tile on one side of the diagonal: |i-j| = |kb| + (r-s) (below) or (s-r) (above)
+                const bool below = kb > 0;
+                double ndw[TI + TJ - 1];
+                if (SC) {
+                    const int base = below ? kb - (TJ - 1) : -kb - (TI - 1);
+#pragma unroll
+                    for (int t = 0; t < TI + TJ - 1; ++t) ndw[t] = cnd[(base + t) * CC];
+                }
+#pragma unroll
+                for (int r = 0; r < TI; ++r) {
+                    const double2 *krow = A.K2 + (size_t)(i0 + r) * nep + j0;
+#pragma unroll
+                    for (int s = 0; s < TJ; ++s) {
+                        const double2 kv = __ldg(krow + s);
+                        if (SC) {
+                            const double ndv = below ? ndw[r - s + TJ - 1] : ndw[s - r + TI - 1];
+                            const double e = kv.x * ndv;
+                            L[r] = fma(e, pj[s], L[r]);
+                            G[r] = fma(e, nj[s], G[r]);
+                            if (below) L[r] = fma(kv.x, pj[s], L[r]);   // spontaneous emission out of i
+                            else G[r] = fma(kv.x, nj[s], G[r]);         // spontaneous emission into i
+                        }
+                        if (RC) {
+                            const double g = kv.y * nsw[r + s];
+                            L[r] = fma(g + kv.y, nj[s], L[r]);
+                            G[r] = fma(g, pj[s], G[r]);
+                        }
+                    }
+                }
+            } else {
+                // tile crosses the diagonal: per-pair index
+#pragma unroll
+                for (int r = 0; r < TI; ++r) {
+                    const double2 *krow = A.K2 + (size_t)(i0 + r) * nep + j0;
+#pragma unroll
+                    for (int s = 0; s < TJ; ++s) {
+                        const double2 kv = __ldg(krow + s);
+                        const int k = kb + r - s;
+                        if (SC && k != 0) {
+                            const double ndv = cnd[(k > 0 ? k : -k) * CC];
+                            const double e = kv.x * ndv;
+                            L[r] = fma(e, pj[s], L[r]);
+                            G[r] = fma(e, nj[s], G[r]);
+                            if (k > 0) L[r] = fma(kv.x, pj[s], L[r]);
+                            else G[r] = fma(kv.x, nj[s], G[r]);
+                        }
+                        if (RC) {
+                            const double g = kv.y * nsw[r + s];
+                            L[r] = fma(g + kv.y, nj[s], L[r]);
+                            G[r] = fma(g, pj[s], G[r]);
+                        }
+                    }
+                }
+            }
+        }
+        if (live) {
+            const int d = A.c2d[q];
+#pragma unroll
+            for (int r = 0; r < TI; ++r) {
+                const int i = i0 + r;
+                if (i < A.ne) A.S[(long long)i * A.ncd + d] = relax_update(ni[r], pi[r] * G[r], L[r], A.dt);
+            }
+        }
+    }
+    if (!PH) return;
+    __syncthreads();  // everyone is done with n_ph(|i-j|), n_ph(i+j): the region becomes the diagonal-family stash
+    double *sta = snd;                         // a of the diagonal family  [nep][CC]
+    double *stb = snd + (size_t)nep * CC;      // b of the diagonal family  [nep][CC]
+
+    // ---- pass 2: diagonals k = i-j > 0 (scattering phonon source) ----------------------------------------
+    if (SC) {
+        const int nkb = nep / TI;
+        const int npair = (nkb + 1) / 2;
+        for (int it = slot; it < npair; it += nslot) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int kbk = half == 0 ? it : nkb - 1 - it;   // pair a long block with a short one
+                if (half == 1 && kbk == it) break;
+                const int k0 = kbk * TI;
+                double Aem[TI], Cab[TI];
+#pragma unroll
+                for (int r = 0; r < TI; ++r) Aem[r] = Cab[r] = 0.0;
+                const int jend = nep - k0;  // pairs exist for j < ne - k
+                for (int j0 = 0; j0 < jend; j0 += TJ) {
+                    double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
+#pragma unroll
+                    for (int s = 0; s < TJ; ++s) {
+                        nj[s] = cn[(j0 + s) * CC];
+                        pj[s] = cp[(j0 + s) * CC];
+                    }
+#pragma unroll
+                    for (int t = 0; t < TI + TJ - 1; ++t) {
+                        nwn[t] = cn[(j0 + k0 + t) * CC];
+                        pwn[t] = cp[(j0 + k0 + t) * CC];
+                    }
+#pragma unroll
+                    for (int r = 0; r < TI; ++r) {
+                        const double *krow = A.KsD + (size_t)(k0 + r) * nep + j0;
+#pragma unroll
+                        for (int s = 0; s < TJ; ++s) {
+                            const double kv = __ldg(krow + s);
+                            Aem[r] = fma(nwn[r + s], kv * pj[s], Aem[r]);   // n_{j+k} Ks p_j   (emission, i = j+k)
+                            Cab[r] = fma(pwn[r + s], kv * nj[s], Cab[r]);   // n_j Ks p_{j+k}   (absorption, i = j)
+                        }
+                    }
+                }
+                if (live) {
+#pragma unroll
+                    for (int r = 0; r < TI; ++r) {
+                        const int k = k0 + r;
+                        if (k >= A.ne) continue;
+                        const double a = Aem[r], b = Aem[r] - Cab[r];
+                        const int om = A.dmap[k];
+                        if (RC && A.mof[om] >= 0) {
+                            sta[k * CC + cl] = a;
+                            stb[k * CC + cl] = b;
+                        } else {
+                            const long long o = (long long)om * ncell + q;
+                            A.P[o] = affine_growth(A.P[o], a, b, A.dt);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!RC) return;
+    __syncthreads();
+
+    // ---- pass 3: anti-diagonals m = i+j (recombination / pair breaking phonon source) ------------------------
+    {
+        const int nmb = 2 * nep / TI;       // blocks of anti-diagonals (the last one is partly padding)
+        const int hb = nmb / 2;
+        for (int it = slot; it < hb; it += nslot) {
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int mb = it + half * hb;   // work(mb) + work(mb + hb) is constant
+                const int m0 = mb * TI;
+                double R[TI], Bp[TI];
+#pragma unroll
+                for (int r = 0; r < TI; ++r) R[r] = Bp[r] = 0.0;
+                int jlo = m0 - (nep - 1);
+                jlo = jlo < 0 ? 0 : (jlo / TJ) * TJ;
+                int jhi = (m0 + TI - 1) / 2;          // largest j with j <= m-j for some m of the block
+                if (jhi > nep - 1) jhi = nep - 1;
+                for (int j0 = jlo; j0 <= jhi; j0 += TJ) {
+                    double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
+#pragma unroll
+                    for (int s = 0; s < TJ; ++s) {
+                        nj[s] = cn[(j0 + s) * CC];
+                        pj[s] = cp[(j0 + s) * CC];
+                    }
+                    const int base = m0 - j0 - (TJ - 1);     // index m-j = base + (r - s + TJ-1)
+#pragma unroll
+                    for (int t = 0; t < TI + TJ - 1; ++t) {
+                        nwn[t] = cn[(base + t) * CC];
+                        pwn[t] = cp[(base + t) * CC];
+                    }
+#pragma unroll
+                    for (int r = 0; r < TI; ++r) {
+                        const double *krow = A.KrA + (size_t)(m0 + r) * nep + j0;
+#pragma unroll
+                        for (int s = 0; s < TJ; ++s) {
+                            const double kv = __ldg(krow + s);
+                            R[r] = fma(nwn[r - s + TJ - 1], kv * nj[s], R[r]);
+                            Bp[r] = fma(pwn[r - s + TJ - 1], kv * pj[s], Bp[r]);
+                        }
+                    }
+                }
+                if (live) {
+#pragma unroll
+                    for (int r = 0; r < TI; ++r) {
+                        const int m = m0 + r;
+                        if (m >= 2 * A.ne - 1) continue;
+                        const int om = A.smap[m];
+                        double a = R[r], b = R[r];
+                        const int k = SC ? A.kof[om] : -1;
+                        if (k >= 0) {   // same phonon bin also fed by the diagonal family
+                            a = sta[k * CC + cl] + R[r];
+                            b = stb[k * CC + cl] + R[r];
+                        }
+                        b -= Bp[r];
+                        const long long o = (long long)om * ncell + q;
+                        A.P[o] = affine_growth(A.P[o], a, b, A.dt);
+                    }
+                }
+            }
+        }
+    }
+}
+
+struct StructTables {
+    double2 *K2 = nullptr;
+    double *KsD = nullptr, *KrA = nullptr, *rho = nullptr;
+    int nep = 0;
+};
+
+}  // namespace
+
+// The structured tables live in the scratch allocation of the context: [K2 | KsD | KrA | rho].
+static StructTables carve_tables(qpb_ctx *c) {
+    StructTables t;
+    const int nep = ((c->cfg.ne + TI - 1) / TI) * TI;
+    t.nep = nep;
+    char *base = (char *)c->d_scratch;
+    t.K2 = (double2 *)base;
+    base += sizeof(double2) * (size_t)nep * nep;
+    t.KsD = (double *)base;
+    base += sizeof(double) * (size_t)nep * nep;
+    t.KrA = (double *)base;
+    base += sizeof(double) * (size_t)2 * nep * nep;
+    t.rho = (double *)base;
+    return t;
+}
+
+int qpbk_collision_setup(qpb_ctx *c) {
+    const auto &cf = c->cfg;
+    const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
+    if (!(scat || rec)) return QPB_OK;
+    if (!(c->structured && cf.ngap == 1)) {
+        c->structured = false;
+        return QPB_OK;
+    }
+    const int ne = cf.ne;
+    const int nep = ((ne + TI - 1) / TI) * TI;
+    const size_t bytes = sizeof(double2) * (size_t)nep * nep + sizeof(double) * (size_t)3 * nep * nep +
+                         sizeof(double) * (size_t)nep;
+    if (c->d_scratch) cudaFree(c->d_scratch);
+    c->d_scratch = nullptr;
+    QPB_CUDA(cudaMalloc((void **)&c->d_scratch, bytes));
+    c->scratch_bytes = bytes;
+    // pull the uploaded matrices back (they are tiny) and build the padded / skewed copies
+    std::vector<double> Ks((size_t)ne * ne, 0.0), Kr((size_t)ne * ne, 0.0), rho(ne);
+    if (scat) QPB_CUDA(cudaMemcpy(Ks.data(), c->d_Ks, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost));
+    if (rec) QPB_CUDA(cudaMemcpy(Kr.data(), c->d_Kr, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost));
+    QPB_CUDA(cudaMemcpy(rho.data(), c->d_rho, sizeof(double) * ne, cudaMemcpyDeviceToHost));
+    std::vector<double2> K2((size_t)nep * nep, make_double2(0.0, 0.0));
+    std::vector<double> KsD((size_t)nep * nep, 0.0), KrA((size_t)2 * nep * nep, 0.0), rhop(nep, 0.0);
+    const double dE = cf.dE;
+    for (int i = 0; i < ne; ++i) {
+        rhop[i] = rho[i];
+        for (int j = 0; j < ne; ++j) {
+            K2[(size_t)i * nep + j] = make_double2(dE * Ks[(size_t)i * ne + j], 2.0 * dE * Kr[(size_t)i * ne + j]);
+            if (i >= j) KsD[(size_t)(i - j) * nep + j] = dE * Ks[(size_t)i * ne + j];
+            if (j <= i) {
+                const double wgt = j < i ? 2.0 : 1.0;
+                KrA[(size_t)(i + j) * nep + j] = wgt * dE * Kr[(size_t)i * ne + j];
+            }
+        }
+    }
+    StructTables t = carve_tables(c);
+    QPB_CUDA(cudaMemcpy(t.K2, K2.data(), sizeof(double2) * K2.size(), cudaMemcpyHostToDevice));
+    QPB_CUDA(cudaMemcpy(t.KsD, KsD.data(), sizeof(double) * KsD.size(), cudaMemcpyHostToDevice));
+    QPB_CUDA(cudaMemcpy(t.KrA, KrA.data(), sizeof(double) * KrA.size(), cudaMemcpyHostToDevice));
+    QPB_CUDA(cudaMemcpy(t.rho, rhop.data(), sizeof(double) * nep, cudaMemcpyHostToDevice));
+    return QPB_OK;
+}
+
+template <int CC, bool SC, bool RC, bool PH>
+static int launch_struct(qpb_ctx *c, const StructArgs &A, size_t smem) {
+    auto kern = k_collide_struct<CC, SC, RC, PH>;
+    static bool configured = false;
+    if (!configured) {
+        QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int blocks = (A.ncell + CC - 1) / CC;
+    kern<<<blocks, 256, smem, c->stream>>>(A);
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+template <int CC>
+static int dispatch_struct(qpb_ctx *c, const StructArgs &A, size_t smem, bool sc, bool rc, bool ph) {
+    if (sc && rc) return ph ? launch_struct<CC, true, true, true>(c, A, smem) : launch_struct<CC, true, true, false>(c, A, smem);
+    if (sc) return ph ? launch_struct<CC, true, false, true>(c, A, smem) : launch_struct<CC, true, false, false>(c, A, smem);
+    return ph ? launch_struct<CC, false, true, true>(c, A, smem) : launch_struct<CC, false, true, false>(c, A, smem);
+}
+
+template <int CG>
+static int launch_generic(qpb_ctx *c, const GenericArgs &A, size_t smem) {
+    auto kern = k_collide_generic<CG>;
+    static bool configured = false;
+    if (!configured) {
+        QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    const int blocks = (A.ncell + CG - 1) / CG;
+    kern<<<blocks, 128, smem, c->stream>>>(A);
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int qpbk_collide(qpb_ctx *c, double dt) {
+    const auto &cf = c->cfg;
+    const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
+    const bool ph = !(cf.flags & QPB_F_FREEZE_PHONONS);
+    ScopedTimer tm(c, 2);
+    c->diag.kernel_launches++;
+    const size_t smem_cap = 227 * 1024;
+    if (c->structured && (scat || rec)) {
+        StructTables t = carve_tables(c);
+        StructArgs A;
+        A.ne = cf.ne; A.nep = t.nep; A.nw = cf.nw; A.ncell = cf.ncell; A.ncd = c->ncd;
+        A.S = c->d_S; A.P = c->d_P; A.c2d = c->d_cell2dense;
+        A.K2 = t.K2; A.KsD = t.KsD; A.KrA = t.KrA; A.rho = t.rho;
+        A.dmap = c->d_dmap; A.smap = c->d_smap; A.kof = c->d_kof; A.mof = c->d_mof;
+        A.dt = dt;
+        auto need = [&](int cc) { return sizeof(double) * (size_t)cc * (2 * (t.nep + PADF + PADB) + 3 * t.nep); };
+        if (need(32) <= smem_cap) return dispatch_struct<32>(c, A, need(32), scat, rec, ph);
+        if (need(16) <= smem_cap) return dispatch_struct<16>(c, A, need(16), scat, rec, ph);
+        if (need(8) <= smem_cap) return dispatch_struct<8>(c, A, need(8), scat, rec, ph);
+        if (need(4) <= smem_cap) return dispatch_struct<4>(c, A, need(4), scat, rec, ph);
+        // energy grids too large for the shared-memory columns fall through to the generic kernel
+    }
+    GenericArgs G;
+    G.ne = cf.ne; G.nw = cf.nw; G.ncell = cf.ncell; G.ncd = c->ncd; G.ngap = cf.ngap;
+    G.S = c->d_S; G.P = c->d_P; G.c2d = c->d_cell2dense;
+    G.Ks = c->d_Ks; G.KsT = c->d_KsT; G.Kr = c->d_Kr; G.KrT = c->d_KrT; G.rho = c->d_rho;
+    G.gapid = c->d_gapid; G.idxd = c->d_idxd; G.idxdT = c->d_idxdT; G.idxs = c->d_idxs;
+    G.sign = c->d_sign; G.signT = c->d_signT;
+    G.dE = cf.dE; G.dt = dt; G.scat = scat; G.rec = rec; G.update_ph = ph;
+    auto need = [&](int cg) { return sizeof(double) * (size_t)cg * (3 * (size_t)cf.ne + 3 * (size_t)cf.nw); };
+    if (need(4) <= 96 * 1024) return launch_generic<4>(c, G, need(4));
+    if (need(2) <= smem_cap) return launch_generic<2>(c, G, need(2));
+    if (need(1) <= smem_cap) return launch_generic<1>(c, G, need(1));
+    qpb_set_error("qpb_collide: %d energy bins / %d phonon bins exceed the shared-memory budget", cf.ne, cf.nw);
+    return QPB_E_INVALID;
+}

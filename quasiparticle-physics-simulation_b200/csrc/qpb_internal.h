@@ -1,0 +1,154 @@
+// Internal declarations shared by the qpb translation units (not part of the C ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "qpb.h"
+
+// per-cell geometry flags (dense grid)
+#define QPB_LK_L 1u   // cell (y,x) linked to (y,x-1)
+#define QPB_LK_R 2u   // linked to (y,x+1)
+#define QPB_LK_U 4u   // linked to (y-1,x)
+#define QPB_LK_D 8u   // linked to (y+1,x)
+#define QPB_IN   16u  // cell is inside the mask
+
+void qpb_set_error(const char *fmt, ...);
+
+#define QPB_CUDA(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            qpb_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__,     \
+                          __LINE__, cudaGetErrorString(_e));                                \
+            return QPB_E_CUDA;                                                              \
+        }                                                                                   \
+    } while (0)
+
+#define QPB_CHECK_LAUNCH() QPB_CUDA(cudaGetLastError())
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// one prepared Crank-Nicolson solve (a step length)
+struct DiffSlot {
+    bool ready = false;
+    double dt = 0.0;
+    int mode = 0;              // 0 iterate, 1 direct sweep along x, 2 direct sweep along y
+    bool commuting = false;
+    int jmax = 0;              // row length of the shift table
+    int launch_iters = 0;      // iterations launched before the first host check
+    std::vector<double> a_bin; // 0.5*dt*D_i/dx^2 per bin (uniform D)
+    std::vector<int> jlen;     // shifts per bin
+    double *d_a = nullptr;     // [ne]
+    double *d_shift = nullptr; // [ne][jmax]
+    int *d_jlen = nullptr;     // [ne]
+    // variable-D coefficient fields (dense, per bin): links to the left / up neighbour, boundary diagonals
+    double *d_ex = nullptr, *d_ey = nullptr, *d_gbx = nullptr, *d_gby = nullptr;
+    // source term dt*D*s, dense [ncd] (uniform: multiplied by D_i on the fly) or [ne][ncd] (variable)
+    double *d_src = nullptr;
+    // fast path tables (uniform D, chunked sweeps)
+    struct FastDir {
+        int n = 0, S = 0, Q = 0, npad = 0, nclass = 0;
+        int *d_cls = nullptr;      // class of every line
+        double *d_tab = nullptr;   // [ne][jmax][nclass][5][npad]  m,f,Fp,g,Gs (chunk-interleaved)
+    } fx, fy;
+    bool fast = false;
+};
+
+struct Timer {
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+
+struct qpb_ctx {
+    qpb_config cfg{};
+    int ncd = 0;  // dense cells ny*nx
+    cudaStream_t stream = nullptr;
+    // geometry
+    bool have_geom = false;
+    std::vector<uint8_t> h_flags;
+    std::vector<double> h_bcx, h_bcy, h_src;
+    std::vector<int32_t> h_cell2dense;
+    uint8_t *d_flags = nullptr;      // [ncd]
+    double *d_bcx = nullptr, *d_bcy = nullptr, *d_srcgeom = nullptr;  // [ncd]
+    int32_t *d_cell2dense = nullptr; // [ncell]
+    bool thin_x = false, thin_y = false;  // no links along y / along x anywhere
+    bool commuting = false;
+    double gmax_x = 0.0, gmax_y = 0.0;    // Gershgorin bounds of -Lx, -Ly (grid units)
+    // diffusion
+    bool have_D = false;
+    std::vector<double> h_D;          // [ne] or [ne][ncell]
+    double *d_Dcell = nullptr;        // variable D: dense [ne][ncd]
+    DiffSlot slot[2];
+    double *d_S = nullptr;            // QP state dense [ne][ncd]
+    double *d_B = nullptr, *d_T1 = nullptr, *d_T2 = nullptr;  // CN work arrays
+    unsigned long long *d_res = nullptr;   // [maxit][ne] residual max-norms (bit patterns of doubles)
+    unsigned long long *d_unorm = nullptr; // [maxit][ne]
+    int *d_done = nullptr;                 // [ne]
+    int maxit = 0;
+    // collision
+    bool have_coll = false;
+    bool structured = false;          // Toeplitz/Hankel index maps, symmetric kernels
+    double *d_Kr = nullptr, *d_Ks = nullptr, *d_KrT = nullptr, *d_KsT = nullptr;  // [ngap][ne][ne]
+    double *d_rho = nullptr;          // [ngap][ne]
+    int32_t *d_gapid = nullptr;       // [ncell] or null
+    int32_t *d_idxd = nullptr, *d_idxs = nullptr, *d_idxdT = nullptr;  // [ne][ne]
+    int8_t *d_sign = nullptr, *d_signT = nullptr;
+    int32_t *d_dmap = nullptr;        // structured: diff index k -> phonon bin  [ne]
+    int32_t *d_smap = nullptr;        // structured: sum index m -> phonon bin   [2ne-1]
+    int32_t *d_kof = nullptr, *d_mof = nullptr;  // phonon bin -> k / m or -1   [nw]
+    double *d_P = nullptr;            // phonon state [nw][ncell]
+    double *d_scratch = nullptr;      // collision scratch
+    size_t scratch_bytes = 0;
+    // generation array
+    double *d_gen = nullptr;          // [ne][ncell]
+    // reductions
+    double *d_integrated = nullptr;   // [ncell]
+    qpb_pauli_rec *d_pauli = nullptr; // [capacity]
+    int pauli_cap = 0;
+    void *d_pauli_part = nullptr;     // block partials
+    int pauli_blocks = 0;
+    // diagnostics
+    qpb_diag diag{};
+    bool timers_on = false;
+    Timer timer[3];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+// ---- launch wrappers implemented in the .cu files (all enqueue on ctx->stream) ----
+int qpbk_build_rhs(qpb_ctx *c, DiffSlot &s);
+int qpbk_sweep_generic(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
+int qpbk_diffuse(qpb_ctx *c, DiffSlot &s);
+int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s);
+int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
+void qpbk_free_slot(DiffSlot &s);
+
+int qpbk_collide(qpb_ctx *c, double dt);
+int qpbk_collision_setup(qpb_ctx *c);
+
+int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_array);
+int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out);
+int qpbk_integrate(qpb_ctx *c);
+int qpbk_scatter_state(qpb_ctx *c, const double *d_compact);  // [ne][ncell] -> dense
+int qpbk_gather_state(qpb_ctx *c, double *d_compact);
+
+struct ScopedTimer {
+    qpb_ctx *c;
+    int which;
+    bool on;
+    ScopedTimer(qpb_ctx *ctx, int w) : c(ctx), which(w), on(ctx->timers_on) {
+        if (on) cudaEventRecord(c->ev0, c->stream);
+    }
+    ~ScopedTimer() {
+        if (on) {
+            cudaEventRecord(c->ev1, c->stream);
+            cudaEventSynchronize(c->ev1);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+            c->timer[which].ms += ms;
+            c->timer[which].launches += 1;
+        }
+    }
+};

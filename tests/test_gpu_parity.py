@@ -1,0 +1,90 @@
+"""CUDA path (through the C ABI / the Python drop-in) against the reference's golden fixtures and the oracle.
+
+Bar (BASELINE.json north_star): max relative error 1e-9 on n(x,y,E), total quasiparticle number to the same
+tolerance.  All tests here need a B200:  python -m pytest tests -m gpu
+"""
+import numpy as np
+import pytest
+
+import cases
+import helpers
+import qpsim_b200 as Q
+from oracle import qp_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = cases.golden_cases()
+
+
+@pytest.mark.parametrize("case", GOLDEN, ids=[c["name"] for c in GOLDEN])
+def test_dropin_matches_reference_fixture(case):
+    want = helpers.load_golden(case["name"])
+    got = helpers.run_dropin(case)
+    np.testing.assert_allclose(got["times"], want["times"], rtol=0, atol=1e-12)
+    helpers.assert_close(got["state"], want["state"], "n(E,cell)")
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
+    np.testing.assert_allclose(got["limits"], want["limits"], rtol=1e-8)
+    if "phonons" in want:
+        helpers.assert_close(got["phonons"], want["phonons"], "n_ph(omega,cell)")
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("flags", [(True, True), (True, False), (False, True)])
+def test_collision_helper_matches_reference_pixels(tag, flags):
+    """apply_collision_step_fischer_catelani_uniform on the fixture's random states (solver.py:794-831)."""
+    z = helpers.load_golden("tables_and_pixels")
+    rec, sc = flags
+    n, ph = z[f"{tag}_n_in"].copy(), z[f"{tag}_ph_in"].copy()
+    dE = float(z[f"{tag}_dE"])
+    args = (z[f"{tag}_Kr"], z[f"{tag}_Ks"], z[f"{tag}_rho"], z[f"{tag}_idx_diff"], z[f"{tag}_idx_sum"], z[f"{tag}_sign"])
+    Q.apply_collision_step_fischer_catelani_uniform(n, ph, *args, dE, 0.3, enable_recombination=rec,
+                                                    enable_scattering=sc)
+    if rec and sc:
+        want_n, want_ph = z[f"{tag}_n_out"], z[f"{tag}_ph_out"]
+    else:
+        want_n, want_ph = z[f"{tag}_n_in"].copy(), z[f"{tag}_ph_in"].copy()
+        O.collide(want_n, want_ph, *args, dE, 0.3, recomb=rec, scat=sc)
+    helpers.assert_close(n.T, want_n.T, "n", rtol=1e-12)
+    helpers.assert_close(ph.T, want_ph.T, "n_ph", rtol=1e-12)
+
+
+def test_generic_collision_kernel_nonuniform_tables():
+    """Per-pixel tables (solver.py:834-875) go through the generic kernel."""
+    rng = np.random.default_rng(5)
+    ne, n = 12, 23
+    E, dE = Q.build_energy_grid(cases.GAP, 1.0, 4.0, ne)
+    om, idd, ids, sg = Q.phonon_frequency_map(E)
+    gaps = np.where(np.arange(n) % 3 == 0, cases.GAP, 0.93 * cases.GAP)
+    rho_all = np.stack([Q.density_of_states(E, g, 0.18) for g in gaps])
+    Kr_all = np.stack([Q.recombination_kernel_base(E, g, 440.0, 1.2) for g in gaps])
+    Ks_all = np.stack([Q.scattering_kernel_base(E, g, 440.0, 1.2) for g in gaps])
+    state = rho_all.T * rng.uniform(0, 0.5, (ne, n))
+    ph = Q.thermal_phonon_occupation(om, 0.3)[:, None] * rng.uniform(0.5, 2, (om.size, n))
+    s_ref, p_ref = state.copy(), ph.copy()
+    O.collide(s_ref, p_ref, Kr_all, Ks_all, rho_all, idd, ids, sg, dE, 0.35, recomb=True, scat=True)
+    Q.apply_collision_step_fischer_catelani_nonuniform(state, ph, Kr_all, Ks_all, rho_all, idd, ids, sg, dE, 0.35,
+                                                       enable_recombination=True, enable_scattering=True)
+    helpers.assert_close(state.T, s_ref.T, "n", rtol=1e-12)
+    helpers.assert_close(ph.T, p_ref.T, "n_ph", rtol=1e-12)
+
+
+def test_reflective_uniform_field_is_stationary():
+    """tests/test_regressions.py:232-252 of the reference: uniform field, reflective walls, mass = 12."""
+    mask = np.ones((3, 4), dtype=bool)
+    edges = Q.extract_edge_segments(mask)
+    bcs = {e.edge_id: Q.BoundaryCondition(kind="reflective") for e in edges}
+    times, frames, mass, *_ = Q.run_2d_crank_nicolson(mask, edges, bcs, np.ones((3, 4)), 1.0, 0.1, 1.0, 1.0)
+    assert np.allclose(frames[-1], 1.0, atol=1e-12)
+    assert all(abs(m - 12.0) < 1e-10 for m in mass)
+
+
+def test_mass_conserved_and_medium_meander():
+    """All-reflective masked diffusion conserves total number to the parity tolerance; larger than the fixtures."""
+    case = cases.meander_c2(ny=96, nx=96, ne=16, steps=4, bc="reflective", pad=8, pitch=16, gap_len=24)
+    case["enable_recombination"] = case["enable_scattering"] = False
+    case["generation"] = None
+    got = helpers.run_dropin(case)
+    want = helpers.run_oracle(case)
+    helpers.assert_close(got["state"], want["state"], "n(E,cell)")
+    assert abs(got["mass"][-1] - got["mass"][0]) <= 1e-9 * got["mass"][0]
+    assert got["frames_nan_outside"]
