@@ -73,6 +73,8 @@ typedef struct qpb_diag {
     int32_t direct_mode;     /* 1: one-cell-thick geometry, CN solved by one direct sweep              */
     int32_t commuting;       /* 1: Lx,Ly commute (planned Wachspress sequence), 0: cyclic shifts        */
     int64_t kernel_launches; /* CUDA kernels launched by the library since creation                     */
+    double  last_advance_ms; /* device time of the most recent qpb_advance step loop (CUDA events on the
+                                library's stream, first launch to last kernel)                          */
 } qpb_diag;
 
 /* one record per time step, mirrors _pauli_occupancy_stats (solver.py:967-996) */
@@ -169,6 +171,14 @@ int qpb_synchronize(qpb_ctx *ctx);
 int qpb_enable_timers(qpb_ctx *ctx, int on);
 int qpb_reset_timers(qpb_ctx *ctx);
 int qpb_get_timer(qpb_ctx *ctx, int which, double *ms, int64_t *launches);
+
+/*
+ * Roofline denominators measured with the library's own micro-kernels on `device`:
+ *   qpb_measure_fp64  dependent-chain-free DFMA loop on every SM -> TFLOP/s (FMA = 2 flop)
+ *   qpb_measure_copy  float64 copy of `bytes` (read + write counted) -> GB/s
+ */
+int qpb_measure_fp64(int device, double *tflops);
+int qpb_measure_copy(int device, int64_t bytes, double *gbs);
 
 /* raw device pointers for NCCL plumbing (torch wraps them): which 0 = dense QP state [ne][ny*nx],
  * 1 = phonon state [nw][N]; *bytes receives the allocation size */

@@ -53,7 +53,7 @@ class Diag(C.Structure):
     _fields_ = [
         ("steps_done", C.c_int64), ("sweeps", C.c_int64), ("bin_sweeps", C.c_int64),
         ("pr_iterations", C.c_int64), ("last_delta", C.c_double), ("direct_mode", C.c_int32),
-        ("commuting", C.c_int32), ("kernel_launches", C.c_int64),
+        ("commuting", C.c_int32), ("kernel_launches", C.c_int64), ("last_advance_ms", C.c_double),
     ]
 
 
@@ -76,7 +76,7 @@ EXPORTED = [
     "qpb_upload_geometry", "qpb_upload_diffusion", "qpb_prepare_diffusion", "qpb_upload_collision",
     "qpb_set_state", "qpb_get_state", "qpb_get_integrated", "qpb_advance", "qpb_collide", "qpb_diffuse",
     "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
-    "qpb_device_ptr",
+    "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy",
 ]
 
 
@@ -154,6 +154,8 @@ def load_library():
     lib.qpb_reset_timers.argtypes = [vp]
     lib.qpb_get_timer.argtypes = [vp, C.c_int, C.POINTER(dbl), C.POINTER(i64)]
     lib.qpb_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    lib.qpb_measure_fp64.argtypes = [C.c_int, C.POINTER(dbl)]
+    lib.qpb_measure_copy.argtypes = [C.c_int, i64, C.POINTER(dbl)]
     for name in EXPORTED:
         fn = getattr(lib, name)
         if name not in ("qpb_last_error", "qpb_destroy"):
@@ -304,3 +306,21 @@ class Context:
         p, n = C.c_void_p(), C.c_int64()
         self._check(self.lib.qpb_device_ptr(self.handle, int(which), C.byref(p), C.byref(n)))
         return p.value, n.value
+
+
+def measure_fp64_tflops(device: int = 0) -> float:
+    lib = load_library()
+    out = C.c_double()
+    rc = lib.qpb_measure_fp64(int(device), C.byref(out))
+    if rc != 0:
+        raise QpbError(rc, lib.qpb_last_error().decode())
+    return out.value
+
+
+def measure_copy_gbs(device: int = 0, nbytes: int = 1 << 30) -> float:
+    lib = load_library()
+    out = C.c_double()
+    rc = lib.qpb_measure_copy(int(device), int(nbytes), C.byref(out))
+    if rc != 0:
+        raise QpbError(rc, lib.qpb_last_error().decode())
+    return out.value

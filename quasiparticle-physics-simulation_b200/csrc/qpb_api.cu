@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <random>
 
@@ -618,6 +619,8 @@ extern "C" int qpb_upload_collision(qpb_ctx *c, const double *K_r0, const double
             return true;
         };
         ok = ok && symmetric(scat ? K_s0 : nullptr) && symmetric(rec ? K_r0 : nullptr);
+        if (const char *env = getenv("QPB_FORCE_GENERIC"))   // test hook: exercise the generic kernels
+            if (env[0] == '1') ok = false;
         if (ok && scat)
             for (int g = 0; g < ng && ok; ++g)
                 for (int i = 0; i < ne; ++i)
@@ -754,6 +757,14 @@ extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, 
     }
     double t = t_start;
     int rc;
+    cudaEvent_t ea = nullptr, eb = nullptr;
+    QPB_CUDA(cudaEventCreate(&ea));
+    QPB_CUDA(cudaEventCreate(&eb));
+    struct EvGuard {
+        cudaEvent_t a, b;
+        ~EvGuard() { cudaEventDestroy(a); cudaEventDestroy(b); }
+    } guard{ea, eb};
+    QPB_CUDA(cudaEventRecord(ea, c->stream));
     for (int s = 0; s < nsteps; ++s) {
         if (gmode == QPB_GEN_CONSTANT) {
             if ((rc = qpbk_add_generation(c, dt, gen->rate, nullptr)) != QPB_OK) return rc;
@@ -775,10 +786,14 @@ extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, 
         t += dt;
         c->diag.steps_done++;
     }
+    QPB_CUDA(cudaEventRecord(eb, c->stream));
     if (pauli && pauli_out && nsteps > 0)
         QPB_CUDA(cudaMemcpyAsync(pauli_out, c->d_pauli, sizeof(qpb_pauli_rec) * nsteps, cudaMemcpyDeviceToHost,
                                  c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    QPB_CUDA(cudaEventElapsedTime(&ms, ea, eb));
+    c->diag.last_advance_ms = ms;
     return QPB_OK;
 }
 

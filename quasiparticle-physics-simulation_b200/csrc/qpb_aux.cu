@@ -192,3 +192,80 @@ int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out) {
     c->diag.kernel_launches += 2;
     return QPB_OK;
 }
+
+// ---- roofline denominators ------------------------------------------------------------------------------
+namespace {
+__global__ void k_fp64_peak(double *out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 1.0000001, b = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+__global__ void k_copy(const double2 *__restrict__ in, double2 *__restrict__ out, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+}  // namespace
+
+extern "C" int qpb_measure_fp64(int device, double *tflops) {
+    if (!tflops) return QPB_E_INVALID;
+    QPB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp p;
+    QPB_CUDA(cudaGetDeviceProperties(&p, device));
+    const int blocks = p.multiProcessorCount * 8, threads = 256, iters = 4096;
+    double *d = nullptr;
+    QPB_CUDA(cudaMalloc((void **)&d, sizeof(double) * blocks * threads));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(a);
+        k_fp64_peak<<<blocks, threads>>>(d, iters);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep >= 1 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d);
+    QPB_CHECK_LAUNCH();
+    *tflops = 2.0 * 8.0 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return QPB_OK;
+}
+
+extern "C" int qpb_measure_copy(int device, int64_t bytes, double *gbs) {
+    if (!gbs || bytes < 1024) return QPB_E_INVALID;
+    QPB_CUDA(cudaSetDevice(device));
+    const long long n = bytes / 16;
+    double2 *x = nullptr, *y = nullptr;
+    QPB_CUDA(cudaMalloc((void **)&x, n * 16));
+    QPB_CUDA(cudaMalloc((void **)&y, n * 16));
+    QPB_CUDA(cudaMemset(x, 0, n * 16));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 8; ++rep) {
+        cudaEventRecord(a);
+        k_copy<<<148 * 16, 512>>>(x, y, n);
+        cudaEventRecord(b);
+        cudaEventSynchronize(b);
+        float ms;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep >= 2 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(x);
+    cudaFree(y);
+    QPB_CHECK_LAUNCH();
+    *gbs = 2.0 * n * 16 / (best * 1e-3) / 1e9;
+    return QPB_OK;
+}

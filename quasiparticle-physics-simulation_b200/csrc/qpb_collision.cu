@@ -25,17 +25,25 @@
 
 namespace {
 
+// exp as the reference's libm evaluates it.  The reference forms (exp(x) - 1)/b and (1 - exp(-mu dt))/mu
+// (solver.py:661, 697), which amplify a 1-ulp difference in exp(x) by 1/|x|.  glibc's exp is correctly rounded
+// for all but near-tie inputs; for small |x| the correctly rounded value is fl(1 + expm1(x)), so this form agrees
+// with it bit for bit where the amplification matters, while CUDA's 1-ulp exp() would not.
+__device__ __forceinline__ double exp_ref(double x) {
+    return fabs(x) < 0.25 ? 1.0 + expm1(x) : exp(x);
+}
+
 __device__ __forceinline__ double relax_update(double n, double gain, double loss, double dt) {
     const double mu = fmax(loss, 0.0);                       // solver.py:655
     const double P = fmax(gain + (mu - loss) * n, 0.0);      // solver.py:656
-    const double decay = exp(-mu * dt);
+    const double decay = exp_ref(-mu * dt);
     const double coeff = mu < 1e-14 ? dt : (1.0 - decay) / mu;
     return fmax(decay * n + coeff * P, 0.0);
 }
 
 __device__ __forceinline__ double affine_growth(double y, double a, double b, double dt) {
     const double x = fmin(fmax(b * dt, -80.0), 80.0);        // solver.py:693
-    const double ex = exp(x);
+    const double ex = exp_ref(x);
     const double coeff = fabs(b) < 1e-14 ? dt : (ex - 1.0) / b;
     return fmax(ex * y + coeff * a, 0.0);
 }

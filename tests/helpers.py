@@ -13,6 +13,11 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 # tolerance of BASELINE.json's north_star: max relative error 1e-9 (fp64) on n(x,y,E)
 RTOL = 1e-9
+# Phonon occupations are an internal state, not the north-star quantity.  The reference updates them with
+# (exp(x)-1)/b (solver.py:697), which amplifies a one-ulp difference between libm exp implementations by 1/|x|;
+# numpy's own exp changes by an ulp between SIMD builds, so the reference's n_ph is only reproducible to ~1e-7
+# in bins where the source term dominates (see test_phonon_update_within_reference_libm_band).
+RTOL_PHONON = 2e-6
 
 
 def load_golden(name: str):

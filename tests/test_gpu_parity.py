@@ -25,7 +25,7 @@ def test_dropin_matches_reference_fixture(case):
     np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
     np.testing.assert_allclose(got["limits"], want["limits"], rtol=1e-8)
     if "phonons" in want:
-        helpers.assert_close(got["phonons"], want["phonons"], "n_ph(omega,cell)")
+        helpers.assert_close(got["phonons"], want["phonons"], "n_ph(omega,cell)", rtol=helpers.RTOL_PHONON)
 
 
 @pytest.mark.parametrize("tag", ["a", "b", "c"])
@@ -44,8 +44,33 @@ def test_collision_helper_matches_reference_pixels(tag, flags):
     else:
         want_n, want_ph = z[f"{tag}_n_in"].copy(), z[f"{tag}_ph_in"].copy()
         O.collide(want_n, want_ph, *args, dE, 0.3, recomb=rec, scat=sc)
-    helpers.assert_close(n.T, want_n.T, "n", rtol=1e-12)
-    helpers.assert_close(ph.T, want_ph.T, "n_ph", rtol=1e-12)
+    helpers.assert_close(n.T, want_n.T, "n", rtol=1e-10)
+    helpers.assert_close(ph.T, want_ph.T, "n_ph", rtol=helpers.RTOL_PHONON)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_phonon_update_within_reference_libm_band(generic, monkeypatch):
+    """One collision call, element by element: the CUDA result must lie within the spread the reference itself
+    shows between a correctly rounded exp and numpy's SIMD exp (plus 1e-12), for both kernels."""
+    monkeypatch.setenv("QPB_FORCE_GENERIC", "1" if generic else "0")
+    z = helpers.load_golden("tables_and_pixels")
+    for tag in "abc":
+        dE = float(z[f"{tag}_dE"])
+        args = (z[f"{tag}_Kr"], z[f"{tag}_Ks"], z[f"{tag}_rho"], z[f"{tag}_idx_diff"], z[f"{tag}_idx_sum"], z[f"{tag}_sign"])
+        outs = []
+        for impl in (O._exp_numpy, O._exp_correctly_rounded):
+            monkeypatch.setattr(O, "EXP", impl)
+            n, ph = z[f"{tag}_n_in"].copy(), z[f"{tag}_ph_in"].copy()
+            O.collide(n, ph, *args, dE, 0.3, recomb=True, scat=True)
+            outs.append((n, ph))
+        monkeypatch.setattr(O, "EXP", O._exp_numpy)
+        n, ph = z[f"{tag}_n_in"].copy(), z[f"{tag}_ph_in"].copy()
+        Q.apply_collision_step_fischer_catelani_uniform(n, ph, *args, dE, 0.3, enable_recombination=True,
+                                                        enable_scattering=True)
+        for got, a, b in ((n, outs[0][0], outs[1][0]), (ph, outs[0][1], outs[1][1])):
+            band = np.abs(a - b)
+            err = np.minimum(np.abs(got - a), np.abs(got - b))
+            assert np.all(err <= 4.0 * band + 1e-12 * np.abs(a) + 1e-300)
 
 
 def test_generic_collision_kernel_nonuniform_tables():
@@ -64,8 +89,8 @@ def test_generic_collision_kernel_nonuniform_tables():
     O.collide(s_ref, p_ref, Kr_all, Ks_all, rho_all, idd, ids, sg, dE, 0.35, recomb=True, scat=True)
     Q.apply_collision_step_fischer_catelani_nonuniform(state, ph, Kr_all, Ks_all, rho_all, idd, ids, sg, dE, 0.35,
                                                        enable_recombination=True, enable_scattering=True)
-    helpers.assert_close(state.T, s_ref.T, "n", rtol=1e-12)
-    helpers.assert_close(ph.T, p_ref.T, "n_ph", rtol=1e-12)
+    helpers.assert_close(state.T, s_ref.T, "n", rtol=1e-10)
+    helpers.assert_close(ph.T, p_ref.T, "n_ph", rtol=helpers.RTOL_PHONON)
 
 
 def test_reflective_uniform_field_is_stationary():
