@@ -52,7 +52,9 @@ struct DiffSlot {
     struct FastDir {
         int n = 0, S = 0, Q = 0, npad = 0, nclass = 0;
         int *d_cls = nullptr;      // class of every line
-        double *d_tab = nullptr;   // [ne][jmax][nclass][5][npad]  m,f,Fp,g,Gs (chunk-interleaved)
+        double *d_tab = nullptr;   // [ne][jmax][nclass][npad] pivot reciprocals (x: chunk-interleaved)
+        bool use_tma = false;      // x sweep staged by TMA (nx % 16 == 0, nx <= 512)
+        std::vector<unsigned char> tma;  // host copy of the CUtensorMap triple passed as a kernel parameter
     } fx, fy;
     bool fast = false;
 };
