@@ -1,0 +1,391 @@
+// Structured collision kernel (included by qpb_collision.cu inside its anonymous namespace).
+//
+// Uniform energy grid: the phonon index maps depend on |i-j| and i+j only, the kernels are symmetric, one gap
+// table.  Work decomposition:
+//   * lanes of a warp are different CELLS (CC cells per CTA; 32/CC "sub-slots" per warp when CC < 32), so every
+//     per-cell vector n, p, n_ph(|i-j|), n_ph(i+j) is a shared-memory column read without bank conflicts and
+//     every kernel-matrix element is the same for all lanes of a sub-slot;
+//   * a thread owns TI = 8 rows (pass 1), diagonals (pass 2) or anti-diagonals (pass 3) and walks the other index
+//     in register tiles of TJ = 4; its accumulators never leave registers, so there is no cross-thread reduction;
+//   * the kernel-matrix tiles (8 x 4 elements) stream from L2 through a per-warp cp.async ring (3 stages), so the
+//     FP64 pipe does not wait on global loads; operands of a tile are read as 128-bit broadcasts.
+//
+//   pass 1 (rows, quasiparticles)      L_i = sum_j [dE Ks (nd + [i>j]) p_j + 2dE Kr (1 + ns) n_j]
+//                                      G_i = sum_j [dE Ks (nd + [j>i]) n_j + 2dE Kr ns p_j],  gain_i = p_i G_i
+//   pass 2 (diagonals k = i-j > 0)     A_k = sum_j n_{j+k} dE Ks[j+k,j] p_j,  C_k = sum_j n_j dE Ks[j,j+k] p_{j+k}
+//   pass 3 (anti-diagonals m = i+j)    R_m = sum n_i dE Kr n_j,  B_m = sum p_i dE Kr p_j   (symmetric halves folded)
+#pragma once
+
+constexpr int TI = 8;     // rows / diagonals / anti-diagonals per thread
+constexpr int TJ = 4;     // columns per register tile
+constexpr int PADF = 8;   // zero padding in front of the n,p columns in shared memory
+constexpr int PADB = 16;  // and behind
+constexpr int NSTAGE = 3; // cp.async ring depth
+
+struct StructArgs {
+    int ne, nep, nw, ncell, ncd;
+    double *S;
+    double *P;
+    const int32_t *c2d;
+    const double2 *K2;   // [nep][nep]  (dE*Ks, 2dE*Kr)
+    const double *KsD;   // [nep][nep]  dE*Ks[j+k][j]
+    const double *KrA;   // [2nep][nep] dE*Kr[m-j][j] * (2 if j<m-j, 1 if j==m-j, else 0)
+    const double *rho;   // [nep] zero padded
+    const int32_t *dmap, *smap, *kof, *mof;
+    double dt;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Copy one TI-row tile (UPR 16-byte units per row) from global to this sub-slot's ring stage.
+template <int CC, int UPR>
+__device__ __forceinline__ void ring_prefetch(char *stage, const char *gsrc, size_t row_stride, int cl) {
+    constexpr int U = TI * UPR;
+#pragma unroll
+    for (int e0 = 0; e0 < U; e0 += CC) {
+        const int e = e0 + cl;
+        if (U % CC == 0 || e < U) cp_async16(stage + e * 16, gsrc + (size_t)(e / UPR) * row_stride + (e % UPR) * 16);
+    }
+}
+
+// quasiparticle tile, one side of the diagonal (SIDE 0: i > j everywhere, 1: i < j everywhere, 2: mixed)
+template <int CC, bool SC, bool RC, int SIDE>
+__device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const double *__restrict__ cn,
+                                        const double *__restrict__ cp, const double *__restrict__ cnd,
+                                        const double *__restrict__ cns, int i0, int j0, double (&L)[TI],
+                                        double (&G)[TI]) {
+    double nj[TJ], pj[TJ];
+#pragma unroll
+    for (int s = 0; s < TJ; ++s) {
+        nj[s] = cn[(j0 + s) * CC];
+        pj[s] = cp[(j0 + s) * CC];
+    }
+    double nsw[TI + TJ - 1], ndw[TI + TJ - 1];
+    if (RC) {
+#pragma unroll
+        for (int t = 0; t < TI + TJ - 1; ++t) nsw[t] = cns[(i0 + j0 + t) * CC];
+    }
+    const int kb = i0 - j0;
+    if (SC && SIDE != 2) {
+        const int base = SIDE == 0 ? kb - (TJ - 1) : -kb - (TI - 1);
+#pragma unroll
+        for (int t = 0; t < TI + TJ - 1; ++t) ndw[t] = cnd[(base + t) * CC];
+    }
+#pragma unroll
+    for (int r = 0; r < TI; ++r) {
+#pragma unroll
+        for (int s = 0; s < TJ; ++s) {
+            const double2 kv = kt[r * TJ + s];
+            if (SC) {
+                if (SIDE == 0) {
+                    const double e = kv.x * ndw[r - s + TJ - 1];
+                    L[r] = fma(e + kv.x, pj[s], L[r]);   // stimulated + spontaneous emission out of i
+                    G[r] = fma(e, nj[s], G[r]);
+                } else if (SIDE == 1) {
+                    const double e = kv.x * ndw[s - r + TI - 1];
+                    L[r] = fma(e, pj[s], L[r]);
+                    G[r] = fma(e + kv.x, nj[s], G[r]);   // spontaneous emission into i
+                } else {
+                    const int k = kb + r - s;
+                    if (k != 0) {
+                        const double e = kv.x * cnd[(k > 0 ? k : -k) * CC];
+                        L[r] = fma(k > 0 ? e + kv.x : e, pj[s], L[r]);
+                        G[r] = fma(k > 0 ? e : e + kv.x, nj[s], G[r]);
+                    }
+                }
+            }
+            if (RC) {
+                const double g = kv.y * nsw[r + s];
+                L[r] = fma(g + kv.y, nj[s], L[r]);
+                G[r] = fma(g, pj[s], G[r]);
+            }
+        }
+    }
+}
+
+// CC = cells per CTA; NT = threads per CTA.
+template <int CC, int NT, bool SC, bool RC, bool PH>
+__global__ void __launch_bounds__(NT, 1) k_collide_struct(StructArgs A) {
+    extern __shared__ __align__(16) double sm[];
+    const int nep = A.nep;
+    const int ncol = nep + PADF + PADB;
+    constexpr int SUBS = 32 / CC;
+    constexpr int NWARP = NT / 32;
+    constexpr int STAGE_BYTES = TI * TJ * 16;               // one K2 tile (the largest)
+    double *sn = sm;                                   // [ncol][CC]
+    double *sp = sn + (size_t)ncol * CC;               // [ncol][CC]
+    double *snd = sp + (size_t)ncol * CC;              // [nep][CC]   n_ph at |i-j| ; later: stash a (diag family)
+    double *sns = snd + (size_t)nep * CC;              // [2nep][CC]  n_ph at i+j   ; later: stash b (diag family)
+    char *ring_all = reinterpret_cast<char *>(sns + (size_t)2 * nep * CC);
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cl = lane % CC, sub = lane / CC;
+    constexpr int nslot = NWARP * SUBS;
+    const int slot = warp * SUBS + sub;
+    char *ring = ring_all + (size_t)(warp * SUBS + sub) * NSTAGE * STAGE_BYTES;
+    const int cell0 = blockIdx.x * CC;
+    const int ncell = A.ncell;
+
+    // ---- stage the per-cell columns -------------------------------------------------------------------
+    for (int e = tid; e < ncol * CC; e += NT) {
+        const int col = e / CC, c = e - col * CC;
+        const int i = col - PADF;
+        const int q = cell0 + c;
+        double nv = 0.0, pv = 0.0;
+        if (i >= 0 && i < A.ne && q < ncell) {
+            nv = A.S[(long long)i * A.ncd + A.c2d[q]];
+            const double r = A.rho[i];
+            pv = r * fmax(1.0 - nv / fmax(r, 1e-30), 0.0);
+        }
+        sn[e] = nv;
+        sp[e] = pv;
+    }
+    for (int e = tid; e < 3 * nep * CC; e += NT) {
+        const int idx = e / CC, c = e - idx * CC;
+        const int q = cell0 + c;
+        double v = 0.0;
+        if (q < ncell) {
+            if (idx < nep) {
+                if (idx < A.ne) v = A.P[(long long)A.dmap[idx] * ncell + q];
+            } else {
+                const int m = idx - nep;
+                if (m < 2 * A.ne - 1) v = A.P[(long long)A.smap[m] * ncell + q];
+            }
+        }
+        snd[e] = v;  // snd and sns are contiguous
+    }
+    __syncthreads();
+    const double *cn = sn + (size_t)PADF * CC + cl;   // cn[idx*CC] = n[idx] of this lane's cell
+    const double *cp = sp + (size_t)PADF * CC + cl;
+    const double *cnd = snd + cl;
+    const double *cns = sns + cl;
+    const int q = cell0 + cl;
+    const bool live = q < ncell;
+
+    // ---- pass 1: rows ------------------------------------------------------------------------------------
+    {
+        const int nib = nep / TI;
+        const int ntile = nep / TJ;
+        // all sub-slots of a warp iterate the same number of times so that __syncwarp() is legal
+        const int nround = (nib + nslot - 1) / nslot;
+        for (int rd = 0; rd < nround; ++rd) {
+            const int ib = slot + rd * nslot;
+            const bool work = ib < nib;
+            const int i0 = work ? ib * TI : 0;
+            double L[TI], G[TI];
+#pragma unroll
+            for (int r = 0; r < TI; ++r) L[r] = G[r] = 0.0;
+            const char *gk = reinterpret_cast<const char *>(A.K2 + (size_t)i0 * nep);
+            const size_t rstride = (size_t)nep * 16;
+            __syncwarp();  // the previous round's last tile is no longer being read
+#pragma unroll
+            for (int t = 0; t < NSTAGE - 1; ++t) {
+                if (t < ntile) ring_prefetch<CC, TJ>(ring + t * STAGE_BYTES, gk + (size_t)t * TJ * 16, rstride, cl);
+                cp_async_commit();
+            }
+            for (int t = 0; t < ntile; ++t) {
+                __syncwarp();
+                const int tn = t + NSTAGE - 1;
+                if (tn < ntile)
+                    ring_prefetch<CC, TJ>(ring + (tn % NSTAGE) * STAGE_BYTES, gk + (size_t)tn * TJ * 16, rstride, cl);
+                cp_async_commit();
+                cp_async_wait<NSTAGE - 1>();
+                __syncwarp();
+                const double2 *kt = reinterpret_cast<const double2 *>(ring + (t % NSTAGE) * STAGE_BYTES);
+                const int j0 = t * TJ;
+                const int kb = i0 - j0;
+                if (kb >= TJ) qp_tile<CC, SC, RC, 0>(kt, cn, cp, cnd, cns, i0, j0, L, G);
+                else if (kb <= -TI) qp_tile<CC, SC, RC, 1>(kt, cn, cp, cnd, cns, i0, j0, L, G);
+                else qp_tile<CC, SC, RC, 2>(kt, cn, cp, cnd, cns, i0, j0, L, G);
+            }
+            cp_async_wait<0>();
+            if (live && work) {
+                const int d = A.c2d[q];
+#pragma unroll
+                for (int r = 0; r < TI; ++r) {
+                    const int i = i0 + r;
+                    if (i < A.ne)
+                        A.S[(long long)i * A.ncd + d] = relax_update(cn[i * CC], cp[i * CC] * G[r], L[r], A.dt);
+                }
+            }
+        }
+    }
+    if (!PH) return;
+    __syncthreads();  // everyone is done with n_ph(|i-j|), n_ph(i+j): the region becomes the diagonal-family stash
+    double *sta = snd;                         // a of the diagonal family  [nep][CC]
+    double *stb = snd + (size_t)nep * CC;      // b of the diagonal family  [nep][CC]
+
+    // ---- pass 2: diagonals k = i-j > 0 (scattering phonon source) ----------------------------------------
+    if (SC) {
+        const int nkb = nep / TI;
+        const int npair = (nkb + 1) / 2;
+        const int nround = (npair + nslot - 1) / nslot;
+        for (int rd = 0; rd < nround; ++rd) {
+            const int it = slot + rd * nslot;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int kbk = half == 0 ? it : nkb - 1 - it;   // pair a long block with a short one
+                const bool work = it < npair && !(half == 1 && kbk == it);
+                const int k0 = work ? kbk * TI : 0;
+                double Aem[TI], Cab[TI];
+#pragma unroll
+                for (int r = 0; r < TI; ++r) Aem[r] = Cab[r] = 0.0;
+                // the longest range among the lanes of this warp decides the trip count (extra tiles multiply zeros)
+                int ntile = work ? (nep - k0) / TJ : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ntile = max(ntile, __shfl_xor_sync(0xffffffffu, ntile, o));
+                const char *gk = reinterpret_cast<const char *>(A.KsD + (size_t)k0 * nep);
+                const size_t rstride = (size_t)nep * 8;
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < NSTAGE - 1; ++t) {
+                    if (t < ntile) ring_prefetch<CC, TJ / 2>(ring + t * STAGE_BYTES, gk + (size_t)t * TJ * 8, rstride, cl);
+                    cp_async_commit();
+                }
+                for (int t = 0; t < ntile; ++t) {
+                    __syncwarp();
+                    const int tn = t + NSTAGE - 1;
+                    if (tn < ntile)
+                        ring_prefetch<CC, TJ / 2>(ring + (tn % NSTAGE) * STAGE_BYTES, gk + (size_t)tn * TJ * 8, rstride, cl);
+                    cp_async_commit();
+                    cp_async_wait<NSTAGE - 1>();
+                    __syncwarp();
+                    const double *kt = reinterpret_cast<const double *>(ring + (t % NSTAGE) * STAGE_BYTES);
+                    const int j0 = t * TJ;
+                    if (j0 + k0 >= nep) continue;   // beyond this sub-slot's own range: nothing but padding
+                    double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
+#pragma unroll
+                    for (int s = 0; s < TJ; ++s) {
+                        nj[s] = cn[(j0 + s) * CC];
+                        pj[s] = cp[(j0 + s) * CC];
+                    }
+#pragma unroll
+                    for (int t2 = 0; t2 < TI + TJ - 1; ++t2) {
+                        nwn[t2] = cn[(j0 + k0 + t2) * CC];
+                        pwn[t2] = cp[(j0 + k0 + t2) * CC];
+                    }
+#pragma unroll
+                    for (int r = 0; r < TI; ++r) {
+#pragma unroll
+                        for (int s = 0; s < TJ; ++s) {
+                            const double kv = kt[r * TJ + s];
+                            Aem[r] = fma(nwn[r + s], kv * pj[s], Aem[r]);   // n_{j+k} Ks p_j   (emission, i = j+k)
+                            Cab[r] = fma(pwn[r + s], kv * nj[s], Cab[r]);   // n_j Ks p_{j+k}   (absorption, i = j)
+                        }
+                    }
+                }
+                cp_async_wait<0>();
+                if (live && work) {
+#pragma unroll
+                    for (int r = 0; r < TI; ++r) {
+                        const int k = k0 + r;
+                        if (k >= A.ne) continue;
+                        const double a = Aem[r], b = Aem[r] - Cab[r];
+                        const int om = A.dmap[k];
+                        if (RC && A.mof[om] >= 0) {
+                            sta[k * CC + cl] = a;
+                            stb[k * CC + cl] = b;
+                        } else {
+                            const long long o = (long long)om * ncell + q;
+                            A.P[o] = affine_growth(A.P[o], a, b, A.dt);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (!RC) return;
+    __syncthreads();
+
+    // ---- pass 3: anti-diagonals m = i+j (recombination / pair breaking phonon source) ------------------------
+    {
+        const int nmb = 2 * nep / TI;       // blocks of anti-diagonals (the last one is partly padding)
+        const int hb = nmb / 2;
+        const int nround = (hb + nslot - 1) / nslot;
+        for (int rd = 0; rd < nround; ++rd) {
+            const int it = slot + rd * nslot;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const bool work = it < hb;
+                const int mb = work ? it + half * hb : 0;   // work(mb) + work(mb + hb) is constant
+                const int m0 = mb * TI;
+                double R[TI], Bp[TI];
+#pragma unroll
+                for (int r = 0; r < TI; ++r) R[r] = Bp[r] = 0.0;
+                int jlo = m0 - (nep - 1);
+                jlo = jlo < 0 ? 0 : (jlo / TJ) * TJ;
+                int jhi = (m0 + TI - 1) / 2;          // largest j with j <= m-j for some m of the block
+                if (jhi > nep - 1) jhi = nep - 1;
+                const int mytiles = work ? (jhi - jlo) / TJ + 1 : 0;
+                int ntile = mytiles;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) ntile = max(ntile, __shfl_xor_sync(0xffffffffu, ntile, o));
+                const char *gk = reinterpret_cast<const char *>(A.KrA + (size_t)m0 * nep + jlo);
+                const size_t rstride = (size_t)nep * 8;
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < NSTAGE - 1; ++t) {
+                    if (t < mytiles) ring_prefetch<CC, TJ / 2>(ring + t * STAGE_BYTES, gk + (size_t)t * TJ * 8, rstride, cl);
+                    cp_async_commit();
+                }
+                for (int t = 0; t < ntile; ++t) {
+                    __syncwarp();
+                    const int tn = t + NSTAGE - 1;
+                    if (tn < mytiles)
+                        ring_prefetch<CC, TJ / 2>(ring + (tn % NSTAGE) * STAGE_BYTES, gk + (size_t)tn * TJ * 8, rstride, cl);
+                    cp_async_commit();
+                    cp_async_wait<NSTAGE - 1>();
+                    __syncwarp();
+                    if (t >= mytiles) continue;
+                    const double *kt = reinterpret_cast<const double *>(ring + (t % NSTAGE) * STAGE_BYTES);
+                    const int j0 = jlo + t * TJ;
+                    double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
+#pragma unroll
+                    for (int s = 0; s < TJ; ++s) {
+                        nj[s] = cn[(j0 + s) * CC];
+                        pj[s] = cp[(j0 + s) * CC];
+                    }
+                    const int base = m0 - j0 - (TJ - 1);     // index m-j = base + (r - s + TJ-1)
+#pragma unroll
+                    for (int t2 = 0; t2 < TI + TJ - 1; ++t2) {
+                        nwn[t2] = cn[(base + t2) * CC];
+                        pwn[t2] = cp[(base + t2) * CC];
+                    }
+#pragma unroll
+                    for (int r = 0; r < TI; ++r) {
+#pragma unroll
+                        for (int s = 0; s < TJ; ++s) {
+                            const double kv = kt[r * TJ + s];
+                            R[r] = fma(nwn[r - s + TJ - 1], kv * nj[s], R[r]);
+                            Bp[r] = fma(pwn[r - s + TJ - 1], kv * pj[s], Bp[r]);
+                        }
+                    }
+                }
+                cp_async_wait<0>();
+                if (live && work) {
+#pragma unroll
+                    for (int r = 0; r < TI; ++r) {
+                        const int m = m0 + r;
+                        if (m >= 2 * A.ne - 1) continue;
+                        const int om = A.smap[m];
+                        double a = R[r], b = R[r];
+                        const int k = SC ? A.kof[om] : -1;
+                        if (k >= 0) {   // same phonon bin also fed by the diagonal family
+                            a = sta[k * CC + cl] + R[r];
+                            b = stb[k * CC + cl] + R[r];
+                        }
+                        b -= Bp[r];
+                        const long long o = (long long)om * ncell + q;
+                        A.P[o] = affine_growth(A.P[o], a, b, A.dt);
+                    }
+                }
+            }
+        }
+    }
+}

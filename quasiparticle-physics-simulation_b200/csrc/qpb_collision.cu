@@ -172,297 +172,7 @@ __global__ void __launch_bounds__(128) k_collide_generic(GenericArgs A) {
     }
 }
 
-// =========================================================================================================
-// structured kernel
-// =========================================================================================================
-constexpr int TI = 8;     // rows / diagonals / anti-diagonals per thread
-constexpr int TJ = 4;     // columns per register tile
-constexpr int PADF = 8;   // zero padding in front of the n,p columns in shared memory
-constexpr int PADB = 16;  // and behind
-
-struct StructArgs {
-    int ne, nep, nw, ncell, ncd;
-    double *S;
-    double *P;
-    const int32_t *c2d;
-    const double2 *K2;   // [nep][nep]  (dE*Ks, 2dE*Kr)
-    const double *KsD;   // [nep][nep]  dE*Ks[j+k][j]
-    const double *KrA;   // [2nep][nep] dE*Kr[m-j][j] * (2 if j<m-j, 1 if j==m-j, else 0)
-    const double *rho;   // [nep] zero padded
-    const int32_t *dmap, *smap, *kof, *mof;
-    double dt;
-};
-
-// CC = cells per CTA-row (lanes that differ in cell); 32/CC sub-slots per warp work on different blocks.
-template <int CC, bool SC, bool RC, bool PH>
-__global__ void __launch_bounds__(256) k_collide_struct(StructArgs A) {
-    extern __shared__ double sm[];
-    const int nep = A.nep;
-    const int ncol = nep + PADF + PADB;
-    double *sn = sm;                                   // [ncol][CC]
-    double *sp = sn + (size_t)ncol * CC;               // [ncol][CC]
-    double *snd = sp + (size_t)ncol * CC;              // [nep][CC]      n_ph at |i-j| ; later: stash a (diag family)
-    double *sns = snd + (size_t)nep * CC;              // [2nep][CC]     n_ph at i+j   ; later: stash b (diag family)
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    const int cl = lane % CC, sub = lane / CC;
-    constexpr int SUBS = 32 / CC;
-    const int nslot = (blockDim.x >> 5) * SUBS;
-    const int slot = warp * SUBS + sub;
-    const int cell0 = blockIdx.x * CC;
-    const int ncell = A.ncell;
-
-    // ---- stage the per-cell columns -------------------------------------------------------------------
-    for (int e = tid; e < ncol * CC; e += blockDim.x) {
-        const int col = e / CC, c = e - col * CC;
-        const int i = col - PADF;
-        const int q = cell0 + c;
-        double nv = 0.0, pv = 0.0;
-        if (i >= 0 && i < A.ne && q < ncell) {
-            nv = A.S[(long long)i * A.ncd + A.c2d[q]];
-            const double r = A.rho[i];
-            pv = r * fmax(1.0 - nv / fmax(r, 1e-30), 0.0);
-        }
-        sn[e] = nv;
-        sp[e] = pv;
-    }
-    for (int e = tid; e < 3 * nep * CC; e += blockDim.x) {
-        const int idx = e / CC, c = e - idx * CC;
-        const int q = cell0 + c;
-        double v = 0.0;
-        if (q < ncell) {
-            if (idx < nep) {
-                if (idx < A.ne) v = A.P[(long long)A.dmap[idx] * ncell + q];
-            } else {
-                const int m = idx - nep;
-                if (m < 2 * A.ne - 1) v = A.P[(long long)A.smap[m] * ncell + q];
-            }
-        }
-        snd[e] = v;  // snd and sns are contiguous
-    }
-    __syncthreads();
-    const double *cn = sn + (size_t)PADF * CC + cl;   // cn[idx*CC] = n[idx] of this lane's cell
-    const double *cp = sp + (size_t)PADF * CC + cl;
-    const double *cnd = snd + cl;
-    const double *cns = sns + cl;
-    const int q = cell0 + cl;
-    const bool live = q < ncell;
-
-    // ---- pass 1: rows ------------------------------------------------------------------------------------
-    const int nib = nep / TI;
-    for (int ib = slot; ib < nib; ib += nslot) {
-        const int i0 = ib * TI;
-        double ni[TI], pi[TI], L[TI], G[TI];
-#pragma unroll
-        for (int r = 0; r < TI; ++r) {
-            ni[r] = cn[(i0 + r) * CC];
-            pi[r] = cp[(i0 + r) * CC];
-            L[r] = 0.0;
-            G[r] = 0.0;
-        }
-        for (int j0 = 0; j0 < nep; j0 += TJ) {
-            double nj[TJ], pj[TJ];
-#pragma unroll
-            for (int s = 0; s < TJ; ++s) {
-                nj[s] = cn[(j0 + s) * CC];
-                pj[s] = cp[(j0 + s) * CC];
-            }
-            double nsw[TI + TJ - 1];
-            if (RC) {
-#pragma unroll
-                for (int t = 0; t < TI + TJ - 1; ++t) nsw[t] = cns[(i0 + j0 + t) * CC];
-            }
-            const int kb = i0 - j0;
-            if (kb >= TJ || kb <= -TI) {
-                // whole tile on one side of the diagonal: |i-j| = |kb| + (r-s) (below) or (s-r) (above)
-                const bool below = kb > 0;
-                double ndw[TI + TJ - 1];
-                if (SC) {
-                    const int base = below ? kb - (TJ - 1) : -kb - (TI - 1);
-#pragma unroll
-                    for (int t = 0; t < TI + TJ - 1; ++t) ndw[t] = cnd[(base + t) * CC];
-                }
-#pragma unroll
-                for (int r = 0; r < TI; ++r) {
-                    const double2 *krow = A.K2 + (size_t)(i0 + r) * nep + j0;
-#pragma unroll
-                    for (int s = 0; s < TJ; ++s) {
-                        const double2 kv = __ldg(krow + s);
-                        if (SC) {
-                            const double ndv = below ? ndw[r - s + TJ - 1] : ndw[s - r + TI - 1];
-                            const double e = kv.x * ndv;
-                            L[r] = fma(e, pj[s], L[r]);
-                            G[r] = fma(e, nj[s], G[r]);
-                            if (below) L[r] = fma(kv.x, pj[s], L[r]);   // spontaneous emission out of i
-                            else G[r] = fma(kv.x, nj[s], G[r]);         // spontaneous emission into i
-                        }
-                        if (RC) {
-                            const double g = kv.y * nsw[r + s];
-                            L[r] = fma(g + kv.y, nj[s], L[r]);
-                            G[r] = fma(g, pj[s], G[r]);
-                        }
-                    }
-                }
-            } else {
-                // tile crosses the diagonal: per-pair index
-#pragma unroll
-                for (int r = 0; r < TI; ++r) {
-                    const double2 *krow = A.K2 + (size_t)(i0 + r) * nep + j0;
-#pragma unroll
-                    for (int s = 0; s < TJ; ++s) {
-                        const double2 kv = __ldg(krow + s);
-                        const int k = kb + r - s;
-                        if (SC && k != 0) {
-                            const double ndv = cnd[(k > 0 ? k : -k) * CC];
-                            const double e = kv.x * ndv;
-                            L[r] = fma(e, pj[s], L[r]);
-                            G[r] = fma(e, nj[s], G[r]);
-                            if (k > 0) L[r] = fma(kv.x, pj[s], L[r]);
-                            else G[r] = fma(kv.x, nj[s], G[r]);
-                        }
-                        if (RC) {
-                            const double g = kv.y * nsw[r + s];
-                            L[r] = fma(g + kv.y, nj[s], L[r]);
-                            G[r] = fma(g, pj[s], G[r]);
-                        }
-                    }
-                }
-            }
-        }
-        if (live) {
-            const int d = A.c2d[q];
-#pragma unroll
-            for (int r = 0; r < TI; ++r) {
-                const int i = i0 + r;
-                if (i < A.ne) A.S[(long long)i * A.ncd + d] = relax_update(ni[r], pi[r] * G[r], L[r], A.dt);
-            }
-        }
-    }
-    if (!PH) return;
-    __syncthreads();  // everyone is done with n_ph(|i-j|), n_ph(i+j): the region becomes the diagonal-family stash
-    double *sta = snd;                         // a of the diagonal family  [nep][CC]
-    double *stb = snd + (size_t)nep * CC;      // b of the diagonal family  [nep][CC]
-
-    // ---- pass 2: diagonals k = i-j > 0 (scattering phonon source) ----------------------------------------
-    if (SC) {
-        const int nkb = nep / TI;
-        const int npair = (nkb + 1) / 2;
-        for (int it = slot; it < npair; it += nslot) {
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int kbk = half == 0 ? it : nkb - 1 - it;   // pair a long block with a short one
-                if (half == 1 && kbk == it) break;
-                const int k0 = kbk * TI;
-                double Aem[TI], Cab[TI];
-#pragma unroll
-                for (int r = 0; r < TI; ++r) Aem[r] = Cab[r] = 0.0;
-                const int jend = nep - k0;  // pairs exist for j < ne - k
-                for (int j0 = 0; j0 < jend; j0 += TJ) {
-                    double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
-#pragma unroll
-                    for (int s = 0; s < TJ; ++s) {
-                        nj[s] = cn[(j0 + s) * CC];
-                        pj[s] = cp[(j0 + s) * CC];
-                    }
-#pragma unroll
-                    for (int t = 0; t < TI + TJ - 1; ++t) {
-                        nwn[t] = cn[(j0 + k0 + t) * CC];
-                        pwn[t] = cp[(j0 + k0 + t) * CC];
-                    }
-#pragma unroll
-                    for (int r = 0; r < TI; ++r) {
-                        const double *krow = A.KsD + (size_t)(k0 + r) * nep + j0;
-#pragma unroll
-                        for (int s = 0; s < TJ; ++s) {
-                            const double kv = __ldg(krow + s);
-                            Aem[r] = fma(nwn[r + s], kv * pj[s], Aem[r]);   // n_{j+k} Ks p_j   (emission, i = j+k)
-                            Cab[r] = fma(pwn[r + s], kv * nj[s], Cab[r]);   // n_j Ks p_{j+k}   (absorption, i = j)
-                        }
-                    }
-                }
-                if (live) {
-#pragma unroll
-                    for (int r = 0; r < TI; ++r) {
-                        const int k = k0 + r;
-                        if (k >= A.ne) continue;
-                        const double a = Aem[r], b = Aem[r] - Cab[r];
-                        const int om = A.dmap[k];
-                        if (RC && A.mof[om] >= 0) {
-                            sta[k * CC + cl] = a;
-                            stb[k * CC + cl] = b;
-                        } else {
-                            const long long o = (long long)om * ncell + q;
-                            A.P[o] = affine_growth(A.P[o], a, b, A.dt);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    if (!RC) return;
-    __syncthreads();
-
-    // ---- pass 3: anti-diagonals m = i+j (recombination / pair breaking phonon source) ------------------------
-    {
-        const int nmb = 2 * nep / TI;       // blocks of anti-diagonals (the last one is partly padding)
-        const int hb = nmb / 2;
-        for (int it = slot; it < hb; it += nslot) {
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int mb = it + half * hb;   // work(mb) + work(mb + hb) is constant
-                const int m0 = mb * TI;
-                double R[TI], Bp[TI];
-#pragma unroll
-                for (int r = 0; r < TI; ++r) R[r] = Bp[r] = 0.0;
-                int jlo = m0 - (nep - 1);
-                jlo = jlo < 0 ? 0 : (jlo / TJ) * TJ;
-                int jhi = (m0 + TI - 1) / 2;          // largest j with j <= m-j for some m of the block
-                if (jhi > nep - 1) jhi = nep - 1;
-                for (int j0 = jlo; j0 <= jhi; j0 += TJ) {
-                    double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
-#pragma unroll
-                    for (int s = 0; s < TJ; ++s) {
-                        nj[s] = cn[(j0 + s) * CC];
-                        pj[s] = cp[(j0 + s) * CC];
-                    }
-                    const int base = m0 - j0 - (TJ - 1);     // index m-j = base + (r - s + TJ-1)
-#pragma unroll
-                    for (int t = 0; t < TI + TJ - 1; ++t) {
-                        nwn[t] = cn[(base + t) * CC];
-                        pwn[t] = cp[(base + t) * CC];
-                    }
-#pragma unroll
-                    for (int r = 0; r < TI; ++r) {
-                        const double *krow = A.KrA + (size_t)(m0 + r) * nep + j0;
-#pragma unroll
-                        for (int s = 0; s < TJ; ++s) {
-                            const double kv = __ldg(krow + s);
-                            R[r] = fma(nwn[r - s + TJ - 1], kv * nj[s], R[r]);
-                            Bp[r] = fma(pwn[r - s + TJ - 1], kv * pj[s], Bp[r]);
-                        }
-                    }
-                }
-                if (live) {
-#pragma unroll
-                    for (int r = 0; r < TI; ++r) {
-                        const int m = m0 + r;
-                        if (m >= 2 * A.ne - 1) continue;
-                        const int om = A.smap[m];
-                        double a = R[r], b = R[r];
-                        const int k = SC ? A.kof[om] : -1;
-                        if (k >= 0) {   // same phonon bin also fed by the diagonal family
-                            a = sta[k * CC + cl] + R[r];
-                            b = stb[k * CC + cl] + R[r];
-                        }
-                        b -= Bp[r];
-                        const long long o = (long long)om * ncell + q;
-                        A.P[o] = affine_growth(A.P[o], a, b, A.dt);
-                    }
-                }
-            }
-        }
-    }
-}
+#include "qpb_collide_struct.cuh"
 
 struct StructTables {
     double2 *K2 = nullptr;
@@ -531,16 +241,26 @@ int qpbk_collision_setup(qpb_ctx *c) {
     return QPB_OK;
 }
 
+template <int CC>
+struct StructCfg {
+    static constexpr int NT = CC >= 16 ? 512 : (CC == 8 ? 256 : 128);
+    static size_t smem(int nep) {
+        return sizeof(double) * (size_t)CC * (2 * (nep + PADF + PADB) + 3 * nep) +
+               (size_t)(NT / 32) * (32 / CC) * NSTAGE * (TI * TJ * 16);
+    }
+};
+
 template <int CC, bool SC, bool RC, bool PH>
 static int launch_struct(qpb_ctx *c, const StructArgs &A, size_t smem) {
-    auto kern = k_collide_struct<CC, SC, RC, PH>;
+    constexpr int NT = StructCfg<CC>::NT;
+    auto kern = k_collide_struct<CC, NT, SC, RC, PH>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
     const int blocks = (A.ncell + CC - 1) / CC;
-    kern<<<blocks, 256, smem, c->stream>>>(A);
+    kern<<<blocks, NT, smem, c->stream>>>(A);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
 }
@@ -581,11 +301,10 @@ int qpbk_collide(qpb_ctx *c, double dt) {
         A.K2 = t.K2; A.KsD = t.KsD; A.KrA = t.KrA; A.rho = t.rho;
         A.dmap = c->d_dmap; A.smap = c->d_smap; A.kof = c->d_kof; A.mof = c->d_mof;
         A.dt = dt;
-        auto need = [&](int cc) { return sizeof(double) * (size_t)cc * (2 * (t.nep + PADF + PADB) + 3 * t.nep); };
-        if (need(32) <= smem_cap) return dispatch_struct<32>(c, A, need(32), scat, rec, ph);
-        if (need(16) <= smem_cap) return dispatch_struct<16>(c, A, need(16), scat, rec, ph);
-        if (need(8) <= smem_cap) return dispatch_struct<8>(c, A, need(8), scat, rec, ph);
-        if (need(4) <= smem_cap) return dispatch_struct<4>(c, A, need(4), scat, rec, ph);
+        if (StructCfg<32>::smem(t.nep) <= smem_cap) return dispatch_struct<32>(c, A, StructCfg<32>::smem(t.nep), scat, rec, ph);
+        if (StructCfg<16>::smem(t.nep) <= smem_cap) return dispatch_struct<16>(c, A, StructCfg<16>::smem(t.nep), scat, rec, ph);
+        if (StructCfg<8>::smem(t.nep) <= smem_cap) return dispatch_struct<8>(c, A, StructCfg<8>::smem(t.nep), scat, rec, ph);
+        if (StructCfg<4>::smem(t.nep) <= smem_cap) return dispatch_struct<4>(c, A, StructCfg<4>::smem(t.nep), scat, rec, ph);
         // energy grids too large for the shared-memory columns fall through to the generic kernel
     }
     GenericArgs G;
