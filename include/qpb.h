@@ -184,6 +184,17 @@ int qpb_measure_copy(int device, int64_t bytes, double *gbs);
  * 1 = phonon state [nw][N]; *bytes receives the allocation size */
 int qpb_device_ptr(qpb_ctx *ctx, int which, void **ptr, int64_t *bytes);
 
+/*
+ * Multi-GPU plumbing: diffusion is sharded by energy bin, collisions by cell.  A rank
+ * holds a diffusion context (its bins, all cells) and a collision context (all bins, its cells as a 1 x N_local
+ * strip); between the stages the host moves blocks with NCCL and these two calls convert between a received
+ * block  d_block[ne][count]  (cells cell0 .. cell0+count-1 of the compressed ordering, DEVICE memory) and the
+ * dense state of the context.  qpb_add_generation applies  state += scale * rate  (solver.py:1464) as a stage.
+ */
+int qpb_scatter_block(qpb_ctx *ctx, const double *d_block, int32_t cell0, int32_t count);
+int qpb_gather_block(qpb_ctx *ctx, double *d_block, int32_t cell0, int32_t count);
+int qpb_add_generation(qpb_ctx *ctx, double scale, double rate);
+
 #ifdef __cplusplus
 }
 #endif

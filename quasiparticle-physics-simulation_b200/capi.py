@@ -76,7 +76,8 @@ EXPORTED = [
     "qpb_upload_geometry", "qpb_upload_diffusion", "qpb_prepare_diffusion", "qpb_upload_collision",
     "qpb_set_state", "qpb_get_state", "qpb_get_integrated", "qpb_advance", "qpb_collide", "qpb_diffuse",
     "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
-    "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy",
+    "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
+    "qpb_add_generation",
 ]
 
 
@@ -154,6 +155,9 @@ def load_library():
     lib.qpb_reset_timers.argtypes = [vp]
     lib.qpb_get_timer.argtypes = [vp, C.c_int, C.POINTER(dbl), C.POINTER(i64)]
     lib.qpb_device_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(i64)]
+    lib.qpb_scatter_block.argtypes = [vp, vp, i32, i32]
+    lib.qpb_gather_block.argtypes = [vp, vp, i32, i32]
+    lib.qpb_add_generation.argtypes = [vp, dbl, dbl]
     lib.qpb_measure_fp64.argtypes = [C.c_int, C.POINTER(dbl)]
     lib.qpb_measure_copy.argtypes = [C.c_int, i64, C.POINTER(dbl)]
     for name in EXPORTED:
@@ -301,6 +305,15 @@ class Context:
         ms, n = C.c_double(), C.c_int64()
         self._check(self.lib.qpb_get_timer(self.handle, int(which), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def scatter_block(self, dev_ptr: int, cell0: int, count: int):
+        self._check(self.lib.qpb_scatter_block(self.handle, C.c_void_p(int(dev_ptr)), int(cell0), int(count)))
+
+    def gather_block(self, dev_ptr: int, cell0: int, count: int):
+        self._check(self.lib.qpb_gather_block(self.handle, C.c_void_p(int(dev_ptr)), int(cell0), int(count)))
+
+    def add_generation(self, scale: float, rate: float):
+        self._check(self.lib.qpb_add_generation(self.handle, float(scale), float(rate)))
 
     def device_ptr(self, which: int):
         p, n = C.c_void_p(), C.c_int64()

@@ -193,6 +193,55 @@ int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out) {
     return QPB_OK;
 }
 
+// ---- block <-> dense conversion for the energy-sharded / cell-sharded exchange -----------------------------
+namespace {
+__global__ void k_block(int ne, int count, int ncd, int cell0, double *__restrict__ block, double *__restrict__ dense,
+                        const int32_t *__restrict__ c2d, int to_dense) {
+    const long long total = (long long)ne * count;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(g / count);
+        const int q = (int)(g - (long long)i * count);
+        const long long d = (long long)i * ncd + c2d[cell0 + q];
+        if (to_dense) dense[d] = block[g];
+        else block[g] = dense[d];
+    }
+}
+}  // namespace
+
+static int block_call(qpb_ctx *c, double *d_block, int cell0, int count, int to_dense) {
+    if (!c || !d_block || cell0 < 0 || count < 0 || cell0 + count > c->cfg.ncell || !c->have_geom) {
+        qpb_set_error("qpb_scatter/gather_block: bad arguments (cell0=%d count=%d)", cell0, count);
+        return QPB_E_INVALID;
+    }
+    QPB_CUDA(cudaSetDevice(c->cfg.device));
+    if (count == 0) return QPB_OK;
+    const long long total = (long long)c->cfg.ne * count;
+    k_block<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(c->cfg.ne, count, c->ncd, cell0, d_block, c->d_S,
+                                                                  c->d_cell2dense, to_dense);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_scatter_block(qpb_ctx *c, const double *d_block, int32_t cell0, int32_t count) {
+    return block_call(c, const_cast<double *>(d_block), cell0, count, 1);
+}
+
+extern "C" int qpb_gather_block(qpb_ctx *c, double *d_block, int32_t cell0, int32_t count) {
+    return block_call(c, d_block, cell0, count, 0);
+}
+
+extern "C" int qpb_add_generation(qpb_ctx *c, double scale, double rate) {
+    if (!c || !c->have_geom) {
+        qpb_set_error("qpb_add_generation: context without geometry");
+        return QPB_E_INVALID;
+    }
+    QPB_CUDA(cudaSetDevice(c->cfg.device));
+    return qpbk_add_generation(c, scale, rate, nullptr);
+}
+
 // ---- roofline denominators ------------------------------------------------------------------------------
 namespace {
 __global__ void k_fp64_peak(double *out, int iters) {
