@@ -33,22 +33,38 @@ UNIT = "updates/s"
 # ----------------------------------------------------------------------------------------------------------
 # workload
 # ----------------------------------------------------------------------------------------------------------
-def c2_workload(tile: int = 1, ny: int = 256, nx: int = 256, ne: int = 128):
+def c2_workload(tile_y: int = 1, tile_x: int = 1, ny: int = 256, nx: int = 256, ne: int = 128):
+    """BASELINE configs[1]; tile_y x tile_x copies of the 256 x 256 mask side by side for the weak-scaling runs
+    (the copies touch, so the tiled mask is one connected domain with longer rows and columns)."""
     import cases
 
     base = cases.meander_mask(ny, nx, pad=8, slot=4, pitch=16, gap_len=32)
-    mask = np.concatenate([base] * tile, axis=1) if tile > 1 else base
-    field = cases.gaussian_field(mask, cx=0.4 / tile, cy=0.5, sigma=0.05, base=1e-4, amp=2e-4)
+    mask = np.tile(base, (tile_y, tile_x))
+    if tile_x > 1:   # connect neighbouring copies through their padding columns at mid height of every copy
+        for ty in range(tile_y):
+            r = ty * ny + ny // 2
+            mask[r - 4:r + 4, :] |= True
+            mask[r - 4:r + 4, :8] = False
+            mask[r - 4:r + 4, -8:] = False
+    if tile_y > 1:
+        for tx in range(tile_x):
+            c = tx * nx + nx // 2
+            mask[:, c - 4:c + 4] |= True
+            mask[:8, c - 4:c + 4] = False
+            mask[-8:, c - 4:c + 4] = False
+    field = cases.gaussian_field(mask, cx=0.4 / tile_x, cy=0.5 / tile_y, sigma=0.05, base=1e-4, amp=2e-4)
     return dict(
-        name=f"C2 meander {ny}x{nx * tile} x {ne} bins", mask=mask, bc="short_absorbing", initial_field=field,
+        name=f"C2 meander {ny * tile_y}x{nx * tile_x} x {ne} bins", mask=mask, bc="short_absorbing", initial_field=field,
         diffusion_coefficient=cases.D0, dt=0.5, dx=1.0, energy_gap=cases.GAP, energy_min_factor=1.0,
         energy_max_factor=5.0, num_energy_bins=ne, dynes_gamma=cases.GAMMA, tau_0=cases.TAU, T_c=cases.TC,
         bath_temperature=cases.TBATH, pulse_rate=3e-8, pulse_start=0.0, pulse_duration=5.0,
     )
 
 
-def build_tables(w, Q):
+def build_tables(w, Q=None):
     """Host-side setup shared by the device-resident run and the CPU baseline."""
+    if Q is None:
+        import qpsim_b200 as Q
     mask = w["mask"]
     n = int(mask.sum())
     E, dE = Q.build_energy_grid(w["energy_gap"], w["energy_min_factor"], w["energy_max_factor"], w["num_energy_bins"])
@@ -314,7 +330,10 @@ def run_reference(args):
         return
     import qpsim_b200 as Q
 
-    w = c2_workload(tile=max(1, args.gpus))
+    from qpsim_b200.multigpu import weak_tiling
+
+    ty, tx = weak_tiling(max(1, args.gpus))
+    w = c2_workload(tile_y=ty, tile_x=tx)
     tabs = build_tables(w, Q)
     vals = []
     last = None

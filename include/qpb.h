@@ -194,6 +194,11 @@ int qpb_device_ptr(qpb_ctx *ctx, int which, void **ptr, int64_t *bytes);
 int qpb_scatter_block(qpb_ctx *ctx, const double *d_block, int32_t cell0, int32_t count);
 int qpb_gather_block(qpb_ctx *ctx, double *d_block, int32_t cell0, int32_t count);
 int qpb_add_generation(qpb_ctx *ctx, double scale, double rate);
+/* Enqueue all further work of the context on the caller's CUDA stream (a cudaStream_t; NULL = back to the stream
+ * the library created).  The host driver passes the stream its NCCL calls are ordered against, so stages and
+ * exchanges need no host synchronisation between them.  scatter/gather_block and add_generation are stream
+ * ordered (no host sync); every call that returns data to the host synchronises that stream. */
+int qpb_set_stream(qpb_ctx *ctx, void *cuda_stream);
 
 #ifdef __cplusplus
 }

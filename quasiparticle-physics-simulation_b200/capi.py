@@ -77,7 +77,7 @@ EXPORTED = [
     "qpb_set_state", "qpb_get_state", "qpb_get_integrated", "qpb_advance", "qpb_collide", "qpb_diffuse",
     "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
     "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
-    "qpb_add_generation",
+    "qpb_add_generation", "qpb_set_stream",
 ]
 
 
@@ -158,6 +158,7 @@ def load_library():
     lib.qpb_scatter_block.argtypes = [vp, vp, i32, i32]
     lib.qpb_gather_block.argtypes = [vp, vp, i32, i32]
     lib.qpb_add_generation.argtypes = [vp, dbl, dbl]
+    lib.qpb_set_stream.argtypes = [vp, vp]
     lib.qpb_measure_fp64.argtypes = [C.c_int, C.POINTER(dbl)]
     lib.qpb_measure_copy.argtypes = [C.c_int, i64, C.POINTER(dbl)]
     for name in EXPORTED:
@@ -314,6 +315,9 @@ class Context:
 
     def add_generation(self, scale: float, rate: float):
         self._check(self.lib.qpb_add_generation(self.handle, float(scale), float(rate)))
+
+    def set_stream(self, cuda_stream: int | None):
+        self._check(self.lib.qpb_set_stream(self.handle, C.c_void_p(int(cuda_stream)) if cuda_stream else None))
 
     def device_ptr(self, which: int):
         p, n = C.c_void_p(), C.c_int64()

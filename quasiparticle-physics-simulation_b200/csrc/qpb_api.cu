@@ -142,7 +142,8 @@ extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
             return fail(QPB_E_CUDA);                                                                   \
         }                                                                                              \
     } while (0)
-    TRYCUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    TRYCUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
     TRYCUDA(cudaEventCreate(&c->ev0));
     TRYCUDA(cudaEventCreate(&c->ev1));
     const size_t nstate = (size_t)cfg->ne * c->ncd;
@@ -194,7 +195,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     if (c->d_pauli_part) cudaFree(c->d_pauli_part);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
 
@@ -809,6 +810,13 @@ extern "C" int qpb_get_diag(qpb_ctx *c, qpb_diag *out) {
 extern "C" int qpb_synchronize(qpb_ctx *c) {
     QPB_ENTER(c);
     QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_set_stream(qpb_ctx *c, void *cuda_stream) {
+    QPB_ENTER(c);
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
     return QPB_OK;
 }
 

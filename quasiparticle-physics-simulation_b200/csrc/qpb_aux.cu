@@ -221,8 +221,7 @@ static int block_call(qpb_ctx *c, double *d_block, int cell0, int count, int to_
                                                                   c->d_cell2dense, to_dense);
     c->diag.kernel_launches++;
     QPB_CHECK_LAUNCH();
-    QPB_CUDA(cudaStreamSynchronize(c->stream));
-    return QPB_OK;
+    return QPB_OK;   // stream ordered: the caller synchronises (qpb_synchronize) or enqueues on the same stream
 }
 
 extern "C" int qpb_scatter_block(qpb_ctx *c, const double *d_block, int32_t cell0, int32_t count) {

@@ -67,7 +67,8 @@ struct Timer {
 struct qpb_ctx {
     qpb_config cfg{};
     int ncd = 0;  // dense cells ny*nx
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream every kernel of the context is enqueued on
+    cudaStream_t own_stream = nullptr;  // the stream created with the context (stream == own_stream unless qpb_set_stream)
     // geometry
     bool have_geom = false;
     std::vector<uint8_t> h_flags;

@@ -113,3 +113,47 @@ def test_mass_conserved_and_medium_meander():
     helpers.assert_close(got["state"], want["state"], "n(E,cell)")
     assert abs(got["mass"][-1] - got["mass"][0]) <= 1e-9 * got["mass"][0]
     assert got["frames_nan_outside"]
+
+
+def test_sharded_driver_on_one_gpu_matches_single_context():
+    """multigpu.DeviceStages + ShardedStepper with world = 1 (two contexts, block scatter/gather, row permutation,
+    shared stream) against qpb_advance on one context and against the oracle."""
+    from qpsim_b200 import capi
+    from qpsim_b200.multigpu import DeviceStages, ShardedProblem, ShardedStepper, ShardPlan
+    import torch
+
+    case = cases.meander_c2(ny=40, nx=48, ne=12, steps=3)
+    mask = case["mask"]
+    edges = Q.extract_edge_segments(mask)
+    bcs = cases.make_bcs(edges, case["bc"], Q.BoundaryCondition)
+    bcx, bcy, src = Q.compile_boundaries(mask, edges, bcs, case["dx"])
+    E, dE = Q.build_energy_grid(case["energy_gap"], 1.0, case["energy_max_factor"], case["num_energy_bins"])
+    rho = Q.density_of_states(E, case["energy_gap"], case["dynes_gamma"])
+    om, idd, ids, sg = Q.phonon_frequency_map(E)
+    n = int(mask.sum())
+    state = (rho / (rho.sum() * dE))[:, None] * case["initial_field"][mask][None, :]
+    phon = Q.thermal_phonon_occupation(om, case["bath_temperature"])[:, None] * np.ones((1, n))
+    D = case["diffusion_coefficient"] * np.sqrt(np.maximum(0.0, 1.0 - (case["energy_gap"] / E) ** 2))
+    Kr = Q.recombination_kernel_base(E, case["energy_gap"], case["tau_0"], case["T_c"])
+    Ks = Q.scattering_kernel_base(E, case["energy_gap"], case["tau_0"], case["T_c"])
+    prob = ShardedProblem(mask=mask, bcx=bcx, bcy=bcy, src=src, dx=case["dx"], dE=dE, D=D, variable_D=False,
+                          rho=rho[None], Kr=Kr[None], Ks=Ks[None], gap_id=None, idx_diff=idd, idx_sum=ids, sign=sg,
+                          nw=om.size, state=state, phonons=phon)
+    plan = ShardPlan(E.size, n, 1, 0, interleave=True)
+    stages = DeviceStages(plan, prob, 0, case["dt"])
+    g = case["generation"]
+    with torch.cuda.stream(stages.stream):
+        st = ShardedStepper(plan, stages, diffusion=True, collisions=True)
+        t, recs = 0.0, []
+        for _ in range(3):
+            rate = g["pulse_rate"] if g["pulse_start"] <= t < g["pulse_start"] + g["pulse_duration"] else None
+            recs.append(st.step(case["dt"], 0, rate, want_pauli=True))
+            t += case["dt"]
+        got = st.gather_state()
+        merged = st.merge_pauli(recs)
+    stages.close()
+    want = helpers.run_oracle(case)
+    helpers.assert_close(got, want["state"][-1], "sharded n(E,cell)")
+    single = helpers.run_dropin(case)
+    helpers.assert_close(got, single["state"][-1], "sharded vs single context", rtol=1e-12)
+    assert all(m[2] == -1 and 0.0 < m[0] < 1.0 for m in merged)
