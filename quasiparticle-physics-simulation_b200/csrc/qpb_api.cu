@@ -75,10 +75,13 @@ void qpbk_free_slot(DiffSlot &s) {
     dev_free(s.d_src);
     dev_free(s.fx.d_cls);
     dev_free(s.fx.d_tab);
+    dev_free(s.fx.d_tabg);
+    dev_free(s.fy.d_tabg);
     dev_free(s.fy.d_cls);
     dev_free(s.fy.d_tab);
     s.ready = false;
     s.fast = false;
+    s.pipe = PipePlan();
 }
 
 extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
@@ -160,6 +163,8 @@ extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
         TRY(dev_alloc(&c->d_bcx, (size_t)c->ncd));
         TRY(dev_alloc(&c->d_bcy, (size_t)c->ncd));
         TRY(dev_alloc(&c->d_srcgeom, (size_t)c->ncd));
+        TRY(dev_alloc(&c->d_cx, (size_t)c->ncd));
+        TRY(dev_alloc(&c->d_cy, (size_t)c->ncd));
         TRY(dev_alloc(&c->d_res, (size_t)c->maxit * cfg->ne));
         TRY(dev_alloc(&c->d_unorm, (size_t)c->maxit * cfg->ne));
         TRY(dev_alloc(&c->d_done, 2 * (size_t)cfg->ne));
@@ -184,7 +189,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     qpbk_free_slot(c->slot[0]);
     qpbk_free_slot(c->slot[1]);
-    dev_free(c->d_flags); dev_free(c->d_bcx); dev_free(c->d_bcy); dev_free(c->d_srcgeom);
+    dev_free(c->d_cx); dev_free(c->d_cy); dev_free(c->d_flags); dev_free(c->d_bcx); dev_free(c->d_bcy); dev_free(c->d_srcgeom);
     dev_free(c->d_cell2dense); dev_free(c->d_Dcell); dev_free(c->d_S); dev_free(c->d_B);
     dev_free(c->d_T1); dev_free(c->d_T2); dev_free(c->d_res); dev_free(c->d_unorm); dev_free(c->d_done);
     dev_free(c->d_Kr); dev_free(c->d_Ks); dev_free(c->d_KrT); dev_free(c->d_KsT); dev_free(c->d_rho);

@@ -31,6 +31,15 @@ void qpb_set_error(const char *fmt, ...);
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// launch plan of the persistent TMA-pipelined sweeps (qpb_sweep_pipe.cu)
+struct PipePlan {
+    bool x_ok = false, y_ok = false;
+    int nsm = 148;
+    int x_qp = 0, x_ns = 0, x_tpb = 0;      // lanes per row (power of two), input stages, tiles per bin
+    int y_cw = 0, y_ns = 0, y_tpb = 0;      // columns per strip, input stages, tiles per bin
+    std::vector<unsigned char> xmaps, ymaps;  // host copies of the CUtensorMap triples
+};
+
 // one prepared Crank-Nicolson solve (a step length)
 struct DiffSlot {
     bool ready = false;
@@ -52,11 +61,13 @@ struct DiffSlot {
     struct FastDir {
         int n = 0, S = 0, Q = 0, npad = 0, nclass = 0;
         int *d_cls = nullptr;      // class of every line
-        double *d_tab = nullptr;   // [ne][jmax][nclass][npad] pivot reciprocals (x: chunk-interleaved)
+        double *d_tab = nullptr;   // [ne][jmax][nclass][npad] pivot reciprocals m (x: chunk-interleaved), 0 outside the mask
+        double *d_tabg = nullptr;  // same layout: g_t = e_{t+1} m_t
         bool use_tma = false;      // x sweep staged by TMA (nx % 16 == 0, nx <= 512)
         std::vector<unsigned char> tma;  // host copy of the CUtensorMap triple passed as a kernel parameter
     } fx, fy;
     bool fast = false;
+    PipePlan pipe;
 };
 
 struct Timer {
@@ -76,6 +87,7 @@ struct qpb_ctx {
     std::vector<int32_t> h_cell2dense;
     uint8_t *d_flags = nullptr;      // [ncd]
     double *d_bcx = nullptr, *d_bcy = nullptr, *d_srcgeom = nullptr;  // [ncd]
+    double *d_cx = nullptr, *d_cy = nullptr;  // [ncd] linked neighbours along x / y + boundary diagonal (0 outside the mask)
     int32_t *d_cell2dense = nullptr; // [ncell]
     bool thin_x = false, thin_y = false;  // no links along y / along x anywhere
     bool commuting = false;
@@ -126,6 +138,8 @@ int qpbk_sweep_generic(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
 int qpbk_diffuse(qpb_ctx *c, DiffSlot &s);
 int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s);
 int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
+int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p);
+int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter);
 void qpbk_free_slot(DiffSlot &s);
 
 int qpbk_collide(qpb_ctx *c, double dt);

@@ -35,14 +35,16 @@ namespace {
 #define QPB_BCYNZ 64u
 
 // ---- pivot factorisation ---------------------------------------------------------------------------------
-// One thread per (bin, shift index, class).  geometry tables per class: lk[pos] (1 = linked to pos-1), bc[pos].
-// m_k = 1 / (sigma + rho + e_k + e_{k+1} + a*bc_k - e_k^2 m_{k-1}),  e_k = a*lk_k.
+// One thread per (bin, shift index, class).  geometry tables per class: lk[pos] (bit 0 = linked to pos-1, bit 1 = cell
+// inside the mask), bc[pos].
+// m_k = 1 / (sigma + rho + e_k + e_{k+1} + a*bc_k - e_k^2 m_{k-1}),  e_k = a*lk_k;  m_k = 0 outside the mask.
+// g_k = e_{k+1} m_k (the multiplier of the scaled recurrences in qpb_sweep_pipe.cu), same layout, optional.
 // interleave > 0 stores position k at ((k%S)/2 * Q + k/S)*2 + k%2 (16-byte units of a chunk side by side across
 // chunks, for coalesced 128-bit loads by lanes that own adjacent chunks).
 __global__ void k_factor(int ne, int jmax, int nclass, int npad, int S, int interleave, double sigma,
                          const double *__restrict__ a_bin, const double *__restrict__ shift,
                          const int *__restrict__ jlen, const uint8_t *__restrict__ lk, const double *__restrict__ bc,
-                         double *__restrict__ tab) {
+                         double *__restrict__ tab, double *__restrict__ tabg) {
     const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long total = (long long)ne * jmax * nclass;
     if (gid >= total) return;
@@ -55,14 +57,16 @@ __global__ void k_factor(int ne, int jmax, int nclass, int npad, int S, int inte
     const uint8_t *l = lk + (size_t)cls * (npad + 1);
     const double *g = bc + (size_t)cls * npad;
     double *out = tab + (size_t)gid * npad;
+    double *outg = tabg ? tabg + (size_t)gid * npad : nullptr;
     const int Q = npad / S;
     double mprev = 0.0;
     for (int k = 0; k < npad; ++k) {
-        const double e = l[k] ? a : 0.0, en = l[k + 1] ? a : 0.0;
-        const double m = 1.0 / (sigma + rho + e + en + a * g[k] - e * e * mprev);
+        const double e = (l[k] & 1) ? a : 0.0, en = (l[k + 1] & 1) ? a : 0.0;
+        const double m = (l[k] & 2) ? 1.0 / (sigma + rho + e + en + a * g[k] - e * e * mprev) : 0.0;
         mprev = m;
         const int pos = interleave ? (((k % S) / 2) * Q + k / S) * 2 + (k & 1) : k;
         out[pos] = m;
+        if (outg) outg[pos] = en * m;
     }
 }
 
@@ -605,7 +609,7 @@ ClassInfo build_classes(const qpb_ctx *c, int dir, int npad, bool add_cross) {
             const int p = dir == 0 ? l * nx + k : k * nx + l;
             const unsigned f = c->h_flags[p];
             if (!(f & QPB_IN)) continue;
-            lk[k] = (f & (dir == 0 ? QPB_LK_L : QPB_LK_U)) ? 1 : 0;
+            lk[k] = ((f & (dir == 0 ? QPB_LK_L : QPB_LK_U)) ? 1 : 0) | 2;   // bit 1: inside the mask
             bc[k] = dir == 0 ? c->h_bcx[p] : c->h_bcy[p];
             if (add_cross) bc[k] += dir == 0 ? c->h_bcy[p] : c->h_bcx[p];
         }
@@ -641,18 +645,19 @@ int next_pow2(int v) {
 // kept in FastDir (n = line length, S, Q, npad, nclass).
 static size_t cls_bytes(int nlines) { return ((sizeof(int) * (size_t)nlines + 255) / 256) * 256; }
 
-static int setup_dir(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir, bool direct, bool interleave) {
+static int setup_dir(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir, bool direct, bool interleave,
+                     bool pipe = false) {
     const auto &cf = c->cfg;
     const int n = dir == 0 ? cf.nx : cf.ny;
     const int nlines = dir == 0 ? cf.ny : cf.nx;
     fd.n = n;
-    fd.S = pick_S(n, dir);
+    fd.S = pipe ? 16 : pick_S(n, dir);
     fd.Q = (n + fd.S - 1) / fd.S;
     fd.npad = fd.Q * fd.S;
     ClassInfo ci = build_classes(c, dir, fd.npad, direct);
     fd.nclass = ci.nclass;
     const size_t tab_elems = (size_t)cf.ne * s.jmax * ci.nclass * fd.npad;
-    if (tab_elems * sizeof(double) > ((size_t)6 << 30)) return 1;  // irregular geometry: not worth tabulating
+    if (tab_elems * sizeof(double) * (pipe ? 2 : 1) > ((size_t)6 << 30)) return 1;  // irregular geometry: not worth tabulating
     const size_t cb = cls_bytes(nlines);
     char *blob = nullptr;
     QPB_CUDA(cudaMalloc((void **)&blob, cb + ci.lk.size()));
@@ -663,10 +668,11 @@ static int setup_dir(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir, bo
     QPB_CUDA(cudaMalloc((void **)&d_bc, sizeof(double) * ci.bc.size()));
     QPB_CUDA(cudaMemcpy(d_bc, ci.bc.data(), sizeof(double) * ci.bc.size(), cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMalloc((void **)&fd.d_tab, sizeof(double) * tab_elems));
+    if (pipe) QPB_CUDA(cudaMalloc((void **)&fd.d_tabg, sizeof(double) * tab_elems));
     const long long total = (long long)cf.ne * s.jmax * ci.nclass;
     k_factor<<<(int)ceil_div64(total, 64), 64, 0, c->stream>>>(cf.ne, s.jmax, ci.nclass, fd.npad, fd.S, interleave ? 1 : 0,
                                                               direct ? 1.0 : 0.5, s.d_a, s.d_shift, s.d_jlen,
-                                                              (const uint8_t *)(blob + cb), d_bc, fd.d_tab);
+                                                              (const uint8_t *)(blob + cb), d_bc, fd.d_tab, fd.d_tabg);
     c->diag.kernel_launches++;
     QPB_CHECK_LAUNCH();
     QPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -737,11 +743,25 @@ int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s) {
         if (c->h_bcy[p] != 0.0) fl[p] |= QPB_BCYNZ;
     }
     QPB_CUDA(cudaMemcpy(c->d_flags, fl.data(), c->ncd, cudaMemcpyHostToDevice));
+    {   // per-cell doubles of the select-free sweeps: linked neighbours + boundary diagonal, 0 outside the mask
+        std::vector<double> cx(c->ncd, 0.0), cy(c->ncd, 0.0);
+        for (int p = 0; p < c->ncd; ++p) {
+            const unsigned f = c->h_flags[p];
+            if (!(f & QPB_IN)) continue;
+            cx[p] = ((f & QPB_LK_L) ? 1.0 : 0.0) + ((f & QPB_LK_R) ? 1.0 : 0.0) + c->h_bcx[p];
+            cy[p] = ((f & QPB_LK_U) ? 1.0 : 0.0) + ((f & QPB_LK_D) ? 1.0 : 0.0) + c->h_bcy[p];
+        }
+        QPB_CUDA(cudaMemcpy(c->d_cx, cx.data(), sizeof(double) * c->ncd, cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(c->d_cy, cy.data(), sizeof(double) * c->ncd, cudaMemcpyHostToDevice));
+    }
     int rc;
+    const bool no_pipe = getenv("QPB_NO_PIPE") && getenv("QPB_NO_PIPE")[0] == '1';
     if (s.mode == 0) {
-        if ((rc = setup_dir(c, s, s.fx, 0, false, true)) < 0) return rc;
+        const bool px = !no_pipe && cf.nx % 16 == 0 && cf.nx <= 512;
+        const bool py = !no_pipe && cf.nx % 2 == 0 && cf.ny <= 512;
+        if ((rc = setup_dir(c, s, s.fx, 0, false, true, px)) < 0) return rc;
         if (rc > 0) return QPB_OK;
-        if ((rc = setup_dir(c, s, s.fy, 1, false, false)) < 0) return rc;
+        if ((rc = setup_dir(c, s, s.fy, 1, false, false, py)) < 0) return rc;
         if (rc > 0) return QPB_OK;
     } else if (s.mode == 1) {
         if ((rc = setup_dir(c, s, s.fx, 0, true, true)) != 0) return rc < 0 ? rc : QPB_OK;
@@ -750,6 +770,9 @@ int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s) {
     }
     if (s.mode != 2) setup_tma(c, s);
     s.fast = true;
+    if ((rc = qpbp_plan(c, s, s.pipe)) != QPB_OK) return rc;
+    // the old y kernel holds at most 16 chunks per column: a 16-row chunking of longer columns needs the pipelined kernel
+    if (s.mode == 0 && !s.pipe.y_ok && s.fy.S == 16 && s.fy.Q > 16) s.fast = false;
     return QPB_OK;
 }
 
@@ -814,6 +837,8 @@ static int dispatch_x(qpb_ctx *c, const SweepArgs &A) {
 }
 
 int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode) {
+    if (mode == 0 && dir == 0 && s.pipe.x_ok) return qpbp_sweep(c, s, 0, iter);
+    if (mode == 1 && dir == 1 && s.pipe.y_ok) return qpbp_sweep(c, s, 1, iter);
     const auto &cf = c->cfg;
     const DiffSlot::FastDir &fd = dir == 0 ? s.fx : s.fy;
     const int nlines = dir == 0 ? cf.ny : cf.nx;

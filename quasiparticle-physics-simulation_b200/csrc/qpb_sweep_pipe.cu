@@ -1,0 +1,726 @@
+// Persistent, TMA-pipelined tridiagonal sweeps (the hot diffusion kernels for uniform D, lines up to 512 cells).
+//
+// Same linear algebra as qpb_sweep_fast.cu / qpb_diffusion.cu (one Peaceman-Rachford half step per launch:
+// solver.py:1428-1452 restated as batched x / y tridiagonal solves), reorganised so that the kernel is bound by
+// HBM and not by instruction issue or load latency:
+//
+//  * one persistent CTA per SM (8 warps, the whole register file) walks a static list of tiles (bin, block of
+//    lines).  A ring of NS input stages is kept full with TMA (cp.async.bulk.tensor + mbarrier complete_tx): at the
+//    top of iteration k one elected thread issues the loads of tile k+NS-1 into the stage that iteration k-1
+//    released; results leave through a double-buffered shared-memory tile and a TMA store.  Loads of tiles
+//    k+1..k+NS-1, the solve of tile k and the store of tile k-1 overlap.
+//  * the sweeps contain no selects, bit tests or divisions: the geometry enters as two per-cell doubles
+//    (cx, cy = number of linked neighbours + boundary diagonal, 0 outside the mask; cells outside the mask hold
+//    u = 0, so  sum over linked neighbours of (u0 - u_nb) = c*u0 - u_left - u_right ) and the LU factors come from
+//    tables  m_t = 1/pivot  (0 outside the mask) and  g_t = e_{t+1} m_t  factored once per prepared step.
+//  * scaled Thomas recurrences   y~_t = d_t + g_{t-1} y~_{t-1},   x_t = m_t y~_t + g_t x_{t+1}:  2 FP64 operations
+//    per cell and direction; a thread owns a 16-cell chunk, chunk carries are affine maps composed by a
+//    warp-shuffle scan (x sweep) or through shared memory (y sweep), then added back as a geometric correction.
+//
+// Traffic per cell*bin: x sweep reads u (+2 halo rows per 16) and b, writes u*; y sweep reads u* and u, writes u.
+#include "qpb_internal.h"
+
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
+namespace {
+
+constexpr int S = 16;            // cells per chunk
+constexpr int NCONS = 256;       // consumer threads
+constexpr int NTHREADS = NCONS;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_expect(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void cons_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NCONS) : "memory"); }
+
+// Inclusive Kogge-Stone scan of affine maps over WIDTH adjacent lanes; returns the carry entering this lane's chunk.
+template <int WIDTH, bool REVERSE>
+__device__ __forceinline__ double warp_carry(double A, double B, int q) {
+#pragma unroll
+    for (int off = 1; off < WIDTH; off <<= 1) {
+        const double Ao = REVERSE ? __shfl_down_sync(0xffffffffu, A, off, WIDTH) : __shfl_up_sync(0xffffffffu, A, off, WIDTH);
+        const double Bo = REVERSE ? __shfl_down_sync(0xffffffffu, B, off, WIDTH) : __shfl_up_sync(0xffffffffu, B, off, WIDTH);
+        const bool has = REVERSE ? (q + off < WIDTH) : (q >= off);
+        if (has) {
+            B = fma(A, Bo, B);
+            A = A * Ao;
+        }
+    }
+    const double prev = REVERSE ? __shfl_down_sync(0xffffffffu, B, 1, WIDTH) : __shfl_up_sync(0xffffffffu, B, 1, WIDTH);
+    const bool first = REVERSE ? (q == WIDTH - 1) : (q == 0);
+    return first ? 0.0 : prev;
+}
+
+struct PipeArgs {
+    int ne, ny, nx, iter, jmax;
+    double tol;
+    const double *cx, *cy;       // dense geometry doubles
+    const uint8_t *flags;        // dense flag bytes (QPB_IN = 16)
+    const double *a_bin, *shift;
+    const int *jlen;
+    const int *cls;              // class of every line
+    const double *tabm, *tabg;   // [ne][jmax][nclass][npad]
+    int nclass, npad, Q;         // Q = chunks per line
+    int tiles_per_bin, ntiles;
+    unsigned long long *res, *unorm;
+    int *done, *iters_out;
+};
+
+struct XMaps {
+    CUtensorMap u, b, out;
+};
+struct YMaps {
+    CUtensorMap u, w, out;
+};
+
+// MODE 0 (x sweep): a bin is active until it is marked done.  MODE 1 (y sweep): additionally the residual that the
+// x sweep of this iteration measured decides; the first tile of a bin records the decision.
+template <int MODE>
+__device__ __forceinline__ bool tile_active(const PipeArgs &A, int bin, bool leader) {
+    if (A.done[bin]) return false;
+    if (MODE == 1) {
+        const double r = __longlong_as_double((long long)A.res[(long long)A.iter * A.ne + bin]);
+        const double un = __longlong_as_double((long long)A.unorm[(long long)A.iter * A.ne + bin]);
+        if (r <= A.tol * un) {
+            if (leader) {
+                A.iters_out[bin] = A.iter;
+                __threadfence();
+                A.done[bin] = 1;
+            }
+            return false;
+        }
+    }
+    return true;
+}
+
+// scaled Thomas solve of one 16-cell chunk held in v[]; carries resolved by the caller-provided functors
+struct ChunkSolve {
+    double v[S];
+    double g[S];
+    double m[S];
+
+    // forward, zero carry in.  Returns (A, B): carry_out = A*carry_in + B.
+    __device__ __forceinline__ void forward(double &A, double &B) {
+        double y = v[0], P = g[0];
+#pragma unroll
+        for (int t = 1; t < S; ++t) {
+            y = fma(g[t - 1], y, v[t]);
+            v[t] = y;
+            P *= g[t];
+        }
+        A = P;
+        B = g[S - 1] * y;
+    }
+    __device__ __forceinline__ void forward_fix(double carry) {
+        double c = carry;
+        v[0] += c;
+#pragma unroll
+        for (int t = 1; t < S; ++t) {
+            c *= g[t - 1];
+            v[t] += c;
+        }
+    }
+    // backward, zero carry in.  Returns B (A is the same product as in forward).
+    __device__ __forceinline__ double backward() {
+        double x = m[S - 1] * v[S - 1];
+        v[S - 1] = x;
+#pragma unroll
+        for (int t = S - 2; t >= 0; --t) {
+            x = fma(g[t], x, m[t] * v[t]);
+            v[t] = x;
+        }
+        return x;
+    }
+    __device__ __forceinline__ void backward_fix(double carry) {
+        double c = carry;
+#pragma unroll
+        for (int t = S - 1; t >= 0; --t) {
+            c *= g[t];
+            v[t] += c;
+        }
+    }
+};
+
+// =========================================================================================================
+// x sweep
+// =========================================================================================================
+// Tile = (bin, R = 256/QP consecutive rows); smem stage = u tile with one halo row above and below + b tile, both as
+// 128-byte-swizzled boxes (16 doubles | Q chunks | rows | 1 bin).  Consumer thread (g, q) owns chunk q of row g.
+template <int QP, int NS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
+    constexpr int R = NCONS / QP;
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    const int Q = A.Q;
+    const int u_bytes = ((R + 2) * Q * 128 + 1023) / 1024 * 1024;
+    const int b_bytes = (R * Q * 128 + 1023) / 1024 * 1024;
+    const int stage_bytes = u_bytes + b_bytes;
+    unsigned char *out_base = smraw + (size_t)NS * stage_bytes;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + 2 * (size_t)b_bytes);
+    const int tid = threadIdx.x;
+    const uint32_t full0 = smem_u32(bars);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(full0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // per-bin parameters of this launch, read once (the tile loop touches no global scalars)
+    double *s_a = reinterpret_cast<double *>(bars + 8);
+    double *s_rho = s_a + A.ne;
+    int *s_j = reinterpret_cast<int *>(s_rho + A.ne);
+    for (int b = tid; b < A.ne; b += NCONS) {
+        const bool act = tile_active<0>(A, b, blockIdx.x == 0);
+        const int j = A.iter % A.jlen[b];
+        s_j[b] = act ? j : -1;
+        s_a[b] = A.a_bin[b];
+        s_rho[b] = A.shift[(long long)b * A.jmax + j];
+    }
+    __syncthreads();
+    const int tpb = A.tiles_per_bin;
+    // producer cursor (thread 0 only): next tile index to load and number of loads issued
+    int pt = blockIdx.x, pk = 0;
+    auto produce = [&]() {
+        while (pt < A.ntiles) {
+            const int bin = pt / tpb;
+            if (s_j[bin] >= 0) {
+                const int y0 = (pt - bin * tpb) * R;
+                const int s = pk % NS;
+                const uint32_t dst = smem_u32(smraw + (size_t)s * stage_bytes);
+                mbar_expect(full0 + 8 * s, (uint32_t)((R + 2) * Q * 128 + R * Q * 128));
+                tma_load_4d(dst, &maps.u, full0 + 8 * s, 0, 0, y0 - 1, bin);
+                tma_load_4d(dst + u_bytes, &maps.b, full0 + 8 * s, 0, 0, y0, bin);
+                ++pk;
+                pt += gridDim.x;
+                return;
+            }
+            pt += gridDim.x;
+        }
+    };
+    if (tid == 0) {
+#pragma unroll 1
+        for (int i = 0; i < NS - 1; ++i) produce();
+    }
+    const int g = tid / QP, q = tid - g * QP;
+    const bool qok = q < Q;
+    const int qc = qok ? q : Q - 1;
+    const int nx = A.nx;
+    int k = 0;
+    int cur_y = -1;
+    double cx[S], cy[S];
+    uint4 fl4 = make_uint4(0, 0, 0, 0);
+    int cls = 0;
+    bool rowok = false;
+    for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
+        const int bin = t / tpb;
+        const int jidx = s_j[bin];
+        if (jidx < 0) continue;
+        const int y0 = (t - bin * tpb) * R;
+        const int y = y0 + g;
+        // every thread finished reading the stage of tile k-1 before the last named barrier of that iteration
+        if (tid == 0) produce();
+        if (y != cur_y) {   // geometry of this thread's chunk (constant while the CTA stays on one row block)
+            cur_y = y;
+            rowok = y < A.ny && qok;
+            const int yc = min(y, A.ny - 1);
+            cls = A.cls[yc];
+            const size_t o = (size_t)yc * nx + qc * S;
+            fl4 = *reinterpret_cast<const uint4 *>(A.flags + o);
+            const double2 *px = reinterpret_cast<const double2 *>(A.cx + o);
+            const double2 *py = reinterpret_cast<const double2 *>(A.cy + o);
+#pragma unroll
+            for (int un = 0; un < S / 2; ++un) {
+                const double2 a2 = px[un], b2 = py[un];
+                cx[2 * un] = rowok ? a2.x : 0.0;
+                cx[2 * un + 1] = rowok ? a2.y : 0.0;
+                cy[2 * un] = rowok ? b2.x : 0.0;
+                cy[2 * un + 1] = rowok ? b2.y : 0.0;
+            }
+            if (!rowok) fl4 = make_uint4(0, 0, 0, 0);
+        }
+        const double a = s_a[bin];
+        const double rho = s_rho[bin];
+        ChunkSolve ch;
+        {   // LU factors of this chunk (L2 / L1 resident table), issued before the wait on the tile
+            const size_t base = (((size_t)bin * A.jmax + jidx) * A.nclass + cls) * A.npad;
+            const double2 *pm = reinterpret_cast<const double2 *>(A.tabm + base);
+            const double2 *pg = reinterpret_cast<const double2 *>(A.tabg + base);
+#pragma unroll
+            for (int un = 0; un < S / 2; ++un) {
+                const double2 mm = pm[un * Q + qc], gg = pg[un * Q + qc];
+                ch.m[2 * un] = rowok ? mm.x : 0.0;
+                ch.m[2 * un + 1] = rowok ? mm.y : 0.0;
+                ch.g[2 * un] = rowok ? gg.x : 0.0;
+                ch.g[2 * un + 1] = rowok ? gg.y : 0.0;
+            }
+        }
+        const int s = k % NS;
+        mbar_wait(full0 + 8 * s, (k / NS) & 1);
+        const double *su = reinterpret_cast<const double *>(smraw + (size_t)s * stage_bytes);
+        const double *sb = reinterpret_cast<const double *>(smraw + (size_t)s * stage_bytes + u_bytes);
+        int rhi = 0, uhi = 0;
+        {
+            const int rb = g * Q + qc;              // 128-byte row index in the b tile
+            const int ru = (g + 1) * Q + qc;        // in the u tile (one halo row on top)
+            const double2 *pb = reinterpret_cast<const double2 *>(sb + (size_t)rb * S);
+            const double2 *pc = reinterpret_cast<const double2 *>(su + (size_t)ru * S);
+            const double2 *pu = reinterpret_cast<const double2 *>(su + (size_t)(ru - Q) * S);
+            const double2 *pd = reinterpret_cast<const double2 *>(su + (size_t)(ru + Q) * S);
+            const int swb = rb & 7, swc = ru & 7, swu = (ru - Q) & 7, swd = (ru + Q) & 7;
+            double uc[S];
+#pragma unroll
+            for (int un = 0; un < S / 2; ++un) {
+                const double2 tq = pc[un ^ swc];
+                uc[2 * un] = qok ? tq.x : 0.0;
+                uc[2 * un + 1] = qok ? tq.y : 0.0;
+            }
+            double ul = __shfl_up_sync(0xffffffffu, uc[S - 1], 1, QP);
+            double ur = __shfl_down_sync(0xffffffffu, uc[0], 1, QP);
+            if (q == 0) ul = 0.0;
+            if (q == QP - 1) ur = 0.0;
+            const double rm = rho - 0.5, rp = rho + 0.5;
+            const unsigned flw[4] = {fl4.x, fl4.y, fl4.z, fl4.w};
+#pragma unroll
+            for (int un = 0; un < S / 2; ++un) {
+                const double2 tu = pu[un ^ swu], td = pd[un ^ swd], tb = pb[un ^ swb];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int tt = 2 * un + h;
+                    const double u0 = uc[tt];
+                    const double uu = h == 0 ? tu.x : tu.y, ud = h == 0 ? td.x : td.y, bv = h == 0 ? tb.x : tb.y;
+                    const double left = tt == 0 ? ul : uc[tt - 1], right = tt == S - 1 ? ur : uc[tt + 1];
+                    const double cross = fma(cy[tt], u0, -uu) - ud;
+                    const double along = fma(cx[tt], u0, -left) - right;
+                    const double d = fma(-a, cross, fma(rm, u0, bv));      // b - (V - rho) u
+                    ch.v[tt] = d;
+                    const double rres = fma(-a, along, fma(-rp, u0, d));   // b - A u
+                    const int rh = __double2hiint(rres) & 0x7fffffff;
+                    if (flw[tt >> 2] & (16u << (8 * (tt & 3)))) rhi = max(rhi, rh);
+                    uhi = max(uhi, __double2hiint(u0) & 0x7fffffff);
+                }
+            }
+        }
+        {
+            rhi = __reduce_max_sync(0xffffffffu, rhi);
+            uhi = __reduce_max_sync(0xffffffffu, uhi);
+            if ((tid & 31) == 0) {
+                // high words only: the residual norm is rounded up, the solution norm down (both conservative)
+                atomicMax(&A.res[(long long)A.iter * A.ne + bin], ((unsigned long long)(unsigned)(rhi + (rhi ? 1 : 0))) << 32);
+                atomicMax(&A.unorm[(long long)A.iter * A.ne + bin], ((unsigned long long)(unsigned)uhi) << 32);
+            }
+        }
+        double Am, Bm;
+        ch.forward(Am, Bm);
+        const double yin = warp_carry<QP, false>(Am, Bm, q);
+        ch.forward_fix(yin);
+        Bm = ch.backward();
+        const double xin = warp_carry<QP, true>(Am, Bm, q);
+        ch.backward_fix(xin);
+        // ---- out tile ----
+        const int ob = k & 1;
+        double *so = reinterpret_cast<double *>(out_base + (size_t)ob * b_bytes);
+        cons_bar(1);   // thread 0 has seen the store of tile k-2 finish reading this buffer
+        if (qok) {
+            const int rb = g * Q + q;
+            double2 *dst = reinterpret_cast<double2 *>(so + (size_t)rb * S);
+            const int swb = rb & 7;
+#pragma unroll
+            for (int un = 0; un < S / 2; ++un) dst[un ^ swb] = make_double2(ch.v[2 * un], ch.v[2 * un + 1]);
+        }
+        fence_async_smem();
+        cons_bar(2);
+        if (tid == 0) {
+            tma_store_4d(&maps.out, smem_u32(so), 0, 0, y0, bin);
+            bulk_commit();
+            bulk_wait_read<1>();
+        }
+        ++k;
+    }
+    if (tid == 0) bulk_wait_read<0>();
+}
+
+// =========================================================================================================
+// y sweep
+// =========================================================================================================
+// Tile = (bin, strip of CW columns, all rows).  smem stage = u strip + u* strip as [npad rows][CW] (no swizzle:
+// the CW lanes of a row read one contiguous segment).  Consumer thread (q, c): chunk q (16 rows) of column c.
+template <int CW, int NS>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
+    constexpr int NCH = NCONS / CW;   // chunk slots per column
+    extern __shared__ __align__(1024) unsigned char smraw[];
+    const int Q = A.Q;                // real chunks per column (<= NCH)
+    const int npad = A.npad;
+    const int strip_bytes = (npad * CW * 8 + 127) / 128 * 128;
+    const int stage_bytes = 2 * strip_bytes;
+    unsigned char *out_base = smraw + (size_t)NS * stage_bytes;
+    double *carry = reinterpret_cast<double *>(out_base + 2 * (size_t)strip_bytes);   // [2][NCH][CW]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * NCH * CW);
+    const int tid = threadIdx.x;
+    const uint32_t full0 = smem_u32(bars);
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(full0 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // per-bin parameters of this launch, read once (the tile loop touches no global scalars)
+    double *s_a = reinterpret_cast<double *>(bars + 8);
+    double *s_rho = s_a + A.ne;
+    int *s_j = reinterpret_cast<int *>(s_rho + A.ne);
+    for (int b = tid; b < A.ne; b += NCONS) {
+        const bool act = tile_active<1>(A, b, blockIdx.x == 0);
+        const int j = A.iter % A.jlen[b];
+        s_j[b] = act ? j : -1;
+        s_a[b] = A.a_bin[b];
+        s_rho[b] = A.shift[(long long)b * A.jmax + j];
+    }
+    __syncthreads();
+    const int tpb = A.tiles_per_bin;
+    const int nbox = (npad + 255) / 256;          // TMA boxes per strip (box rows <= 256)
+    const int box_rows = npad / nbox;             // host guarantees divisibility
+    int pt = blockIdx.x, pk = 0;
+    auto produce = [&]() {
+        while (pt < A.ntiles) {
+            const int bin = pt / tpb;
+            if (s_j[bin] >= 0) {
+                const int x0 = (pt - bin * tpb) * CW;
+                const int s = pk % NS;
+                const uint32_t dst = smem_u32(smraw + (size_t)s * stage_bytes);
+                mbar_expect(full0 + 8 * s, (uint32_t)(2 * npad * CW * 8));
+                for (int bx = 0; bx < nbox; ++bx) {
+                    tma_load_3d(dst + bx * box_rows * CW * 8, &maps.u, full0 + 8 * s, x0, bx * box_rows, bin);
+                    tma_load_3d(dst + strip_bytes + bx * box_rows * CW * 8, &maps.w, full0 + 8 * s, x0, bx * box_rows, bin);
+                }
+                ++pk;
+                pt += gridDim.x;
+                return;
+            }
+            pt += gridDim.x;
+        }
+    };
+    if (tid == 0) {
+#pragma unroll 1
+        for (int i = 0; i < NS - 1; ++i) produce();
+    }
+    const int q = tid / CW, c = tid - q * CW;
+    const bool qok = q < Q;
+    const int r0 = (qok ? q : 0) * S;
+    int k = 0;
+    for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
+        const int bin = t / tpb;
+        const int strip = t - bin * tpb;
+        const int jidx = s_j[bin];
+        if (jidx < 0) continue;
+        if (tid == 0) produce();
+        const int x0 = strip * CW;
+        const int x = min(x0 + c, A.nx - 1);
+        const double rho2 = 2.0 * s_rho[bin];
+        ChunkSolve ch;
+        {
+            const int cls = A.cls[x];
+            const size_t base = (((size_t)bin * A.jmax + jidx) * A.nclass + cls) * npad + r0;
+            const double2 *pm = reinterpret_cast<const double2 *>(A.tabm + base);
+            const double2 *pg = reinterpret_cast<const double2 *>(A.tabg + base);
+#pragma unroll
+            for (int un = 0; un < S / 2; ++un) {
+                const double2 mm = pm[un], gg = pg[un];
+                ch.m[2 * un] = qok ? mm.x : 0.0;
+                ch.m[2 * un + 1] = qok ? mm.y : 0.0;
+                ch.g[2 * un] = qok ? gg.x : 0.0;
+                ch.g[2 * un + 1] = qok ? gg.y : 0.0;
+            }
+        }
+        const int s = k % NS;
+        mbar_wait(full0 + 8 * s, (k / NS) & 1);
+        const double *su = reinterpret_cast<const double *>(smraw + (size_t)s * stage_bytes) + (size_t)r0 * CW + c;
+        const double *sw = reinterpret_cast<const double *>(smraw + (size_t)s * stage_bytes + strip_bytes) + (size_t)r0 * CW + c;
+        double uold[S];
+#pragma unroll
+        for (int tt = 0; tt < S; ++tt) {
+            uold[tt] = su[tt * CW];
+            ch.v[tt] = sw[tt * CW] - uold[tt];
+        }
+        double Am, Bm;
+        ch.forward(Am, Bm);
+        double *cA = carry, *cB = carry + NCH * CW;
+        cons_bar(1);   // previous tile's carries are consumed; also orders thread 0's wait on the store of tile k-2
+        cA[q * CW + c] = Am;
+        cB[q * CW + c] = Bm;
+        cons_bar(2);
+        double cin = 0.0;
+        for (int kk = 0; kk < q; ++kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
+        ch.forward_fix(cin);
+        Bm = ch.backward();
+        cons_bar(3);
+        cB[q * CW + c] = Bm;
+        cons_bar(4);
+        cin = 0.0;
+        for (int kk = NCH - 1; kk > q; --kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
+        ch.backward_fix(cin);
+        const int ob = k & 1;
+        double *so = reinterpret_cast<double *>(out_base + (size_t)ob * strip_bytes) + (size_t)r0 * CW + c;
+        if (qok) {
+#pragma unroll
+            for (int tt = 0; tt < S; ++tt) so[tt * CW] = fma(rho2, ch.v[tt], uold[tt]);
+        }
+        fence_async_smem();
+        cons_bar(5);
+        if (tid == 0) {
+            const uint32_t src = smem_u32(out_base + (size_t)ob * strip_bytes);
+            for (int bx = 0; bx < nbox; ++bx) tma_store_3d(&maps.out, src + bx * box_rows * CW * 8, x0, bx * box_rows, bin);
+            bulk_commit();
+            bulk_wait_read<1>();
+        }
+        ++k;
+    }
+    if (tid == 0) bulk_wait_read<0>();
+}
+
+// ---- tensor maps -------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// x: 4-D view (16 | nx/16 | ny | ne) of a dense [ne][ny][nx] array, box (16 | Q | rows | 1), 128-byte swizzle
+bool make_xmap(CUtensorMap *m, double *base, int ne, int ny, int nx, int Q, int rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[4] = {16, (cuuint64_t)(nx / 16), (cuuint64_t)ny, (cuuint64_t)ne};
+    const cuuint64_t strides[3] = {128, (cuuint64_t)nx * 8, (cuuint64_t)ny * nx * 8};
+    const cuuint32_t box[4] = {16, (cuuint32_t)Q, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// y: 3-D view (nx | ny | ne), box (CW | rows | 1), no swizzle
+bool make_ymap(CUtensorMap *m, double *base, int ne, int ny, int nx, int cw, int rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)ne};
+    const cuuint64_t strides[2] = {(cuuint64_t)nx * 8, (cuuint64_t)ny * nx * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)cw, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int next_pow2(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+constexpr int SMEM_CAP = 227 * 1024;
+
+size_t param_smem(int ne) { return (size_t)ne * 20 + 16; }
+
+template <int QP>
+size_t x_smem(int Q, int ns) {
+    constexpr int R = NCONS / QP;
+    const size_t ub = ((size_t)(R + 2) * Q * 128 + 1023) / 1024 * 1024;
+    const size_t bb = ((size_t)R * Q * 128 + 1023) / 1024 * 1024;
+    return ns * (ub + bb) + 2 * bb + 64;   // + per-bin parameters, added by the caller
+}
+
+template <int QP, int NS>
+int launch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
+    auto kern = k_sweep_x_pipe<QP, NS>;
+    static bool configured = false;
+    if (!configured) {
+        QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
+        configured = true;
+    }
+    kern<<<grid, NTHREADS, x_smem<QP>(A.Q, NS) + param_smem(A.ne), c->stream>>>(A, maps);
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+size_t y_smem(int cw, int npad, int ns) {
+    const size_t sb = ((size_t)npad * cw * 8 + 127) / 128 * 128;
+    return ns * 2 * sb + 2 * sb + sizeof(double) * 2 * (NCONS / cw) * cw + 64;
+}
+
+template <int CW, int NS>
+int launch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
+    auto kern = k_sweep_y_pipe<CW, NS>;
+    static bool configured = false;
+    if (!configured) {
+        QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
+        configured = true;
+    }
+    kern<<<grid, NTHREADS, y_smem(CW, A.npad, NS) + param_smem(A.ne), c->stream>>>(A, maps);
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int pick_grid(int ntiles, int tpb, int nsm) {
+    if (ntiles <= nsm) return ntiles;
+    // a multiple of the tiles per bin keeps every CTA on one block of lines (its geometry stays in registers)
+    if (tpb <= nsm) return (nsm / tpb) * tpb;
+    return nsm;
+}
+
+}  // namespace
+
+// ---- host side -------------------------------------------------------------------------------------------------
+int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
+    p = PipePlan();
+    const auto &cf = c->cfg;
+    if (getenv("QPB_NO_PIPE") && getenv("QPB_NO_PIPE")[0] == '1') return QPB_OK;
+    if (s.mode != 0 || !s.fast || !encode_fn()) return QPB_OK;
+    int dev = 0, nsm = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    p.nsm = nsm;
+    // x sweep: rows cut into 16-cell chunks owned by adjacent lanes (<= 32 chunks), TMA boxes of whole chunks
+    if (cf.nx % 16 == 0 && cf.nx <= 512 && s.fx.S == 16 && s.fx.d_tabg) {
+        const int Q = cf.nx / 16, QP = next_pow2(Q), R = NCONS / QP;
+        int ns = 0;
+        for (int cand = 3; cand >= 2 && !ns; --cand) {
+            size_t need = 0;
+            switch (QP) {
+                case 1: need = x_smem<1>(Q, cand); break;
+                case 2: need = x_smem<2>(Q, cand); break;
+                case 4: need = x_smem<4>(Q, cand); break;
+                case 8: need = x_smem<8>(Q, cand); break;
+                case 16: need = x_smem<16>(Q, cand); break;
+                default: need = x_smem<32>(Q, cand); break;
+            }
+            if (need + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
+        }
+        XMaps maps;
+        if (ns && make_xmap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, Q, R + 2) &&
+            make_xmap(&maps.b, c->d_B, cf.ne, cf.ny, cf.nx, Q, R) &&
+            make_xmap(&maps.out, c->d_T1, cf.ne, cf.ny, cf.nx, Q, R)) {
+            p.x_ok = true;
+            p.x_qp = QP;
+            p.x_ns = ns;
+            p.x_tpb = (cf.ny + R - 1) / R;
+            p.xmaps.resize(sizeof(XMaps));
+            memcpy(p.xmaps.data(), &maps, sizeof(XMaps));
+        }
+    }
+    // y sweep: strips of CW columns, columns cut into 16-row chunks (<= 256/CW chunks)
+    if (cf.nx % 2 == 0 && cf.ny <= 2048 && s.fy.S == 16 && s.fy.d_tabg) {
+        const int Q = s.fy.Q, npad = s.fy.npad;
+        int cw = NCONS / next_pow2(Q);
+        cw = std::min(cw, 32);
+        while (cw > 2 && cw / 2 >= cf.nx) cw /= 2;    // narrow grids: do not load columns that do not exist
+        const int nbox = (npad + 255) / 256;
+        if (cw >= 2 && npad % nbox == 0 && (npad / nbox) <= 256) {
+            int ns = 0;
+            for (int cand = 3; cand >= 2 && !ns; --cand)
+                if (y_smem(cw, npad, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
+            YMaps maps;
+            const int rows = npad / nbox;
+            if (ns && make_ymap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, cw, rows) &&
+                make_ymap(&maps.w, c->d_T1, cf.ne, cf.ny, cf.nx, cw, rows) &&
+                make_ymap(&maps.out, c->d_S, cf.ne, cf.ny, cf.nx, cw, rows)) {
+                p.y_ok = true;
+                p.y_cw = cw;
+                p.y_ns = ns;
+                p.y_tpb = (cf.nx + cw - 1) / cw;
+                p.ymaps.resize(sizeof(YMaps));
+                memcpy(p.ymaps.data(), &maps, sizeof(YMaps));
+            }
+        }
+    }
+    return QPB_OK;
+}
+
+int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter) {
+    const auto &cf = c->cfg;
+    const PipePlan &p = s.pipe;
+    const DiffSlot::FastDir &fd = dir == 0 ? s.fx : s.fy;
+    const int nlines = dir == 0 ? cf.ny : cf.nx;
+    PipeArgs A;
+    A.ne = cf.ne; A.ny = cf.ny; A.nx = cf.nx; A.iter = iter; A.jmax = s.jmax; A.tol = cf.diff_tol;
+    A.cx = c->d_cx; A.cy = c->d_cy; A.flags = c->d_flags;
+    A.a_bin = s.d_a; A.shift = s.d_shift; A.jlen = s.d_jlen;
+    A.cls = fd.d_cls;
+    (void)nlines;
+    A.tabm = fd.d_tab; A.tabg = fd.d_tabg; A.nclass = fd.nclass; A.npad = fd.npad; A.Q = fd.Q;
+    A.res = c->d_res; A.unorm = c->d_unorm; A.done = c->d_done; A.iters_out = c->d_done + cf.ne;
+    ScopedTimer tm(c, dir == 0 ? 0 : 1);
+    c->diag.kernel_launches++;
+    if (dir == 0) {
+        A.tiles_per_bin = p.x_tpb;
+        A.ntiles = p.x_tpb * cf.ne;
+        const int grid = pick_grid(A.ntiles, p.x_tpb, p.nsm);
+        const XMaps &maps = *reinterpret_cast<const XMaps *>(p.xmaps.data());
+#define QPB_X(QP)                                                      \
+    case QP:                                                           \
+        return p.x_ns == 3 ? launch_x<QP, 3>(c, A, maps, grid) : launch_x<QP, 2>(c, A, maps, grid);
+        switch (p.x_qp) {
+            QPB_X(1) QPB_X(2) QPB_X(4) QPB_X(8) QPB_X(16)
+            default: return p.x_ns == 3 ? launch_x<32, 3>(c, A, maps, grid) : launch_x<32, 2>(c, A, maps, grid);
+        }
+#undef QPB_X
+    }
+    A.tiles_per_bin = p.y_tpb;
+    A.ntiles = p.y_tpb * cf.ne;
+    const int grid = pick_grid(A.ntiles, p.y_tpb, p.nsm);
+    const YMaps &maps = *reinterpret_cast<const YMaps *>(p.ymaps.data());
+#define QPB_Y(CW)                                                      \
+    case CW:                                                           \
+        return p.y_ns == 3 ? launch_y<CW, 3>(c, A, maps, grid) : launch_y<CW, 2>(c, A, maps, grid);
+    switch (p.y_cw) {
+        QPB_Y(2) QPB_Y(4) QPB_Y(8) QPB_Y(16)
+        default: return p.y_ns == 3 ? launch_y<32, 3>(c, A, maps, grid) : launch_y<32, 2>(c, A, maps, grid);
+    }
+#undef QPB_Y
+}
