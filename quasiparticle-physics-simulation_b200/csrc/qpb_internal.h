@@ -138,6 +138,7 @@ int qpbk_sweep_generic(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
 int qpbk_diffuse(qpb_ctx *c, DiffSlot &s);
 int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s);
 int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
+int qpbp_chunk(int n, int dir);
 int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p);
 int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter);
 void qpbk_free_slot(DiffSlot &s);

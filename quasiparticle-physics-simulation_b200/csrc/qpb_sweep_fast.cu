@@ -651,7 +651,7 @@ static int setup_dir(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir, bo
     const int n = dir == 0 ? cf.nx : cf.ny;
     const int nlines = dir == 0 ? cf.ny : cf.nx;
     fd.n = n;
-    fd.S = pipe ? 16 : pick_S(n, dir);
+    fd.S = pipe ? qpbp_chunk(n, dir) : pick_S(n, dir);
     fd.Q = (n + fd.S - 1) / fd.S;
     fd.npad = fd.Q * fd.S;
     ClassInfo ci = build_classes(c, dir, fd.npad, direct);
@@ -757,8 +757,8 @@ int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s) {
     int rc;
     const bool no_pipe = getenv("QPB_NO_PIPE") && getenv("QPB_NO_PIPE")[0] == '1';
     if (s.mode == 0) {
-        const bool px = !no_pipe && cf.nx % 16 == 0 && cf.nx <= 512;
-        const bool py = !no_pipe && cf.nx % 2 == 0 && cf.ny <= 512;
+        const bool px = !no_pipe && cf.nx % 16 == 0 && qpbp_chunk(cf.nx, 0) > 0 && cf.ne <= 2048;
+        const bool py = !no_pipe && cf.nx % 2 == 0 && qpbp_chunk(cf.ny, 1) > 0 && cf.ne <= 2048;
         if ((rc = setup_dir(c, s, s.fx, 0, false, true, px)) < 0) return rc;
         if (rc > 0) return QPB_OK;
         if ((rc = setup_dir(c, s, s.fy, 1, false, false, py)) < 0) return rc;
@@ -771,8 +771,9 @@ int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s) {
     if (s.mode != 2) setup_tma(c, s);
     s.fast = true;
     if ((rc = qpbp_plan(c, s, s.pipe)) != QPB_OK) return rc;
-    // the old y kernel holds at most 16 chunks per column: a 16-row chunking of longer columns needs the pipelined kernel
-    if (s.mode == 0 && !s.pipe.y_ok && s.fy.S == 16 && s.fy.Q > 16) s.fast = false;
+    // tables chunked for the pipelined kernels cannot be walked by the older kernels: generic sweeps instead
+    if (s.mode == 0 && !s.pipe.x_ok && s.fx.d_tabg && (s.fx.S != pick_S(cf.nx, 0))) s.fast = false;
+    if (s.mode == 0 && !s.pipe.y_ok && s.fy.d_tabg && (s.fy.S != pick_S(cf.ny, 1) || s.fy.Q > 16)) s.fast = false;
     return QPB_OK;
 }
 

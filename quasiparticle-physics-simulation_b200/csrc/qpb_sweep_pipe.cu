@@ -27,9 +27,6 @@
 
 namespace {
 
-constexpr int S = 16;            // cells per chunk
-constexpr int NCONS = 256;       // consumer threads
-constexpr int NTHREADS = NCONS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -71,7 +68,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void cons_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NCONS) : "memory"); }
 
 // Inclusive Kogge-Stone scan of affine maps over WIDTH adjacent lanes; returns the carry entering this lane's chunk.
 template <int WIDTH, bool REVERSE>
@@ -133,7 +129,8 @@ __device__ __forceinline__ bool tile_active(const PipeArgs &A, int bin, bool lea
     return true;
 }
 
-// scaled Thomas solve of one 16-cell chunk held in v[]; carries resolved by the caller-provided functors
+// scaled Thomas solve of one S-cell chunk held in v[]; carries are resolved by the caller
+template <int S>
 struct ChunkSolve {
     double v[S];
     double g[S];
@@ -181,19 +178,38 @@ struct ChunkSolve {
     }
 };
 
+template <int NT>
+__device__ __forceinline__ void cta_bar(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+
+// per-bin parameters of this launch in shared memory (the tile loops touch no global scalars)
+template <int MODE, int NT>
+__device__ __forceinline__ void load_bin_params(const PipeArgs &A, double *s_a, double *s_rho, int *s_j) {
+    for (int b = threadIdx.x; b < A.ne; b += NT) {
+        const bool act = tile_active<MODE>(A, b, blockIdx.x == 0);
+        const int j = A.iter % A.jlen[b];
+        s_j[b] = act ? j : -1;
+        s_a[b] = A.a_bin[b];
+        s_rho[b] = A.shift[(long long)b * A.jmax + j];
+    }
+}
+
 // =========================================================================================================
 // x sweep
 // =========================================================================================================
-// Tile = (bin, R = 256/QP consecutive rows); smem stage = u tile with one halo row above and below + b tile, both as
-// 128-byte-swizzled boxes (16 doubles | Q chunks | rows | 1 bin).  Consumer thread (g, q) owns chunk q of row g.
-template <int QP, int NS>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// Tile = (bin, R = NT/QP consecutive rows), NT = 4096/S threads; smem stage = u tile with one halo row above and
+// below + b tile, both as 128-byte-swizzled boxes (16 doubles | nx/16 | rows | 1 bin).  Thread (g, q) owns the
+// S-cell chunk q of tile row g; the chunks of a row sit in QP adjacent lanes.
+template <int S, int QP, int NS>
+__global__ void __launch_bounds__(4096 / S, 1)
 k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
-    constexpr int R = NCONS / QP;
+    constexpr int NT = 4096 / S;
+    constexpr int R = NT / QP;
+    constexpr int UPC = S / 2;           // 16-byte units per chunk
     extern __shared__ __align__(1024) unsigned char smraw[];
-    const int Q = A.Q;
-    const int u_bytes = ((R + 2) * Q * 128 + 1023) / 1024 * 1024;
-    const int b_bytes = (R * Q * 128 + 1023) / 1024 * 1024;
+    const int Q = A.Q;                   // chunks per row
+    const int Q16 = A.nx / 16;           // 128-byte units per row
+    const int u_bytes = ((R + 2) * Q16 * 128 + 1023) / 1024 * 1024;
+    const int b_bytes = (R * Q16 * 128 + 1023) / 1024 * 1024;
     const int stage_bytes = u_bytes + b_bytes;
     unsigned char *out_base = smraw + (size_t)NS * stage_bytes;
     uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + 2 * (size_t)b_bytes);
@@ -204,17 +220,10 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         for (int s = 0; s < NS; ++s) mbar_init(full0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // per-bin parameters of this launch, read once (the tile loop touches no global scalars)
     double *s_a = reinterpret_cast<double *>(bars + 8);
     double *s_rho = s_a + A.ne;
     int *s_j = reinterpret_cast<int *>(s_rho + A.ne);
-    for (int b = tid; b < A.ne; b += NCONS) {
-        const bool act = tile_active<0>(A, b, blockIdx.x == 0);
-        const int j = A.iter % A.jlen[b];
-        s_j[b] = act ? j : -1;
-        s_a[b] = A.a_bin[b];
-        s_rho[b] = A.shift[(long long)b * A.jmax + j];
-    }
+    load_bin_params<0, NT>(A, s_a, s_rho, s_j);
     __syncthreads();
     const int tpb = A.tiles_per_bin;
     // producer cursor (thread 0 only): next tile index to load and number of loads issued
@@ -226,7 +235,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
                 const int y0 = (pt - bin * tpb) * R;
                 const int s = pk % NS;
                 const uint32_t dst = smem_u32(smraw + (size_t)s * stage_bytes);
-                mbar_expect(full0 + 8 * s, (uint32_t)((R + 2) * Q * 128 + R * Q * 128));
+                mbar_expect(full0 + 8 * s, (uint32_t)((R + 2) * Q16 * 128 + R * Q16 * 128));
                 tma_load_4d(dst, &maps.u, full0 + 8 * s, 0, 0, y0 - 1, bin);
                 tma_load_4d(dst + u_bytes, &maps.b, full0 + 8 * s, 0, 0, y0, bin);
                 ++pk;
@@ -243,11 +252,15 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
     const int g = tid / QP, q = tid - g * QP;
     const bool qok = q < Q;
     const int qc = qok ? q : Q - 1;
+    const int r16 = (qc * S) >> 4;             // 128-byte unit of this chunk within its row
+    const int ubase = ((qc * S) & 15) >> 1;    // first 16-byte unit of the chunk inside that 128-byte unit
     const int nx = A.nx;
     int k = 0;
     int cur_y = -1;
     double cx[S], cy[S];
-    uint4 fl4 = make_uint4(0, 0, 0, 0);
+    unsigned flw[S / 4];
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i) flw[i] = 0;
     int cls = 0;
     bool rowok = false;
     for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
@@ -264,28 +277,29 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
             const int yc = min(y, A.ny - 1);
             cls = A.cls[yc];
             const size_t o = (size_t)yc * nx + qc * S;
-            fl4 = *reinterpret_cast<const uint4 *>(A.flags + o);
+            const unsigned *pf = reinterpret_cast<const unsigned *>(A.flags + o);
+#pragma unroll
+            for (int i = 0; i < S / 4; ++i) flw[i] = rowok ? pf[i] : 0u;
             const double2 *px = reinterpret_cast<const double2 *>(A.cx + o);
             const double2 *py = reinterpret_cast<const double2 *>(A.cy + o);
 #pragma unroll
-            for (int un = 0; un < S / 2; ++un) {
+            for (int un = 0; un < UPC; ++un) {
                 const double2 a2 = px[un], b2 = py[un];
                 cx[2 * un] = rowok ? a2.x : 0.0;
                 cx[2 * un + 1] = rowok ? a2.y : 0.0;
                 cy[2 * un] = rowok ? b2.x : 0.0;
                 cy[2 * un + 1] = rowok ? b2.y : 0.0;
             }
-            if (!rowok) fl4 = make_uint4(0, 0, 0, 0);
         }
         const double a = s_a[bin];
         const double rho = s_rho[bin];
-        ChunkSolve ch;
+        ChunkSolve<S> ch;
         {   // LU factors of this chunk (L2 / L1 resident table), issued before the wait on the tile
             const size_t base = (((size_t)bin * A.jmax + jidx) * A.nclass + cls) * A.npad;
             const double2 *pm = reinterpret_cast<const double2 *>(A.tabm + base);
             const double2 *pg = reinterpret_cast<const double2 *>(A.tabg + base);
 #pragma unroll
-            for (int un = 0; un < S / 2; ++un) {
+            for (int un = 0; un < UPC; ++un) {
                 const double2 mm = pm[un * Q + qc], gg = pg[un * Q + qc];
                 ch.m[2 * un] = rowok ? mm.x : 0.0;
                 ch.m[2 * un + 1] = rowok ? mm.y : 0.0;
@@ -299,17 +313,17 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         const double *sb = reinterpret_cast<const double *>(smraw + (size_t)s * stage_bytes + u_bytes);
         int rhi = 0, uhi = 0;
         {
-            const int rb = g * Q + qc;              // 128-byte row index in the b tile
-            const int ru = (g + 1) * Q + qc;        // in the u tile (one halo row on top)
-            const double2 *pb = reinterpret_cast<const double2 *>(sb + (size_t)rb * S);
-            const double2 *pc = reinterpret_cast<const double2 *>(su + (size_t)ru * S);
-            const double2 *pu = reinterpret_cast<const double2 *>(su + (size_t)(ru - Q) * S);
-            const double2 *pd = reinterpret_cast<const double2 *>(su + (size_t)(ru + Q) * S);
-            const int swb = rb & 7, swc = ru & 7, swu = (ru - Q) & 7, swd = (ru + Q) & 7;
+            const int rb = g * Q16 + r16;            // 128-byte row index in the b tile
+            const int ru = (g + 1) * Q16 + r16;      // in the u tile (one halo row on top)
+            const double2 *pb = reinterpret_cast<const double2 *>(sb + (size_t)rb * 16);
+            const double2 *pc = reinterpret_cast<const double2 *>(su + (size_t)ru * 16);
+            const double2 *pu = reinterpret_cast<const double2 *>(su + (size_t)(ru - Q16) * 16);
+            const double2 *pd = reinterpret_cast<const double2 *>(su + (size_t)(ru + Q16) * 16);
+            const int swb = rb & 7, swc = ru & 7, swu = (ru - Q16) & 7, swd = (ru + Q16) & 7;
             double uc[S];
 #pragma unroll
-            for (int un = 0; un < S / 2; ++un) {
-                const double2 tq = pc[un ^ swc];
+            for (int un = 0; un < UPC; ++un) {
+                const double2 tq = pc[(ubase + un) ^ swc];
                 uc[2 * un] = qok ? tq.x : 0.0;
                 uc[2 * un + 1] = qok ? tq.y : 0.0;
             }
@@ -318,10 +332,9 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
             if (q == 0) ul = 0.0;
             if (q == QP - 1) ur = 0.0;
             const double rm = rho - 0.5, rp = rho + 0.5;
-            const unsigned flw[4] = {fl4.x, fl4.y, fl4.z, fl4.w};
 #pragma unroll
-            for (int un = 0; un < S / 2; ++un) {
-                const double2 tu = pu[un ^ swu], td = pd[un ^ swd], tb = pb[un ^ swb];
+            for (int un = 0; un < UPC; ++un) {
+                const double2 tu = pu[(ubase + un) ^ swu], td = pd[(ubase + un) ^ swd], tb = pb[(ubase + un) ^ swb];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int tt = 2 * un + h;
@@ -358,16 +371,16 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         // ---- out tile ----
         const int ob = k & 1;
         double *so = reinterpret_cast<double *>(out_base + (size_t)ob * b_bytes);
-        cons_bar(1);   // thread 0 has seen the store of tile k-2 finish reading this buffer
+        cta_bar<NT>(1);   // thread 0 has seen the store of tile k-2 finish reading this buffer
         if (qok) {
-            const int rb = g * Q + q;
-            double2 *dst = reinterpret_cast<double2 *>(so + (size_t)rb * S);
+            const int rb = g * Q16 + r16;
+            double2 *dst = reinterpret_cast<double2 *>(so + (size_t)rb * 16);
             const int swb = rb & 7;
 #pragma unroll
-            for (int un = 0; un < S / 2; ++un) dst[un ^ swb] = make_double2(ch.v[2 * un], ch.v[2 * un + 1]);
+            for (int un = 0; un < UPC; ++un) dst[(ubase + un) ^ swb] = make_double2(ch.v[2 * un], ch.v[2 * un + 1]);
         }
         fence_async_smem();
-        cons_bar(2);
+        cta_bar<NT>(2);
         if (tid == 0) {
             tma_store_4d(&maps.out, smem_u32(so), 0, 0, y0, bin);
             bulk_commit();
@@ -381,12 +394,14 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
 // =========================================================================================================
 // y sweep
 // =========================================================================================================
-// Tile = (bin, strip of CW columns, all rows).  smem stage = u strip + u* strip as [npad rows][CW] (no swizzle:
-// the CW lanes of a row read one contiguous segment).  Consumer thread (q, c): chunk q (16 rows) of column c.
-template <int CW, int NS>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// Tile = (bin, strip of CW columns, all rows), NT = 4096/S threads.  smem stage = u strip + u* strip as
+// [npad rows][CW] (no swizzle: the CW lanes of a row read one contiguous segment).  Thread (q, c): chunk q (S rows) of
+// column c.  The LU factors of the NEXT tile are prefetched into registers while the current one is solved.
+template <int S, int CW, int NS>
+__global__ void __launch_bounds__(4096 / S, 1)
 k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
-    constexpr int NCH = NCONS / CW;   // chunk slots per column
+    constexpr int NT = 4096 / S;
+    constexpr int NCH = NT / CW;      // chunk slots per column
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int Q = A.Q;                // real chunks per column (<= NCH)
     const int npad = A.npad;
@@ -402,17 +417,10 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         for (int s = 0; s < NS; ++s) mbar_init(full0 + 8 * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // per-bin parameters of this launch, read once (the tile loop touches no global scalars)
     double *s_a = reinterpret_cast<double *>(bars + 8);
     double *s_rho = s_a + A.ne;
     int *s_j = reinterpret_cast<int *>(s_rho + A.ne);
-    for (int b = tid; b < A.ne; b += NCONS) {
-        const bool act = tile_active<1>(A, b, blockIdx.x == 0);
-        const int j = A.iter % A.jlen[b];
-        s_j[b] = act ? j : -1;
-        s_a[b] = A.a_bin[b];
-        s_rho[b] = A.shift[(long long)b * A.jmax + j];
-    }
+    load_bin_params<1, NT>(A, s_a, s_rho, s_j);
     __syncthreads();
     const int tpb = A.tiles_per_bin;
     const int nbox = (npad + 255) / 256;          // TMA boxes per strip (box rows <= 256)
@@ -444,30 +452,41 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
     const int q = tid / CW, c = tid - q * CW;
     const bool qok = q < Q;
     const int r0 = (qok ? q : 0) * S;
-    int k = 0;
-    for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
+    auto next_tile = [&](int t) {
+        while (t < A.ntiles && s_j[t / tpb] < 0) t += gridDim.x;
+        return t;
+    };
+    double mN[S], gN[S];
+    auto load_factors = [&](int t) {   // factors of this thread's chunk for tile t
         const int bin = t / tpb;
-        const int strip = t - bin * tpb;
-        const int jidx = s_j[bin];
-        if (jidx < 0) continue;
-        if (tid == 0) produce();
-        const int x0 = strip * CW;
-        const int x = min(x0 + c, A.nx - 1);
-        const double rho2 = 2.0 * s_rho[bin];
-        ChunkSolve ch;
-        {
-            const int cls = A.cls[x];
-            const size_t base = (((size_t)bin * A.jmax + jidx) * A.nclass + cls) * npad + r0;
-            const double2 *pm = reinterpret_cast<const double2 *>(A.tabm + base);
-            const double2 *pg = reinterpret_cast<const double2 *>(A.tabg + base);
+        const int x = min((t - bin * tpb) * CW + c, A.nx - 1);
+        const int cls = A.cls[x];
+        const size_t base = (((size_t)bin * A.jmax + s_j[bin]) * A.nclass + cls) * npad + r0;
+        const double2 *pm = reinterpret_cast<const double2 *>(A.tabm + base);
+        const double2 *pg = reinterpret_cast<const double2 *>(A.tabg + base);
 #pragma unroll
-            for (int un = 0; un < S / 2; ++un) {
-                const double2 mm = pm[un], gg = pg[un];
-                ch.m[2 * un] = qok ? mm.x : 0.0;
-                ch.m[2 * un + 1] = qok ? mm.y : 0.0;
-                ch.g[2 * un] = qok ? gg.x : 0.0;
-                ch.g[2 * un + 1] = qok ? gg.y : 0.0;
-            }
+        for (int un = 0; un < S / 2; ++un) {
+            const double2 mm = pm[un], gg = pg[un];
+            mN[2 * un] = qok ? mm.x : 0.0;
+            mN[2 * un + 1] = qok ? mm.y : 0.0;
+            gN[2 * un] = qok ? gg.x : 0.0;
+            gN[2 * un + 1] = qok ? gg.y : 0.0;
+        }
+    };
+    int k = 0;
+    int t = next_tile(blockIdx.x);
+    if (t < A.ntiles) load_factors(t);
+    while (t < A.ntiles) {
+        const int bin = t / tpb;
+        const int x0 = (t - bin * tpb) * CW;
+        const int tn = next_tile(t + gridDim.x);
+        if (tid == 0) produce();
+        const double rho2 = 2.0 * s_rho[bin];
+        ChunkSolve<S> ch;
+#pragma unroll
+        for (int tt = 0; tt < S; ++tt) {
+            ch.m[tt] = mN[tt];
+            ch.g[tt] = gN[tt];
         }
         const int s = k % NS;
         mbar_wait(full0 + 8 * s, (k / NS) & 1);
@@ -479,20 +498,21 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
             uold[tt] = su[tt * CW];
             ch.v[tt] = sw[tt * CW] - uold[tt];
         }
+        if (tn < A.ntiles) load_factors(tn);   // in flight during the solve below
         double Am, Bm;
         ch.forward(Am, Bm);
         double *cA = carry, *cB = carry + NCH * CW;
-        cons_bar(1);   // previous tile's carries are consumed; also orders thread 0's wait on the store of tile k-2
+        cta_bar<NT>(1);   // previous tile's carries are consumed; also orders thread 0's wait on the store of tile k-2
         cA[q * CW + c] = Am;
         cB[q * CW + c] = Bm;
-        cons_bar(2);
+        cta_bar<NT>(2);
         double cin = 0.0;
         for (int kk = 0; kk < q; ++kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
         ch.forward_fix(cin);
         Bm = ch.backward();
-        cons_bar(3);
+        cta_bar<NT>(3);
         cB[q * CW + c] = Bm;
-        cons_bar(4);
+        cta_bar<NT>(4);
         cin = 0.0;
         for (int kk = NCH - 1; kk > q; --kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
         ch.backward_fix(cin);
@@ -503,7 +523,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
             for (int tt = 0; tt < S; ++tt) so[tt * CW] = fma(rho2, ch.v[tt], uold[tt]);
         }
         fence_async_smem();
-        cons_bar(5);
+        cta_bar<NT>(5);
         if (tid == 0) {
             const uint32_t src = smem_u32(out_base + (size_t)ob * strip_bytes);
             for (int bx = 0; bx < nbox; ++bx) tma_store_3d(&maps.out, src + bx * box_rows * CW * 8, x0, bx * box_rows, bin);
@@ -511,6 +531,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
             bulk_wait_read<1>();
         }
         ++k;
+        t = tn;
     }
     if (tid == 0) bulk_wait_read<0>();
 }
@@ -568,41 +589,41 @@ constexpr int SMEM_CAP = 227 * 1024;
 
 size_t param_smem(int ne) { return (size_t)ne * 20 + 16; }
 
-template <int QP>
-size_t x_smem(int Q, int ns) {
-    constexpr int R = NCONS / QP;
-    const size_t ub = ((size_t)(R + 2) * Q * 128 + 1023) / 1024 * 1024;
-    const size_t bb = ((size_t)R * Q * 128 + 1023) / 1024 * 1024;
-    return ns * (ub + bb) + 2 * bb + 64;   // + per-bin parameters, added by the caller
+// x: S cells per chunk, QP lanes per row, nx16 = nx/16
+size_t x_smem(int S, int QP, int nx16, int ns) {
+    const int R = (4096 / S) / QP;
+    const size_t ub = ((size_t)(R + 2) * nx16 * 128 + 1023) / 1024 * 1024;
+    const size_t bb = ((size_t)R * nx16 * 128 + 1023) / 1024 * 1024;
+    return ns * (ub + bb) + 2 * bb + 64;
 }
 
-template <int QP, int NS>
+template <int S, int QP, int NS>
 int launch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
-    auto kern = k_sweep_x_pipe<QP, NS>;
+    auto kern = k_sweep_x_pipe<S, QP, NS>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    kern<<<grid, NTHREADS, x_smem<QP>(A.Q, NS) + param_smem(A.ne), c->stream>>>(A, maps);
+    kern<<<grid, 4096 / S, x_smem(S, QP, A.nx / 16, NS) + param_smem(A.ne), c->stream>>>(A, maps);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
 }
 
-size_t y_smem(int cw, int npad, int ns) {
+size_t y_smem(int S, int cw, int npad, int ns) {
     const size_t sb = ((size_t)npad * cw * 8 + 127) / 128 * 128;
-    return ns * 2 * sb + 2 * sb + sizeof(double) * 2 * (NCONS / cw) * cw + 64;
+    return ns * 2 * sb + 2 * sb + sizeof(double) * 2 * (4096 / S) + 64;
 }
 
-template <int CW, int NS>
+template <int S, int CW, int NS>
 int launch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
-    auto kern = k_sweep_y_pipe<CW, NS>;
+    auto kern = k_sweep_y_pipe<S, CW, NS>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    kern<<<grid, NTHREADS, y_smem(CW, A.npad, NS) + param_smem(A.ne), c->stream>>>(A, maps);
+    kern<<<grid, 4096 / S, y_smem(S, CW, A.npad, NS) + param_smem(A.ne), c->stream>>>(A, maps);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
 }
@@ -617,35 +638,36 @@ int pick_grid(int ntiles, int tpb, int nsm) {
 }  // namespace
 
 // ---- host side -------------------------------------------------------------------------------------------------
+// chunk length the pipelined kernels want for a line of n cells (0: not supported)
+int qpbp_chunk(int n, int dir) {
+    (void)dir;
+    // S = 16 (256 threads, ~250 registers each) measured faster than S = 8 (512 threads) on C2: 43/40 us vs 59/58 us
+    // per x/y sweep; QPB_PIPE_S=8 selects the short chunks for experiments
+    const char *e = getenv("QPB_PIPE_S");
+    if (e && e[0] == '8' && n <= 256) return 8;
+    if (n <= 512) return 16;
+    return 0;
+}
+
 int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
     p = PipePlan();
     const auto &cf = c->cfg;
     if (getenv("QPB_NO_PIPE") && getenv("QPB_NO_PIPE")[0] == '1') return QPB_OK;
-    if (s.mode != 0 || !s.fast || !encode_fn()) return QPB_OK;
+    if (s.mode != 0 || !s.fast || !encode_fn() || cf.ne > 2048) return QPB_OK;
     int dev = 0, nsm = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     p.nsm = nsm;
-    // x sweep: rows cut into 16-cell chunks owned by adjacent lanes (<= 32 chunks), TMA boxes of whole chunks
-    if (cf.nx % 16 == 0 && cf.nx <= 512 && s.fx.S == 16 && s.fx.d_tabg) {
-        const int Q = cf.nx / 16, QP = next_pow2(Q), R = NCONS / QP;
+    // x sweep: rows cut into S-cell chunks owned by adjacent lanes (<= 32 chunks), TMA boxes of whole 128-byte units
+    if (cf.nx % 16 == 0 && s.fx.d_tabg && s.fx.S == qpbp_chunk(cf.nx, 0) && s.fx.S > 0) {
+        const int S = s.fx.S, Q = s.fx.Q, QP = std::max(4, next_pow2(Q)), R = (4096 / S) / QP;
         int ns = 0;
-        for (int cand = 3; cand >= 2 && !ns; --cand) {
-            size_t need = 0;
-            switch (QP) {
-                case 1: need = x_smem<1>(Q, cand); break;
-                case 2: need = x_smem<2>(Q, cand); break;
-                case 4: need = x_smem<4>(Q, cand); break;
-                case 8: need = x_smem<8>(Q, cand); break;
-                case 16: need = x_smem<16>(Q, cand); break;
-                default: need = x_smem<32>(Q, cand); break;
-            }
-            if (need + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
-        }
+        for (int cand = 3; cand >= 2 && !ns; --cand)
+            if (x_smem(S, QP, cf.nx / 16, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
         XMaps maps;
-        if (ns && make_xmap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, Q, R + 2) &&
-            make_xmap(&maps.b, c->d_B, cf.ne, cf.ny, cf.nx, Q, R) &&
-            make_xmap(&maps.out, c->d_T1, cf.ne, cf.ny, cf.nx, Q, R)) {
+        if (QP <= 32 && ns && make_xmap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, cf.nx / 16, R + 2) &&
+            make_xmap(&maps.b, c->d_B, cf.ne, cf.ny, cf.nx, cf.nx / 16, R) &&
+            make_xmap(&maps.out, c->d_T1, cf.ne, cf.ny, cf.nx, cf.nx / 16, R)) {
             p.x_ok = true;
             p.x_qp = QP;
             p.x_ns = ns;
@@ -654,17 +676,16 @@ int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
             memcpy(p.xmaps.data(), &maps, sizeof(XMaps));
         }
     }
-    // y sweep: strips of CW columns, columns cut into 16-row chunks (<= 256/CW chunks)
-    if (cf.nx % 2 == 0 && cf.ny <= 2048 && s.fy.S == 16 && s.fy.d_tabg) {
-        const int Q = s.fy.Q, npad = s.fy.npad;
-        int cw = NCONS / next_pow2(Q);
-        cw = std::min(cw, 32);
-        while (cw > 2 && cw / 2 >= cf.nx) cw /= 2;    // narrow grids: do not load columns that do not exist
+    // y sweep: strips of CW columns, columns cut into S-row chunks (<= NT/CW chunks)
+    if (cf.nx % 2 == 0 && s.fy.d_tabg && s.fy.S == qpbp_chunk(cf.ny, 1) && s.fy.S > 0) {
+        const int S = s.fy.S, Q = s.fy.Q, npad = s.fy.npad, NT = 4096 / S;
+        int cw = std::min(32, NT / next_pow2(Q));
+        while (cw > 4 && cw / 2 >= cf.nx) cw /= 2;    // narrow grids: do not load columns that do not exist
         const int nbox = (npad + 255) / 256;
-        if (cw >= 2 && npad % nbox == 0 && (npad / nbox) <= 256) {
+        if (cw >= 4 && npad % nbox == 0 && (npad / nbox) <= 256 && ((npad / nbox) * cw) % 16 == 0) {
             int ns = 0;
             for (int cand = 3; cand >= 2 && !ns; --cand)
-                if (y_smem(cw, npad, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
+                if (y_smem(S, cw, npad, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
             YMaps maps;
             const int rows = npad / nbox;
             if (ns && make_ymap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, cw, rows) &&
@@ -682,17 +703,39 @@ int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
     return QPB_OK;
 }
 
+template <int S>
+static int dispatch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid, int qp, int ns) {
+#define QPB_X(QP)                                                      \
+    case QP:                                                           \
+        return ns == 3 ? launch_x<S, QP, 3>(c, A, maps, grid) : launch_x<S, QP, 2>(c, A, maps, grid);
+    switch (qp) {
+        QPB_X(4) QPB_X(8) QPB_X(16)
+        default: return ns == 3 ? launch_x<S, 32, 3>(c, A, maps, grid) : launch_x<S, 32, 2>(c, A, maps, grid);
+    }
+#undef QPB_X
+}
+
+template <int S>
+static int dispatch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid, int cw, int ns) {
+#define QPB_Y(CW)                                                      \
+    case CW:                                                           \
+        return ns == 3 ? launch_y<S, CW, 3>(c, A, maps, grid) : launch_y<S, CW, 2>(c, A, maps, grid);
+    switch (cw) {
+        QPB_Y(4) QPB_Y(8) QPB_Y(16)
+        default: return ns == 3 ? launch_y<S, 32, 3>(c, A, maps, grid) : launch_y<S, 32, 2>(c, A, maps, grid);
+    }
+#undef QPB_Y
+}
+
 int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter) {
     const auto &cf = c->cfg;
     const PipePlan &p = s.pipe;
     const DiffSlot::FastDir &fd = dir == 0 ? s.fx : s.fy;
-    const int nlines = dir == 0 ? cf.ny : cf.nx;
     PipeArgs A;
     A.ne = cf.ne; A.ny = cf.ny; A.nx = cf.nx; A.iter = iter; A.jmax = s.jmax; A.tol = cf.diff_tol;
     A.cx = c->d_cx; A.cy = c->d_cy; A.flags = c->d_flags;
     A.a_bin = s.d_a; A.shift = s.d_shift; A.jlen = s.d_jlen;
     A.cls = fd.d_cls;
-    (void)nlines;
     A.tabm = fd.d_tab; A.tabg = fd.d_tabg; A.nclass = fd.nclass; A.npad = fd.npad; A.Q = fd.Q;
     A.res = c->d_res; A.unorm = c->d_unorm; A.done = c->d_done; A.iters_out = c->d_done + cf.ne;
     ScopedTimer tm(c, dir == 0 ? 0 : 1);
@@ -702,25 +745,11 @@ int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter) {
         A.ntiles = p.x_tpb * cf.ne;
         const int grid = pick_grid(A.ntiles, p.x_tpb, p.nsm);
         const XMaps &maps = *reinterpret_cast<const XMaps *>(p.xmaps.data());
-#define QPB_X(QP)                                                      \
-    case QP:                                                           \
-        return p.x_ns == 3 ? launch_x<QP, 3>(c, A, maps, grid) : launch_x<QP, 2>(c, A, maps, grid);
-        switch (p.x_qp) {
-            QPB_X(1) QPB_X(2) QPB_X(4) QPB_X(8) QPB_X(16)
-            default: return p.x_ns == 3 ? launch_x<32, 3>(c, A, maps, grid) : launch_x<32, 2>(c, A, maps, grid);
-        }
-#undef QPB_X
+        return fd.S == 8 ? dispatch_x<8>(c, A, maps, grid, p.x_qp, p.x_ns) : dispatch_x<16>(c, A, maps, grid, p.x_qp, p.x_ns);
     }
     A.tiles_per_bin = p.y_tpb;
     A.ntiles = p.y_tpb * cf.ne;
     const int grid = pick_grid(A.ntiles, p.y_tpb, p.nsm);
     const YMaps &maps = *reinterpret_cast<const YMaps *>(p.ymaps.data());
-#define QPB_Y(CW)                                                      \
-    case CW:                                                           \
-        return p.y_ns == 3 ? launch_y<CW, 3>(c, A, maps, grid) : launch_y<CW, 2>(c, A, maps, grid);
-    switch (p.y_cw) {
-        QPB_Y(2) QPB_Y(4) QPB_Y(8) QPB_Y(16)
-        default: return p.y_ns == 3 ? launch_y<32, 3>(c, A, maps, grid) : launch_y<32, 2>(c, A, maps, grid);
-    }
-#undef QPB_Y
+    return fd.S == 8 ? dispatch_y<8>(c, A, maps, grid, p.y_cw, p.y_ns) : dispatch_y<16>(c, A, maps, grid, p.y_cw, p.y_ns);
 }
