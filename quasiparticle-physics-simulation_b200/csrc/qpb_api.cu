@@ -641,6 +641,7 @@ extern "C" int qpb_upload_collision(qpb_ctx *c, const double *K_r0, const double
             QPB_CUDA(cudaMemcpy(c->d_smap, smap.data(), sizeof(int32_t) * (2 * ne - 1), cudaMemcpyHostToDevice));
             QPB_CUDA(cudaMemcpy(c->d_kof, kof.data(), sizeof(int32_t) * cf.nw, cudaMemcpyHostToDevice));
             QPB_CUDA(cudaMemcpy(c->d_mof, mof.data(), sizeof(int32_t) * cf.nw, cudaMemcpyHostToDevice));
+            c->h_dmap = dmap; c->h_smap = smap; c->h_kof = kof; c->h_mof = mof;
             c->structured = true;
         }
     }

@@ -21,6 +21,7 @@ constexpr int TJ = 4;     // columns per register tile
 constexpr int PADF = 8;   // zero padding in front of the n,p columns in shared memory
 constexpr int PADB = 16;  // and behind
 constexpr int NSTAGE = 3; // cp.async ring depth
+constexpr int NEPMAX = 512; // largest padded energy grid of the structured kernel (index tables ride in the parameters)
 
 struct StructArgs {
     int ne, nep, nw, ncell, ncd;
@@ -31,8 +32,11 @@ struct StructArgs {
     const double *KsD;   // [nep][nep]  dE*Ks[j+k][j]
     const double *KrA;   // [2nep][nep] dE*Kr[m-j][j] * (2 if j<m-j, 1 if j==m-j, else 0)
     const double *rho;   // [nep] zero padded
-    const int32_t *dmap, *smap, *kof, *mof;
     double dt;
+    // Index tables as kernel parameters (constant bank: a lookup is not a memory round trip).  -1 = none.
+    //   dmap[k]  phonon bin of the diagonal k = |i-j|          mofk[k]  >= 0 when that bin is also fed by an anti-diagonal
+    //   smap[m]  phonon bin of the anti-diagonal m = i+j       kofm[m]  diagonal index k sharing that bin, or -1
+    int16_t dmap[NEPMAX], mofk[NEPMAX], smap[2 * NEPMAX], kofm[2 * NEPMAX];
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
@@ -111,7 +115,7 @@ __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const do
 
 // CC = cells per CTA; NT = threads per CTA.
 template <int CC, int NT, bool SC, bool RC, bool PH>
-__global__ void __launch_bounds__(NT, 1) k_collide_struct(StructArgs A) {
+__global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const __grid_constant__ StructArgs A) {
     extern __shared__ __align__(16) double sm[];
     const int nep = A.nep;
     const int ncol = nep + PADF + PADB;
@@ -133,32 +137,60 @@ __global__ void __launch_bounds__(NT, 1) k_collide_struct(StructArgs A) {
     const int ncell = A.ncell;
 
     // ---- stage the per-cell columns -------------------------------------------------------------------
-    for (int e = tid; e < ncol * CC; e += NT) {
-        const int col = e / CC, c = e - col * CC;
-        const int i = col - PADF;
-        const int q = cell0 + c;
-        double nv = 0.0, pv = 0.0;
-        if (i >= 0 && i < A.ne && q < ncell) {
-            nv = A.S[(long long)i * A.ncd + A.c2d[q]];
-            const double r = A.rho[i];
-            pv = r * fmax(1.0 - nv / fmax(r, 1e-30), 0.0);
-        }
-        sn[e] = nv;
-        sp[e] = pv;
-    }
-    for (int e = tid; e < 3 * nep * CC; e += NT) {
-        const int idx = e / CC, c = e - idx * CC;
-        const int q = cell0 + c;
-        double v = 0.0;
-        if (q < ncell) {
-            if (idx < nep) {
-                if (idx < A.ne) v = A.P[(long long)A.dmap[idx] * ncell + q];
-            } else {
-                const int m = idx - nep;
-                if (m < 2 * A.ne - 1) v = A.P[(long long)A.smap[m] * ncell + q];
+    // NT is a multiple of CC, so a thread always serves the same cell: its dense index is read once and every
+    // column load below is independent of the others (8 in flight per thread).
+    static_assert(NT % CC == 0, "threads per CTA must be a multiple of the cells per CTA");
+    {
+        constexpr int RPT = NT / CC;   // columns covered by one pass of the CTA
+        constexpr int UN = 10;
+        const int c_me = tid % CC, row_me = tid / CC;
+        const int q_me = cell0 + c_me;
+        const bool live_me = q_me < ncell;
+        const long long d_me = live_me ? A.c2d[q_me] : 0;
+        for (int col0 = row_me; col0 < ncol; col0 += RPT * UN) {
+            double nv[UN], rv[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int i = col0 + u * RPT - PADF;
+                const bool ok = live_me && i >= 0 && i < A.ne;
+                nv[u] = ok ? A.S[(long long)i * A.ncd + d_me] : 0.0;
+                rv[u] = ok ? A.rho[i] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int col = col0 + u * RPT;
+                if (col < ncol) {
+                    sn[col * CC + c_me] = nv[u];
+                    sp[col * CC + c_me] = rv[u] * fmax(1.0 - nv[u] / fmax(rv[u], 1e-30), 0.0);
+                }
             }
         }
-        snd[e] = v;  // snd and sns are contiguous
+        // phonon occupations of the two index families (snd and sns are contiguous: 3*nep rows).  All index lookups of
+        // a batch are issued first, then all occupation loads: two memory round trips per 12 rows
+        constexpr int UP = 12;
+        for (int idx0 = row_me; idx0 < 3 * nep; idx0 += RPT * UP) {
+            int om[UP];
+#pragma unroll
+            for (int u = 0; u < UP; ++u) {
+                const int idx = idx0 + u * RPT;
+                om[u] = -1;
+                if (live_me && idx < 3 * nep) {
+                    if (idx < nep) {
+                        if (idx < A.ne) om[u] = A.dmap[idx];
+                    } else if (idx - nep < 2 * A.ne - 1) {
+                        om[u] = A.smap[idx - nep];
+                    }
+                }
+            }
+            double v[UP];
+#pragma unroll
+            for (int u = 0; u < UP; ++u) v[u] = om[u] >= 0 ? A.P[(long long)om[u] * ncell + q_me] : 0.0;
+#pragma unroll
+            for (int u = 0; u < UP; ++u) {
+                const int idx = idx0 + u * RPT;
+                if (idx < 3 * nep) snd[idx * CC + c_me] = v[u];
+            }
+        }
     }
     __syncthreads();
     const double *cn = sn + (size_t)PADF * CC + cl;   // cn[idx*CC] = n[idx] of this lane's cell
@@ -222,43 +254,56 @@ __global__ void __launch_bounds__(NT, 1) k_collide_struct(StructArgs A) {
     double *stb = snd + (size_t)nep * CC;      // b of the diagonal family  [nep][CC]
 
     // ---- pass 2: diagonals k = i-j > 0 (scattering phonon source) ----------------------------------------
+    // Blocks of 8 diagonals, a long one paired with a short one; when there are fewer pairs than warp slots every
+    // pair is cut along j into `parts` pieces whose partial sums meet in shared memory.
     if (SC) {
         const int nkb = nep / TI;
         const int npair = (nkb + 1) / 2;
-        const int nround = (npair + nslot - 1) / nslot;
+        int parts = 1;
+        while (parts * 2 * npair <= nslot && parts < 8) parts *= 2;
+        if (parts > 1) {
+            for (int e = tid; e < 2 * nep * CC; e += NT) sta[e] = 0.0;
+            __syncthreads();
+        }
+        const int nunit = npair * parts;
+        const int nround = (nunit + nslot - 1) / nslot;
         for (int rd = 0; rd < nround; ++rd) {
-            const int it = slot + rd * nslot;
+            const int unit = slot + rd * nslot;
+            const int it = unit / parts, part = unit - it * parts;
 #pragma unroll 1
             for (int half = 0; half < 2; ++half) {
                 const int kbk = half == 0 ? it : nkb - 1 - it;   // pair a long block with a short one
-                const bool work = it < npair && !(half == 1 && kbk == it);
+                const bool work = unit < nunit && !(half == 1 && kbk == it);
                 const int k0 = work ? kbk * TI : 0;
                 double Aem[TI], Cab[TI];
 #pragma unroll
                 for (int r = 0; r < TI; ++r) Aem[r] = Cab[r] = 0.0;
-                // the longest range among the lanes of this warp decides the trip count (extra tiles multiply zeros)
-                int ntile = work ? (nep - k0) / TJ : 0;
+                // this piece's tile range; the longest range among the lanes of the warp decides the trip count
+                const int nt_all = work ? (nep - k0) / TJ : 0;
+                const int t_lo = (nt_all * part) / parts, t_hi = (nt_all * (part + 1)) / parts;
+                const int mytiles = t_hi - t_lo;
+                int ntile = mytiles;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ntile = max(ntile, __shfl_xor_sync(0xffffffffu, ntile, o));
-                const char *gk = reinterpret_cast<const char *>(A.KsD + (size_t)k0 * nep);
+                const char *gk = reinterpret_cast<const char *>(A.KsD + (size_t)k0 * nep + (size_t)t_lo * TJ);
                 const size_t rstride = (size_t)nep * 8;
                 __syncwarp();
 #pragma unroll
                 for (int t = 0; t < NSTAGE - 1; ++t) {
-                    if (t < ntile) ring_prefetch<CC, TJ / 2>(ring + t * STAGE_BYTES, gk + (size_t)t * TJ * 8, rstride, cl);
+                    if (t < mytiles) ring_prefetch<CC, TJ / 2>(ring + t * STAGE_BYTES, gk + (size_t)t * TJ * 8, rstride, cl);
                     cp_async_commit();
                 }
                 for (int t = 0; t < ntile; ++t) {
                     __syncwarp();
                     const int tn = t + NSTAGE - 1;
-                    if (tn < ntile)
+                    if (tn < mytiles)
                         ring_prefetch<CC, TJ / 2>(ring + (tn % NSTAGE) * STAGE_BYTES, gk + (size_t)tn * TJ * 8, rstride, cl);
                     cp_async_commit();
                     cp_async_wait<NSTAGE - 1>();
                     __syncwarp();
+                    if (t >= mytiles) continue;
                     const double *kt = reinterpret_cast<const double *>(ring + (t % NSTAGE) * STAGE_BYTES);
-                    const int j0 = t * TJ;
-                    if (j0 + k0 >= nep) continue;   // beyond this sub-slot's own range: nothing but padding
+                    const int j0 = (t_lo + t) * TJ;
                     double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
 #pragma unroll
                     for (int s = 0; s < TJ; ++s) {
@@ -287,15 +332,34 @@ __global__ void __launch_bounds__(NT, 1) k_collide_struct(StructArgs A) {
                         const int k = k0 + r;
                         if (k >= A.ne) continue;
                         const double a = Aem[r], b = Aem[r] - Cab[r];
-                        const int om = A.dmap[k];
-                        if (RC && A.mof[om] >= 0) {
-                            sta[k * CC + cl] = a;
-                            stb[k * CC + cl] = b;
+                        if (parts > 1) {
+                            atomicAdd(&sta[k * CC + cl], a);
+                            atomicAdd(&stb[k * CC + cl], b);
                         } else {
-                            const long long o = (long long)om * ncell + q;
-                            A.P[o] = affine_growth(A.P[o], a, b, A.dt);
+                            const int om = A.dmap[k];
+                            if (RC && A.mofk[k] >= 0) {
+                                sta[k * CC + cl] = a;
+                                stb[k * CC + cl] = b;
+                            } else {
+                                const long long o = (long long)om * ncell + q;
+                                A.P[o] = affine_growth(A.P[o], a, b, A.dt);
+                            }
                         }
                     }
+                }
+            }
+        }
+        if (parts > 1) {
+            // the pieces have met: every thread finishes its share of (diagonal, cell) pairs
+            __syncthreads();
+            constexpr int RPT = NT / CC;
+            const int c_me = tid % CC, q_me = cell0 + c_me;
+            if (q_me < ncell) {
+                for (int k = tid / CC; k < A.ne; k += RPT) {
+                    const int om = A.dmap[k];
+                    if (RC && A.mofk[k] >= 0) continue;   // also fed by an anti-diagonal: stays in the stash for pass 3
+                    const long long o = (long long)om * ncell + q_me;
+                    A.P[o] = affine_growth(A.P[o], sta[k * CC + c_me], stb[k * CC + c_me], A.dt);
                 }
             }
         }
@@ -375,7 +439,7 @@ __global__ void __launch_bounds__(NT, 1) k_collide_struct(StructArgs A) {
                         if (m >= 2 * A.ne - 1) continue;
                         const int om = A.smap[m];
                         double a = R[r], b = R[r];
-                        const int k = SC ? A.kof[om] : -1;
+                        const int k = SC ? A.kofm[m] : -1;
                         if (k >= 0) {   // same phonon bin also fed by the diagonal family
                             a = sta[k * CC + cl] + R[r];
                             b = stb[k * CC + cl] + R[r];

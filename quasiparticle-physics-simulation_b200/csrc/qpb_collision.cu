@@ -21,6 +21,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 namespace {
@@ -202,7 +203,7 @@ int qpbk_collision_setup(qpb_ctx *c) {
     const auto &cf = c->cfg;
     const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
     if (!(scat || rec)) return QPB_OK;
-    if (!(c->structured && cf.ngap == 1)) {
+    if (!(c->structured && cf.ngap == 1) || ((cf.ne + TI - 1) / TI) * TI > NEPMAX || cf.nw > 32767) {
         c->structured = false;
         return QPB_OK;
     }
@@ -243,7 +244,7 @@ int qpbk_collision_setup(qpb_ctx *c) {
 
 template <int CC>
 struct StructCfg {
-    static constexpr int NT = CC >= 16 ? 512 : (CC == 8 ? 256 : 128);
+    static constexpr int NT = CC >= 32 ? 512 : (CC >= 8 ? 256 : 128);
     static size_t smem(int nep) {
         return sizeof(double) * (size_t)CC * (2 * (nep + PADF + PADB) + 3 * nep) +
                (size_t)(NT / 32) * (32 / CC) * NSTAGE * (TI * TJ * 16);
@@ -299,8 +300,23 @@ int qpbk_collide(qpb_ctx *c, double dt) {
         A.ne = cf.ne; A.nep = t.nep; A.nw = cf.nw; A.ncell = cf.ncell; A.ncd = c->ncd;
         A.S = c->d_S; A.P = c->d_P; A.c2d = c->d_cell2dense;
         A.K2 = t.K2; A.KsD = t.KsD; A.KrA = t.KrA; A.rho = t.rho;
-        A.dmap = c->d_dmap; A.smap = c->d_smap; A.kof = c->d_kof; A.mof = c->d_mof;
+        for (int k = 0; k < NEPMAX; ++k) A.dmap[k] = A.mofk[k] = -1;
+        for (int m = 0; m < 2 * NEPMAX; ++m) A.smap[m] = A.kofm[m] = -1;
+        for (int k = 0; k < cf.ne; ++k) {
+            A.dmap[k] = (int16_t)c->h_dmap[k];
+            A.mofk[k] = (int16_t)c->h_mof[c->h_dmap[k]];
+        }
+        for (int m = 0; m < 2 * cf.ne - 1; ++m) {
+            A.smap[m] = (int16_t)c->h_smap[m];
+            A.kofm[m] = (int16_t)c->h_kof[c->h_smap[m]];
+        }
         A.dt = dt;
+        // One 32-cell, 512-thread CTA per SM measured faster (1.19 ms at C2) than two 16-cell, 256-thread CTAs
+        // (1.47 ms: half-warps read different kernel-matrix tiles); QPB_COLL_CC=16 selects the narrow variant
+        const char *ecc = getenv("QPB_COLL_CC");
+        const bool narrow = ecc && ecc[0] == '1';
+        if (narrow && 2 * (StructCfg<16>::smem(t.nep) + 1024) <= 228 * 1024)
+            return dispatch_struct<16>(c, A, StructCfg<16>::smem(t.nep), scat, rec, ph);
         if (StructCfg<32>::smem(t.nep) <= smem_cap) return dispatch_struct<32>(c, A, StructCfg<32>::smem(t.nep), scat, rec, ph);
         if (StructCfg<16>::smem(t.nep) <= smem_cap) return dispatch_struct<16>(c, A, StructCfg<16>::smem(t.nep), scat, rec, ph);
         if (StructCfg<8>::smem(t.nep) <= smem_cap) return dispatch_struct<8>(c, A, StructCfg<8>::smem(t.nep), scat, rec, ph);

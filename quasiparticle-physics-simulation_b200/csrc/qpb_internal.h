@@ -114,6 +114,7 @@ struct qpb_ctx {
     int32_t *d_dmap = nullptr;        // structured: diff index k -> phonon bin  [ne]
     int32_t *d_smap = nullptr;        // structured: sum index m -> phonon bin   [2ne-1]
     int32_t *d_kof = nullptr, *d_mof = nullptr;  // phonon bin -> k / m or -1   [nw]
+    std::vector<int32_t> h_dmap, h_smap, h_kof, h_mof;  // host copies (ride in the kernel parameters)
     double *d_P = nullptr;            // phonon state [nw][ncell]
     double *d_scratch = nullptr;      // collision scratch
     size_t scratch_bytes = 0;

@@ -396,7 +396,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
 // =========================================================================================================
 // Tile = (bin, strip of CW columns, all rows), NT = 4096/S threads.  smem stage = u strip + u* strip as
 // [npad rows][CW] (no swizzle: the CW lanes of a row read one contiguous segment).  Thread (q, c): chunk q (S rows) of
-// column c.  The LU factors of the NEXT tile are prefetched into registers while the current one is solved.
+// column c.  
 template <int S, int CW, int NS>
 __global__ void __launch_bounds__(4096 / S, 1)
 k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
@@ -475,7 +475,6 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
     };
     int k = 0;
     int t = next_tile(blockIdx.x);
-    if (t < A.ntiles) load_factors(t);
     while (t < A.ntiles) {
         const int bin = t / tpb;
         const int x0 = (t - bin * tpb) * CW;
@@ -483,6 +482,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         if (tid == 0) produce();
         const double rho2 = 2.0 * s_rho[bin];
         ChunkSolve<S> ch;
+        load_factors(t);   // issued before the wait on the tile (a register prefetch of the next tile measured slower)
 #pragma unroll
         for (int tt = 0; tt < S; ++tt) {
             ch.m[tt] = mN[tt];
@@ -498,7 +498,6 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
             uold[tt] = su[tt * CW];
             ch.v[tt] = sw[tt * CW] - uold[tt];
         }
-        if (tn < A.ntiles) load_factors(tn);   // in flight during the solve below
         double Am, Bm;
         ch.forward(Am, Bm);
         double *cA = carry, *cB = carry + NCH * CW;
