@@ -210,6 +210,24 @@ def load_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def load_profile_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures of this
+    workload (profiles/r1_ncu_kernels.json; bytes), or nothing when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "r1_ncu_kernels.json")
+    if not os.path.exists(path):
+        return {}
+    with open(path) as f:
+        k = json.load(f)
+    out = {}
+    sw = [v["dram_bytes"] for n, v in k.items() if "k_sweep" in n]
+    if sw:
+        out["sweep"] = float(np.mean(sw))
+    co = [v["dram_bytes"] for n, v in k.items() if "k_collide" in n]
+    if co:
+        out["collide"] = float(np.mean(co))
+    return out
+
+
 def run_single_gpu(args):
     import qpsim_b200 as Q
     import cases
@@ -271,13 +289,14 @@ def run_single_gpu(args):
     sweep_bytes = 16.0 * n * bin_sweeps          # bins that converged early are skipped by the kernel
     sweep_ms = tx + ty
     coll_flops = 21.0 * ne * ne * n * ncl
+    prof = load_profile_traffic()
     roof_sweep = {"bound": "hbm", "achieved": sweep_bytes / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0,
-                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": None,
+                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": prof.get("sweep"),
                   "kernel": "k_sweep (x+y tridiagonal sweeps)", "launches": int(nxl + nyl),
                   "ms_per_launch": sweep_ms / max(1, nxl + nyl), "peak_source": peak_src}
     roof_sweep["frac"] = roof_sweep["achieved"] / roof_sweep["peak"]
     roof_coll = {"bound": "fp64", "achieved": coll_flops / (tc * 1e-3) / 1e12 if tc > 0 else 0.0, "peak": fp64_peak,
-                 "unit": "TFLOP/s", "traffic": None, "kernel": "k_collide_struct", "launches": int(ncl),
+                 "unit": "TFLOP/s", "traffic": prof.get("collide"), "kernel": "k_collide_struct", "launches": int(ncl),
                  "ms_per_launch": tc / max(1, ncl),
                  "peak_source": "measured in this run: DFMA loop on all SMs (qpb_measure_fp64)"}
     roof_coll["frac"] = roof_coll["achieved"] / roof_coll["peak"]
@@ -296,6 +315,7 @@ def run_single_gpu(args):
     import warnings
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
+        Q.run_2d_crank_nicolson(**{**kw, "total_time": w["dt"] * 2, "store_every": 2})   # untimed warm-up call
         t0 = time.perf_counter()
         times, frames, mass, _, eframes, _ = Q.run_2d_crank_nicolson(**kw)
         t_e2e = time.perf_counter() - t0
@@ -357,7 +377,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()

@@ -68,6 +68,7 @@ void qpbk_free_slot(DiffSlot &s) {
     dev_free(s.d_a);
     dev_free(s.d_shift);
     dev_free(s.d_jlen);
+    dev_free(s.d_known);
     dev_free(s.d_ex);
     dev_free(s.d_ey);
     dev_free(s.d_gbx);
@@ -500,6 +501,10 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
     QPB_ALLOC(s.d_a, ne);
     QPB_ALLOC(s.d_shift, (size_t)ne * jmax);
     QPB_ALLOC(s.d_jlen, ne);
+    QPB_ALLOC(s.d_known, ne);
+    QPB_CUDA(cudaMemsetAsync(s.d_known, 0, sizeof(int) * ne, c->stream));
+    s.known_iters = 0;
+    s.solves = 0;
     QPB_CUDA(cudaMemcpyAsync(s.d_a, s.a_bin.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, c->stream));
     QPB_CUDA(cudaMemcpyAsync(s.d_shift, flat.data(), sizeof(double) * flat.size(), cudaMemcpyHostToDevice, c->stream));
     QPB_CUDA(cudaMemcpyAsync(s.d_jlen, s.jlen.data(), sizeof(int) * ne, cudaMemcpyHostToDevice, c->stream));

@@ -48,11 +48,14 @@ struct DiffSlot {
     bool commuting = false;
     int jmax = 0;              // row length of the shift table
     int launch_iters = 0;      // iterations launched before the first host check
+    int known_iters = 0;       // iterations the previous solve needed (0: unknown)
+    long long solves = 0;      // solves done with this slot
     std::vector<double> a_bin; // 0.5*dt*D_i/dx^2 per bin (uniform D)
     std::vector<int> jlen;     // shifts per bin
     double *d_a = nullptr;     // [ne]
     double *d_shift = nullptr; // [ne][jmax]
     int *d_jlen = nullptr;     // [ne]
+    int *d_known = nullptr;    // [ne] iterations the previous solve needed per bin (0: unknown)
     // variable-D coefficient fields (dense, per bin): links to the left / up neighbour, boundary diagonals
     double *d_ex = nullptr, *d_ey = nullptr, *d_gbx = nullptr, *d_gby = nullptr;
     // source term dt*D*s, dense [ncd] (uniform: multiplied by D_i on the fly) or [ne][ncd] (variable)
@@ -60,6 +63,7 @@ struct DiffSlot {
     // fast path tables (uniform D, chunked sweeps)
     struct FastDir {
         int n = 0, S = 0, Q = 0, npad = 0, nclass = 0;
+        int carry_depth = 0;       // chunks a carry must be propagated through (products of g below 1e-18 beyond)
         int *d_cls = nullptr;      // class of every line
         double *d_tab = nullptr;   // [ne][jmax][nclass][npad] pivot reciprocals m (x: chunk-interleaved), 0 outside the mask
         double *d_tabg = nullptr;  // same layout: g_t = e_{t+1} m_t
@@ -138,10 +142,10 @@ int qpbk_build_rhs(qpb_ctx *c, DiffSlot &s);
 int qpbk_sweep_generic(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
 int qpbk_diffuse(qpb_ctx *c, DiffSlot &s);
 int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s);
-int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
+int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode, bool check = true);
 int qpbp_chunk(int n, int dir);
 int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p);
-int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter);
+int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check);
 void qpbk_free_slot(DiffSlot &s);
 
 int qpbk_collide(qpb_ctx *c, double dt);

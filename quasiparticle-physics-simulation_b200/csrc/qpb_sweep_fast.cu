@@ -44,7 +44,7 @@ namespace {
 __global__ void k_factor(int ne, int jmax, int nclass, int npad, int S, int interleave, double sigma,
                          const double *__restrict__ a_bin, const double *__restrict__ shift,
                          const int *__restrict__ jlen, const uint8_t *__restrict__ lk, const double *__restrict__ bc,
-                         double *__restrict__ tab, double *__restrict__ tabg) {
+                         double *__restrict__ tab, double *__restrict__ tabg, unsigned long long *__restrict__ amax) {
     const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const long long total = (long long)ne * jmax * nclass;
     if (gid >= total) return;
@@ -59,7 +59,7 @@ __global__ void k_factor(int ne, int jmax, int nclass, int npad, int S, int inte
     double *out = tab + (size_t)gid * npad;
     double *outg = tabg ? tabg + (size_t)gid * npad : nullptr;
     const int Q = npad / S;
-    double mprev = 0.0;
+    double mprev = 0.0, prod = 1.0, pmax = 0.0;
     for (int k = 0; k < npad; ++k) {
         const double e = (l[k] & 1) ? a : 0.0, en = (l[k + 1] & 1) ? a : 0.0;
         const double m = (l[k] & 2) ? 1.0 / (sigma + rho + e + en + a * g[k] - e * e * mprev) : 0.0;
@@ -67,7 +67,13 @@ __global__ void k_factor(int ne, int jmax, int nclass, int npad, int S, int inte
         const int pos = interleave ? (((k % S) / 2) * Q + k / S) * 2 + (k & 1) : k;
         out[pos] = m;
         if (outg) outg[pos] = en * m;
+        prod *= en * m;                       // coupling of a chunk to its neighbour: product of its g
+        if (k % S == S - 1) {
+            pmax = fmax(pmax, prod);
+            prod = 1.0;
+        }
     }
+    if (amax) atomicMax(amax, (unsigned long long)__double_as_longlong(pmax));
 }
 
 // ---- affine-map scans ------------------------------------------------------------------------------------
@@ -670,12 +676,26 @@ static int setup_dir(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir, bo
     QPB_CUDA(cudaMalloc((void **)&fd.d_tab, sizeof(double) * tab_elems));
     if (pipe) QPB_CUDA(cudaMalloc((void **)&fd.d_tabg, sizeof(double) * tab_elems));
     const long long total = (long long)cf.ne * s.jmax * ci.nclass;
+    unsigned long long *d_amax = nullptr;
+    QPB_CUDA(cudaMalloc((void **)&d_amax, sizeof(unsigned long long)));
+    QPB_CUDA(cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), c->stream));
     k_factor<<<(int)ceil_div64(total, 64), 64, 0, c->stream>>>(cf.ne, s.jmax, ci.nclass, fd.npad, fd.S, interleave ? 1 : 0,
                                                               direct ? 1.0 : 0.5, s.d_a, s.d_shift, s.d_jlen,
-                                                              (const uint8_t *)(blob + cb), d_bc, fd.d_tab, fd.d_tabg);
+                                                              (const uint8_t *)(blob + cb), d_bc, fd.d_tab, fd.d_tabg, d_amax);
     c->diag.kernel_launches++;
     QPB_CHECK_LAUNCH();
+    unsigned long long bits = 0;
+    QPB_CUDA(cudaMemcpyAsync(&bits, d_amax, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(d_amax);
+    {   // how many neighbouring chunks a carry can reach before it drops below one part in 1e18
+        double am;
+        memcpy(&am, &bits, sizeof(am));
+        int depth = fd.Q;
+        if (am <= 0.0) depth = 1;
+        else if (am < 1.0) depth = (int)std::ceil(std::log(1e-18) / std::log(am));
+        fd.carry_depth = std::max(1, std::min(depth, fd.Q));
+    }
     cudaFree(d_bc);
     return 0;
 }
@@ -837,9 +857,9 @@ static int dispatch_x(qpb_ctx *c, const SweepArgs &A) {
     }
 }
 
-int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode) {
-    if (mode == 0 && dir == 0 && s.pipe.x_ok) return qpbp_sweep(c, s, 0, iter);
-    if (mode == 1 && dir == 1 && s.pipe.y_ok) return qpbp_sweep(c, s, 1, iter);
+int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode, bool check) {
+    if (mode == 0 && dir == 0 && s.pipe.x_ok) return qpbp_sweep(c, s, 0, iter, check);
+    if (mode == 1 && dir == 1 && s.pipe.y_ok) return qpbp_sweep(c, s, 1, iter, check);
     const auto &cf = c->cfg;
     const DiffSlot::FastDir &fd = dir == 0 ? s.fx : s.fy;
     const int nlines = dir == 0 ? cf.ny : cf.nx;

@@ -70,10 +70,12 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // Inclusive Kogge-Stone scan of affine maps over WIDTH adjacent lanes; returns the carry entering this lane's chunk.
+// `reach`: only offsets below it are composed (the maps contract so fast that farther chunks cannot be felt).
 template <int WIDTH, bool REVERSE>
-__device__ __forceinline__ double warp_carry(double A, double B, int q) {
+__device__ __forceinline__ double warp_carry(double A, double B, int q, int reach) {
 #pragma unroll
     for (int off = 1; off < WIDTH; off <<= 1) {
+        if (off >= reach) break;
         const double Ao = REVERSE ? __shfl_down_sync(0xffffffffu, A, off, WIDTH) : __shfl_up_sync(0xffffffffu, A, off, WIDTH);
         const double Bo = REVERSE ? __shfl_down_sync(0xffffffffu, B, off, WIDTH) : __shfl_up_sync(0xffffffffu, B, off, WIDTH);
         const bool has = REVERSE ? (q + off < WIDTH) : (q >= off);
@@ -98,6 +100,9 @@ struct PipeArgs {
     const double *tabm, *tabg;   // [ne][jmax][nclass][npad]
     int nclass, npad, Q;         // Q = chunks per line
     int tiles_per_bin, ntiles;
+    int depth;                   // carry reach in chunks (see FastDir::carry_depth)
+    int check_all;               // 1: every bin measures / tests the residual in this iteration
+    const int *known;            // [ne] iterations the previous solve of each bin needed (<= 0: unknown)
     unsigned long long *res, *unorm;
     int *done, *iters_out;
 };
@@ -111,10 +116,18 @@ struct YMaps {
 
 // MODE 0 (x sweep): a bin is active until it is marked done.  MODE 1 (y sweep): additionally the residual that the
 // x sweep of this iteration measured decides; the first tile of a bin records the decision.
+// A bin measures (x sweep) and tests (y sweep) the residual only from two iterations before the count its previous
+// solve needed: consecutive time steps need about as many, and the unchecked sweeps skip a third of the arithmetic.
+__device__ __forceinline__ bool bin_checks(const PipeArgs &A, int bin) {
+    if (A.check_all) return true;
+    const int kn = A.known[bin];
+    return kn <= 0 || A.iter >= kn - 2;
+}
+
 template <int MODE>
 __device__ __forceinline__ bool tile_active(const PipeArgs &A, int bin, bool leader) {
     if (A.done[bin]) return false;
-    if (MODE == 1) {
+    if (MODE == 1 && bin_checks(A, bin)) {
         const double r = __longlong_as_double((long long)A.res[(long long)A.iter * A.ne + bin]);
         const double un = __longlong_as_double((long long)A.unorm[(long long)A.iter * A.ne + bin]);
         if (r <= A.tol * un) {
@@ -187,7 +200,7 @@ __device__ __forceinline__ void load_bin_params(const PipeArgs &A, double *s_a, 
     for (int b = threadIdx.x; b < A.ne; b += NT) {
         const bool act = tile_active<MODE>(A, b, blockIdx.x == 0);
         const int j = A.iter % A.jlen[b];
-        s_j[b] = act ? j : -1;
+        s_j[b] = act ? (j | (bin_checks(A, b) ? 0x10000 : 0)) : -1;   // bit 16: this bin measures the residual
         s_a[b] = A.a_bin[b];
         s_rho[b] = A.shift[(long long)b * A.jmax + j];
     }
@@ -252,6 +265,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
     const int g = tid / QP, q = tid - g * QP;
     const bool qok = q < Q;
     const int qc = qok ? q : Q - 1;
+    const int reach = A.depth + 1;           // an inclusive scan over offsets < reach covers `depth` earlier chunks
     const int r16 = (qc * S) >> 4;             // 128-byte unit of this chunk within its row
     const int ubase = ((qc * S) & 15) >> 1;    // first 16-byte unit of the chunk inside that 128-byte unit
     const int nx = A.nx;
@@ -265,8 +279,10 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
     bool rowok = false;
     for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
         const int bin = t / tpb;
-        const int jidx = s_j[bin];
-        if (jidx < 0) continue;
+        const int jraw = s_j[bin];
+        if (jraw < 0) continue;
+        const int jidx = jraw & 0xffff;
+        const bool chk = (jraw & 0x10000) != 0;
         const int y0 = (t - bin * tpb) * R;
         const int y = y0 + g;
         // every thread finished reading the stage of tile k-1 before the last named barrier of that iteration
@@ -345,14 +361,16 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
                     const double along = fma(cx[tt], u0, -left) - right;
                     const double d = fma(-a, cross, fma(rm, u0, bv));      // b - (V - rho) u
                     ch.v[tt] = d;
-                    const double rres = fma(-a, along, fma(-rp, u0, d));   // b - A u
-                    const int rh = __double2hiint(rres) & 0x7fffffff;
-                    if (flw[tt >> 2] & (16u << (8 * (tt & 3)))) rhi = max(rhi, rh);
-                    uhi = max(uhi, __double2hiint(u0) & 0x7fffffff);
+                    if (chk) {
+                        const double rres = fma(-a, along, fma(-rp, u0, d));   // b - A u
+                        const int rh = __double2hiint(rres) & 0x7fffffff;
+                        if (flw[tt >> 2] & (16u << (8 * (tt & 3)))) rhi = max(rhi, rh);
+                        uhi = max(uhi, __double2hiint(u0) & 0x7fffffff);
+                    }
                 }
             }
         }
-        {
+        if (chk) {
             rhi = __reduce_max_sync(0xffffffffu, rhi);
             uhi = __reduce_max_sync(0xffffffffu, uhi);
             if ((tid & 31) == 0) {
@@ -363,10 +381,10 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         }
         double Am, Bm;
         ch.forward(Am, Bm);
-        const double yin = warp_carry<QP, false>(Am, Bm, q);
+        const double yin = warp_carry<QP, false>(Am, Bm, q, reach);
         ch.forward_fix(yin);
         Bm = ch.backward();
-        const double xin = warp_carry<QP, true>(Am, Bm, q);
+        const double xin = warp_carry<QP, true>(Am, Bm, q, reach);
         ch.backward_fix(xin);
         // ---- out tile ----
         const int ob = k & 1;
@@ -461,7 +479,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         const int bin = t / tpb;
         const int x = min((t - bin * tpb) * CW + c, A.nx - 1);
         const int cls = A.cls[x];
-        const size_t base = (((size_t)bin * A.jmax + s_j[bin]) * A.nclass + cls) * npad + r0;
+        const size_t base = (((size_t)bin * A.jmax + (s_j[bin] & 0xffff)) * A.nclass + cls) * npad + r0;
         const double2 *pm = reinterpret_cast<const double2 *>(A.tabm + base);
         const double2 *pg = reinterpret_cast<const double2 *>(A.tabg + base);
 #pragma unroll
@@ -506,14 +524,14 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         cB[q * CW + c] = Bm;
         cta_bar<NT>(2);
         double cin = 0.0;
-        for (int kk = 0; kk < q; ++kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
+        for (int kk = max(0, q - A.depth); kk < q; ++kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
         ch.forward_fix(cin);
         Bm = ch.backward();
         cta_bar<NT>(3);
         cB[q * CW + c] = Bm;
         cta_bar<NT>(4);
         cin = 0.0;
-        for (int kk = NCH - 1; kk > q; --kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
+        for (int kk = min(NCH - 1, q + A.depth); kk > q; --kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
         ch.backward_fix(cin);
         const int ob = k & 1;
         double *so = reinterpret_cast<double *>(out_base + (size_t)ob * strip_bytes) + (size_t)r0 * CW + c;
@@ -726,7 +744,7 @@ static int dispatch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid
 #undef QPB_Y
 }
 
-int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter) {
+int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check) {
     const auto &cf = c->cfg;
     const PipePlan &p = s.pipe;
     const DiffSlot::FastDir &fd = dir == 0 ? s.fx : s.fy;
@@ -737,6 +755,9 @@ int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter) {
     A.cls = fd.d_cls;
     A.tabm = fd.d_tab; A.tabg = fd.d_tabg; A.nclass = fd.nclass; A.npad = fd.npad; A.Q = fd.Q;
     A.res = c->d_res; A.unorm = c->d_unorm; A.done = c->d_done; A.iters_out = c->d_done + cf.ne;
+    A.depth = std::max(1, fd.carry_depth);
+    A.check_all = check ? 1 : 0;
+    A.known = s.d_known;
     ScopedTimer tm(c, dir == 0 ? 0 : 1);
     c->diag.kernel_launches++;
     if (dir == 0) {
