@@ -196,7 +196,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     dev_free(c->d_Kr); dev_free(c->d_Ks); dev_free(c->d_KrT); dev_free(c->d_KsT); dev_free(c->d_rho);
     dev_free(c->d_gapid); dev_free(c->d_idxd); dev_free(c->d_idxs); dev_free(c->d_idxdT);
     dev_free(c->d_sign); dev_free(c->d_signT); dev_free(c->d_dmap); dev_free(c->d_smap);
-    dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_scratch); dev_free(c->d_gen);
+    dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_scratch); dev_free(c->d_gen);
     dev_free(c->d_integrated); dev_free(c->d_pauli);
     if (c->d_pauli_part) cudaFree(c->d_pauli_part);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -669,6 +669,7 @@ extern "C" int qpb_set_state(qpb_ctx *c, const double *n, const double *n_ph) {
         QPB_CUDA(cudaMemcpyAsync(c->d_P, n_ph, sizeof(double) * (size_t)cf.nw * cf.ncell, cudaMemcpyHostToDevice,
                                  c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));
+    if (cf.nw > 0 && n_ph) return qpbk_uniform_setup(c, n_ph);
     return QPB_OK;
 }
 

@@ -174,6 +174,7 @@ __global__ void __launch_bounds__(128) k_collide_generic(GenericArgs A) {
 }
 
 #include "qpb_collide_struct.cuh"
+#include "qpb_collide_uniform.cuh"
 
 struct StructTables {
     double2 *K2 = nullptr;
@@ -287,6 +288,75 @@ static int launch_generic(qpb_ctx *c, const GenericArgs &A, size_t smem) {
     return QPB_OK;
 }
 
+// ---- frozen, cell-independent phonons: packed effective kernels (solver.py:726-743 with a shared n_ph) -----------
+int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph) {
+    const auto &cf = c->cfg;
+    const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
+    c->uniform_ph = false;
+    if (!(cf.flags & QPB_F_FREEZE_PHONONS) || !(scat || rec) || cf.ngap != 1 || !n_ph || !c->have_coll) return QPB_OK;
+    if (getenv("QPB_NO_UNIFORM") && getenv("QPB_NO_UNIFORM")[0] == '1') return QPB_OK;
+    const int ne = cf.ne, nw = cf.nw;
+    const int nep = ((ne + TI - 1) / TI) * TI;
+    std::vector<double> ph(nw);
+    for (int o = 0; o < nw; ++o) {
+        const double *row = n_ph + (size_t)o * cf.ncell;
+        ph[o] = row[0];
+        for (int q = 1; q < cf.ncell; ++q)
+            if (row[q] != ph[o]) return QPB_OK;   // occupations differ between cells: general kernels
+    }
+    std::vector<double> Ks((size_t)ne * ne, 0.0), Kr((size_t)ne * ne, 0.0), rho(ne);
+    std::vector<int32_t> idd((size_t)ne * ne), ids((size_t)ne * ne);
+    std::vector<int8_t> sg((size_t)ne * ne);
+    if (scat) QPB_CUDA(cudaMemcpy(Ks.data(), c->d_Ks, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost));
+    if (rec) QPB_CUDA(cudaMemcpy(Kr.data(), c->d_Kr, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost));
+    QPB_CUDA(cudaMemcpy(rho.data(), c->d_rho, sizeof(double) * ne, cudaMemcpyDeviceToHost));
+    QPB_CUDA(cudaMemcpy(idd.data(), c->d_idxd, sizeof(int32_t) * ne * ne, cudaMemcpyDeviceToHost));
+    QPB_CUDA(cudaMemcpy(ids.data(), c->d_idxs, sizeof(int32_t) * ne * ne, cudaMemcpyDeviceToHost));
+    QPB_CUDA(cudaMemcpy(sg.data(), c->d_sign, sizeof(int8_t) * ne * ne, cudaMemcpyDeviceToHost));
+    const double dE = cf.dE;
+    auto ke = [&](int i, int j) {   // dE * Ks[i,j] * Np[i,j], zero diagonal (solver.py:730-732)
+        if (i == j || !scat) return 0.0;
+        const double nd = ph[idd[(size_t)i * ne + j]];
+        return dE * (Ks[(size_t)i * ne + j] * (sg[(size_t)i * ne + j] > 0 ? 1.0 + nd : nd));
+    };
+    std::vector<double> K4((size_t)4 * nep * nep, 0.0), rhop(nep, 0.0);
+    for (int i = 0; i < ne; ++i) {
+        rhop[i] = rho[i];
+        for (int j = 0; j < ne; ++j) {
+            double *o = &K4[((size_t)i * nep + j) * 4];
+            o[0] = ke(i, j);
+            o[1] = ke(j, i);
+            if (rec) {
+                const double ns = ph[ids[(size_t)i * ne + j]], kr = Kr[(size_t)i * ne + j];
+                o[2] = 2.0 * dE * (kr * (1.0 + ns));
+                o[3] = 2.0 * dE * (kr * ns);
+            }
+        }
+    }
+    if (c->d_K4) cudaFree(c->d_K4);
+    c->d_K4 = nullptr;
+    QPB_CUDA(cudaMalloc((void **)&c->d_K4, sizeof(double) * (K4.size() + nep)));
+    QPB_CUDA(cudaMemcpy(c->d_K4, K4.data(), sizeof(double) * K4.size(), cudaMemcpyHostToDevice));
+    QPB_CUDA(cudaMemcpy(c->d_K4 + K4.size(), rhop.data(), sizeof(double) * nep, cudaMemcpyHostToDevice));
+    c->uniform_ph = true;
+    return QPB_OK;
+}
+
+template <int CC, int NT>
+static int launch_uniform(qpb_ctx *c, const UniformArgs &A) {
+    auto kern = k_collide_uniform<CC, NT>;
+    const size_t smem = sizeof(double) * (size_t)2 * A.nep * CC + (size_t)(NT / 32) * (32 / CC) * NSTAGE * (TI * TJ * 32);
+    static bool configured = false;
+    if (!configured) {
+        QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        configured = true;
+    }
+    if (smem > 227 * 1024) return 1;
+    kern<<<(A.ncell + CC - 1) / CC, NT, smem, c->stream>>>(A);
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
 int qpbk_collide(qpb_ctx *c, double dt) {
     const auto &cf = c->cfg;
     const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
@@ -294,6 +364,19 @@ int qpbk_collide(qpb_ctx *c, double dt) {
     ScopedTimer tm(c, 2);
     c->diag.kernel_launches++;
     const size_t smem_cap = 227 * 1024;
+    if (c->uniform_ph && !ph && (scat || rec)) {
+        UniformArgs U;
+        U.ne = cf.ne; U.nep = ((cf.ne + TI - 1) / TI) * TI; U.ncell = cf.ncell; U.ncd = c->ncd;
+        U.S = c->d_S; U.c2d = c->d_cell2dense;
+        U.K4 = reinterpret_cast<const double4 *>(c->d_K4);
+        U.rho = c->d_K4 + (size_t)4 * U.nep * U.nep;
+        U.dt = dt;
+        int rc = launch_uniform<32, 512>(c, U);
+        if (rc <= 0) return rc;
+        rc = launch_uniform<8, 256>(c, U);
+        if (rc <= 0) return rc;
+        // too many energy bins for the shared-memory columns: general kernels below
+    }
     if (c->structured && (scat || rec)) {
         StructTables t = carve_tables(c);
         StructArgs A;

@@ -120,6 +120,8 @@ struct qpb_ctx {
     int32_t *d_kof = nullptr, *d_mof = nullptr;  // phonon bin -> k / m or -1   [nw]
     std::vector<int32_t> h_dmap, h_smap, h_kof, h_mof;  // host copies (ride in the kernel parameters)
     double *d_P = nullptr;            // phonon state [nw][ncell]
+    bool uniform_ph = false;          // frozen phonons, identical in every cell: packed effective kernels in d_K4
+    double *d_K4 = nullptr;           // [nep][nep][4] + rho[nep]
     double *d_scratch = nullptr;      // collision scratch
     size_t scratch_bytes = 0;
     // generation array
@@ -150,6 +152,7 @@ void qpbk_free_slot(DiffSlot &s);
 
 int qpbk_collide(qpb_ctx *c, double dt);
 int qpbk_collision_setup(qpb_ctx *c);
+int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph);   // host phonon state [nw][ncell] or null
 
 int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_array);
 int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out);

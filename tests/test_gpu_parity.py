@@ -188,3 +188,31 @@ def test_pipelined_and_legacy_sweeps_agree(monkeypatch):
     monkeypatch.setenv("QPB_NO_PIPE", "1")
     b = helpers.run_dropin(case)
     helpers.assert_close(a["state"], b["state"], "pipe vs legacy", rtol=1e-10)
+
+
+@pytest.mark.parametrize("flags", [(True, True), (True, False), (False, True)])
+def test_frozen_uniform_phonons_use_packed_kernels_and_match(flags, monkeypatch):
+    """freeze_phonon_dynamics with the same occupations in every cell runs the fused 4-product kernel
+    (qpb_collide_uniform.cuh); it must agree with the general structured kernel and with the oracle."""
+    rec, sc = flags
+    rng = np.random.default_rng(17)
+    ne, n = 40, 75
+    E, dE = Q.build_energy_grid(cases.GAP, 1.0, 4.0, ne)
+    om, idd, ids, sg = Q.phonon_frequency_map(E)
+    rho = Q.density_of_states(E, cases.GAP, 0.18)
+    Kr = Q.recombination_kernel_base(E, cases.GAP, 300.0, 1.2)
+    Ks = Q.scattering_kernel_base(E, cases.GAP, 500.0, 1.2)
+    state0 = rho[:, None] * rng.uniform(0, 0.6, (ne, n))
+    ph0 = Q.thermal_phonon_occupation(om, 0.35)[:, None] * np.ones((1, n))
+    outs = []
+    for no_uniform in ("0", "1"):
+        monkeypatch.setenv("QPB_NO_UNIFORM", no_uniform)
+        s, p = state0.copy(), ph0.copy()
+        Q.apply_collision_step_fischer_catelani_uniform(s, p, Kr, Ks, rho, idd, ids, sg, dE, 0.4, enable_recombination=rec,
+                                                        enable_scattering=sc, update_phonons=False)
+        assert np.array_equal(p, ph0)
+        outs.append(s)
+    s_ref, p_ref = state0.copy(), ph0.copy()
+    O.collide(s_ref, p_ref, Kr, Ks, rho, idd, ids, sg, dE, 0.4, recomb=rec, scat=sc, update_phonons=False)
+    helpers.assert_close(outs[0].T, s_ref.T, "packed kernels vs oracle", rtol=1e-11)
+    helpers.assert_close(outs[0].T, outs[1].T, "packed vs structured kernel", rtol=1e-11)
