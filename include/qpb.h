@@ -128,8 +128,14 @@ int qpb_upload_collision(qpb_ctx *ctx, const double *K_r0, const double *K_s0, c
 /* state in the reference layouts; n_ph may be NULL when nw == 0 */
 int qpb_set_state(qpb_ctx *ctx, const double *n, const double *n_ph);
 int qpb_get_state(qpb_ctx *ctx, double *n, double *n_ph);
+/* same as qpb_set_state for the reference's default initial phonon state n_ph_eq[:, None] * ones((1, N))
+ * (solver.py:1183-1185): one occupation per phonon bin [Nw], broadcast over the cells on the device */
+int qpb_set_state_uniform_phonons(qpb_ctx *ctx, const double *n, const double *n_ph_bins);
 /* energy-integrated field  sum_i n[i][cell]*dE  (solver.py:1480), [N] */
 int qpb_get_integrated(qpb_ctx *ctx, double *out);
+/* the NE stored energy frames of one snapshot, dense [NE][ny][nx] with NaN outside the mask: what the reference
+ * builds with NE calls of reconstruct_field (solver.py:215-218, 1484-1486), assembled on the device */
+int qpb_get_frames(qpb_ctx *ctx, double *frames);
 
 /* external generation (solver.py:878-964, 1459-1464) */
 #define QPB_GEN_NONE     0
@@ -199,6 +205,10 @@ int qpb_add_generation(qpb_ctx *ctx, double scale, double rate);
  * exchanges need no host synchronisation between them.  scatter/gather_block and add_generation are stream
  * ordered (no host sync); every call that returns data to the host synchronises that stream. */
 int qpb_set_stream(qpb_ctx *ctx, void *cuda_stream);
+
+/* Device buffers of destroyed contexts are parked in a bounded per-process cache (QPB_CACHE_MB, default 4096) so
+ * that back-to-back runs of the same shape do not pay cudaMalloc/cudaFree again; this returns them to the driver. */
+int qpb_trim_cache(void);
 
 #ifdef __cplusplus
 }

@@ -77,7 +77,7 @@ EXPORTED = [
     "qpb_set_state", "qpb_get_state", "qpb_get_integrated", "qpb_advance", "qpb_collide", "qpb_diffuse",
     "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
     "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
-    "qpb_add_generation", "qpb_set_stream",
+    "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons",
 ]
 
 
@@ -144,7 +144,10 @@ def load_library():
     lib.qpb_upload_collision.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]
     lib.qpb_set_state.argtypes = [vp, vp, vp]
     lib.qpb_get_state.argtypes = [vp, vp, vp]
+    lib.qpb_set_state_uniform_phonons.argtypes = [vp, vp, vp]
     lib.qpb_get_integrated.argtypes = [vp, vp]
+    lib.qpb_get_frames.argtypes = [vp, vp]
+    lib.qpb_trim_cache.argtypes = []
     lib.qpb_advance.argtypes = [vp, i32, dbl, i32, dbl, C.POINTER(Generation), vp]
     lib.qpb_collide.argtypes = [vp, dbl]
     lib.qpb_diffuse.argtypes = [vp, i32]
@@ -250,8 +253,14 @@ class Context:
         p = None if (n_ph is None or self.nw == 0) else _f64(n_ph, (self.nw, self.ncell))
         self._check(self.lib.qpb_set_state(self.handle, _ptr(a), _ptr(p)))
 
-    def get_state(self, want_phonons=True):
-        n = np.empty((self.ne, self.ncell))
+    def set_state_uniform_phonons(self, n, n_ph_bins):
+        """State upload when every cell starts from the same phonon occupations (one value per phonon bin)."""
+        a = _f64(n, (self.ne, self.ncell))
+        p = None if self.nw == 0 else _f64(n_ph_bins, (self.nw,))
+        self._check(self.lib.qpb_set_state_uniform_phonons(self.handle, _ptr(a), _ptr(p)))
+
+    def get_state(self, want_phonons=True, want_qp=True):
+        n = np.empty((self.ne, self.ncell)) if want_qp else None
         p = np.empty((self.nw, self.ncell)) if (want_phonons and self.nw > 0) else None
         self._check(self.lib.qpb_get_state(self.handle, _ptr(n), _ptr(p)))
         return n, p
@@ -259,6 +268,12 @@ class Context:
     def get_integrated(self):
         out = np.empty(self.ncell)
         self._check(self.lib.qpb_get_integrated(self.handle, _ptr(out)))
+        return out
+
+    def get_frames(self):
+        """The NE stored energy frames of one snapshot, (NE, ny, nx) with NaN outside the mask."""
+        out = np.empty((self.ne, self.ny, self.nx))
+        self._check(self.lib.qpb_get_frames(self.handle, _ptr(out)))
         return out
 
     # ---- stepping ------------------------------------------------------------------------------------

@@ -7,7 +7,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <random>
+#include <unordered_map>
 
 static thread_local std::string g_err;
 
@@ -39,11 +41,112 @@ extern "C" int qpb_device_count(void) {
     return usable;
 }
 
+// ---- device block cache ------------------------------------------------------------------------------------
+// cudaMalloc / cudaFree of the state-sized arrays cost ~100 ms each way per run on the reference-facing path (one
+// context per run_2d_crank_nicolson call).  Freed blocks are parked here (exact-size reuse, per device) so that the
+// next run with the same shapes pays nothing; the cache is bounded (QPB_CACHE_MB, default 4096; 0 disables it),
+// evicts oldest first, and is emptied on an allocation failure before the allocation is retried.
+namespace {
+struct CachedBlock {
+    int device;
+    size_t bytes;
+    void *ptr;
+};
+std::mutex g_cache_mu;
+std::vector<CachedBlock> g_cache;                       // oldest first
+std::unordered_map<void *, size_t> g_live;              // bytes of every block handed out
+size_t g_cache_bytes = 0;
+
+size_t cache_cap() {
+    static size_t cap = [] {
+        const char *e = getenv("QPB_CACHE_MB");
+        const long long mb = e ? atoll(e) : 4096;
+        return (size_t)(mb < 0 ? 0 : mb) << 20;
+    }();
+    return cap;
+}
+
+void cache_release_all_locked() {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto &b : g_cache) {
+        cudaSetDevice(b.device);
+        cudaFree(b.ptr);
+    }
+    g_cache.clear();
+    g_cache_bytes = 0;
+    cudaSetDevice(cur);
+}
+}  // namespace
+
+cudaError_t qpb_dev_malloc(void **p, size_t bytes) {
+    *p = nullptr;
+    if (bytes == 0) return cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    for (size_t i = g_cache.size(); i-- > 0;)
+        if (g_cache[i].device == dev && g_cache[i].bytes == bytes) {
+            *p = g_cache[i].ptr;
+            g_cache_bytes -= bytes;
+            g_cache.erase(g_cache.begin() + i);
+            g_live[*p] = bytes;
+            // a block from the driver arrives zeroed; keep that property for recycled ones
+            cudaMemsetAsync(*p, 0, bytes, 0);
+            return cudaStreamSynchronize(0);
+        }
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess && !g_cache.empty()) {
+        cudaGetLastError();
+        cache_release_all_locked();
+        e = cudaMalloc(p, bytes);
+    }
+    if (e == cudaSuccess) g_live[*p] = bytes;
+    return e;
+}
+
+void qpb_dev_free(void *p) {
+    if (!p) return;
+    // what cudaFree guarantees implicitly: nothing in flight still uses the block when somebody else gets it
+    cudaDeviceSynchronize();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    size_t bytes = 0;
+    auto it = g_live.find(p);
+    if (it != g_live.end()) {
+        bytes = it->second;
+        g_live.erase(it);
+    }
+    const size_t cap = cache_cap();
+    if (bytes == 0 || bytes > cap) {
+        cudaFree(p);
+        return;
+    }
+    while (g_cache_bytes + bytes > cap && !g_cache.empty()) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(g_cache.front().device);
+        cudaFree(g_cache.front().ptr);
+        cudaSetDevice(cur);
+        g_cache_bytes -= g_cache.front().bytes;
+        g_cache.erase(g_cache.begin());
+    }
+    g_cache.push_back({dev, bytes, p});
+    g_cache_bytes += bytes;
+}
+
+extern "C" int qpb_trim_cache(void) {
+    std::lock_guard<std::mutex> lk(g_cache_mu);
+    cache_release_all_locked();
+    return QPB_OK;
+}
+
 template <class T>
 static int dev_alloc(T **p, size_t count) {
     *p = nullptr;
     if (count == 0) return QPB_OK;
-    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T));
+    cudaError_t e = qpb_dev_malloc((void **)p, count * sizeof(T));
     if (e != cudaSuccess) {
         cudaGetLastError();
         qpb_set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
@@ -60,7 +163,7 @@ static int dev_alloc(T **p, size_t count) {
 
 template <class T>
 static void dev_free(T *&p) {
-    if (p) cudaFree(p);
+    if (p) qpb_dev_free(p);
     p = nullptr;
 }
 
@@ -198,7 +301,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     dev_free(c->d_sign); dev_free(c->d_signT); dev_free(c->d_dmap); dev_free(c->d_smap);
     dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_scratch); dev_free(c->d_gen);
     dev_free(c->d_integrated); dev_free(c->d_pauli);
-    if (c->d_pauli_part) cudaFree(c->d_pauli_part);
+    if (c->d_pauli_part) qpb_dev_free(c->d_pauli_part);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -673,6 +776,30 @@ extern "C" int qpb_set_state(qpb_ctx *c, const double *n, const double *n_ph) {
     return QPB_OK;
 }
 
+extern "C" int qpb_set_state_uniform_phonons(qpb_ctx *c, const double *n, const double *n_ph_bins) {
+    QPB_ENTER(c);
+    const auto &cf = c->cfg;
+    if (!c->have_geom || !n || (cf.nw > 0 && !n_ph_bins)) {
+        qpb_set_error("qpb_set_state_uniform_phonons: upload the geometry first and pass both arrays");
+        return QPB_E_INVALID;
+    }
+    QPB_CUDA(cudaMemcpyAsync(c->d_T1, n, sizeof(double) * (size_t)cf.ne * cf.ncell, cudaMemcpyHostToDevice, c->stream));
+    int rc = qpbk_scatter_state(c, c->d_T1);
+    if (rc != QPB_OK) return rc;
+    if (cf.nw > 0) {
+        double *d_bins = nullptr;
+        QPB_ALLOC(d_bins, cf.nw);
+        QPB_CUDA(cudaMemcpyAsync(d_bins, n_ph_bins, sizeof(double) * cf.nw, cudaMemcpyHostToDevice, c->stream));
+        rc = qpbk_broadcast_phonons(c, d_bins);
+        QPB_CUDA(cudaStreamSynchronize(c->stream));
+        dev_free(d_bins);
+        if (rc != QPB_OK) return rc;
+        return qpbk_uniform_setup(c, n_ph_bins, true);
+    }
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
 extern "C" int qpb_get_state(qpb_ctx *c, double *n, double *n_ph) {
     QPB_ENTER(c);
     const auto &cf = c->cfg;
@@ -698,6 +825,22 @@ extern "C" int qpb_get_integrated(qpb_ctx *c, double *out) {
     int rc = qpbk_integrate(c);
     if (rc != QPB_OK) return rc;
     QPB_CUDA(cudaMemcpyAsync(out, c->d_integrated, sizeof(double) * c->cfg.ncell, cudaMemcpyDeviceToHost, c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
+extern "C" int qpb_get_frames(qpb_ctx *c, double *frames) {
+    QPB_ENTER(c);
+    if (!frames || !c->have_geom) {
+        qpb_set_error("qpb_get_frames: null output or no geometry");
+        return QPB_E_INVALID;
+    }
+    int rc = qpbk_frames(c, c->d_T1);   // T1 is free between solves (it also stages qpb_get_state)
+    if (rc != QPB_OK) return rc;
+    QPB_CUDA(cudaMemcpyAsync(frames, c->d_T1, sizeof(double) * (size_t)c->cfg.ne * c->ncd, cudaMemcpyDeviceToHost,
+                             c->stream));
+    // no NaN may survive in a work array: 0 * NaN would leak into cells outside the mask
+    QPB_CUDA(cudaMemsetAsync(c->d_T1, 0, sizeof(double) * (size_t)c->cfg.ne * c->ncd, c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));
     return QPB_OK;
 }

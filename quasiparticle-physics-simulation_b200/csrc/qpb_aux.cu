@@ -30,6 +30,17 @@ __global__ void k_gather_state(int ne, int ncell, int ncd, double *__restrict__ 
     }
 }
 
+// frames[i][p] = cell p in the mask ? S[i][p] : NaN   (reconstruct_field for every bin, solver.py:215-218)
+__global__ void k_frames(long long total, int ncd, const double *__restrict__ S, const uint8_t *__restrict__ flags,
+                         double *__restrict__ out) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int p = (int)(g % ncd);
+        out[g] = (flags[p] & QPB_IN) ? S[g] : nan;
+    }
+}
+
 // state += scale * g   (g: one rate for every bin and cell, or a host-evaluated array [ne][ncell])
 __global__ void k_add_generation(int ne, int ncell, int ncd, double *__restrict__ S,
                                  const int32_t *__restrict__ c2d, double scale, double rate,
@@ -155,6 +166,28 @@ int qpbk_gather_state(qpb_ctx *c, double *d_compact) {
     return QPB_OK;
 }
 
+__global__ void k_broadcast_rows(long long total, int ncell, const double *__restrict__ bins, double *__restrict__ P) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x)
+        P[g] = bins[g / ncell];
+}
+
+int qpbk_broadcast_phonons(qpb_ctx *c, const double *d_bins) {
+    const long long total = (long long)c->cfg.nw * c->cfg.ncell;
+    k_broadcast_rows<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(total, c->cfg.ncell, d_bins, c->d_P);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int qpbk_frames(qpb_ctx *c, double *d_out) {
+    const long long total = (long long)c->cfg.ne * c->ncd;
+    k_frames<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(total, c->ncd, c->d_S, c->d_flags, d_out);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
 int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_array) {
     const auto &cf = c->cfg;
     const long long total = (long long)cf.ne * cf.ncell;
@@ -179,10 +212,10 @@ int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out) {
     const long long total = (long long)cf.ne * cf.ncell;
     const int blocks = grid_for(total, 256, 148 * 8);
     if (!c->d_pauli_part || c->pauli_blocks < blocks) {
-        if (c->d_pauli_part) cudaFree(c->d_pauli_part);
+        if (c->d_pauli_part) qpb_dev_free(c->d_pauli_part);
         c->d_pauli_part = nullptr;
         c->pauli_blocks = 148 * 8;
-        QPB_CUDA(cudaMalloc(&c->d_pauli_part, sizeof(PauliPart) * c->pauli_blocks));
+        QPB_CUDA(qpb_dev_malloc(&c->d_pauli_part, sizeof(PauliPart) * c->pauli_blocks));
     }
     k_pauli_stage1<<<blocks, 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S, c->d_cell2dense, c->d_rho,
                                                   c->d_gapid, cf.pauli_floor, (PauliPart *)c->d_pauli_part);

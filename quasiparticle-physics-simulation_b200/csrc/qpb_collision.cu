@@ -212,9 +212,9 @@ int qpbk_collision_setup(qpb_ctx *c) {
     const int nep = ((ne + TI - 1) / TI) * TI;
     const size_t bytes = sizeof(double2) * (size_t)nep * nep + sizeof(double) * (size_t)3 * nep * nep +
                          sizeof(double) * (size_t)nep;
-    if (c->d_scratch) cudaFree(c->d_scratch);
+    if (c->d_scratch) qpb_dev_free(c->d_scratch);
     c->d_scratch = nullptr;
-    QPB_CUDA(cudaMalloc((void **)&c->d_scratch, bytes));
+    QPB_CUDA(qpb_dev_malloc((void **)&c->d_scratch, bytes));
     c->scratch_bytes = bytes;
     // pull the uploaded matrices back (they are tiny) and build the padded / skewed copies
     std::vector<double> Ks((size_t)ne * ne, 0.0), Kr((size_t)ne * ne, 0.0), rho(ne);
@@ -289,7 +289,7 @@ static int launch_generic(qpb_ctx *c, const GenericArgs &A, size_t smem) {
 }
 
 // ---- frozen, cell-independent phonons: packed effective kernels (solver.py:726-743 with a shared n_ph) -----------
-int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph) {
+int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin) {
     const auto &cf = c->cfg;
     const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
     c->uniform_ph = false;
@@ -299,6 +299,10 @@ int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph) {
     const int nep = ((ne + TI - 1) / TI) * TI;
     std::vector<double> ph(nw);
     for (int o = 0; o < nw; ++o) {
+        if (per_bin) {   // the caller passed one occupation per phonon bin
+            ph[o] = n_ph[o];
+            continue;
+        }
         const double *row = n_ph + (size_t)o * cf.ncell;
         ph[o] = row[0];
         for (int q = 1; q < cf.ncell; ++q)
@@ -333,9 +337,9 @@ int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph) {
             }
         }
     }
-    if (c->d_K4) cudaFree(c->d_K4);
+    if (c->d_K4) qpb_dev_free(c->d_K4);
     c->d_K4 = nullptr;
-    QPB_CUDA(cudaMalloc((void **)&c->d_K4, sizeof(double) * (K4.size() + nep)));
+    QPB_CUDA(qpb_dev_malloc((void **)&c->d_K4, sizeof(double) * (K4.size() + nep)));
     QPB_CUDA(cudaMemcpy(c->d_K4, K4.data(), sizeof(double) * K4.size(), cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMemcpy(c->d_K4 + K4.size(), rhop.data(), sizeof(double) * nep, cudaMemcpyHostToDevice));
     c->uniform_ph = true;

@@ -17,6 +17,10 @@
 
 void qpb_set_error(const char *fmt, ...);
 
+// cached device allocations (qpb_api.cu): drop-in for cudaMalloc / cudaFree of library-owned buffers
+cudaError_t qpb_dev_malloc(void **p, size_t bytes);
+void qpb_dev_free(void *p);
+
 #define QPB_CUDA(expr)                                                                      \
     do {                                                                                    \
         cudaError_t _e = (expr);                                                            \
@@ -152,13 +156,15 @@ void qpbk_free_slot(DiffSlot &s);
 
 int qpbk_collide(qpb_ctx *c, double dt);
 int qpbk_collision_setup(qpb_ctx *c);
-int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph);   // host phonon state [nw][ncell] or null
+int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin = false);   // host phonon state [nw][ncell] ([nw] when per_bin) or null
+int qpbk_broadcast_phonons(qpb_ctx *c, const double *d_bins);  // P[o][q] = bins[o]
 
 int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_array);
 int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out);
 int qpbk_integrate(qpb_ctx *c);
 int qpbk_scatter_state(qpb_ctx *c, const double *d_compact);  // [ne][ncell] -> dense
 int qpbk_gather_state(qpb_ctx *c, double *d_compact);
+int qpbk_frames(qpb_ctx *c, double *d_out);                   // dense NaN-padded frames [ne][ncd]
 
 struct ScopedTimer {
     qpb_ctx *c;

@@ -666,18 +666,18 @@ static int setup_dir(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir, bo
     if (tab_elems * sizeof(double) * (pipe ? 2 : 1) > ((size_t)6 << 30)) return 1;  // irregular geometry: not worth tabulating
     const size_t cb = cls_bytes(nlines);
     char *blob = nullptr;
-    QPB_CUDA(cudaMalloc((void **)&blob, cb + ci.lk.size()));
+    QPB_CUDA(qpb_dev_malloc((void **)&blob, cb + ci.lk.size()));
     fd.d_cls = (int *)blob;
     QPB_CUDA(cudaMemcpy(blob, ci.cls.data(), sizeof(int) * nlines, cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMemcpy(blob + cb, ci.lk.data(), ci.lk.size(), cudaMemcpyHostToDevice));
     double *d_bc = nullptr;
-    QPB_CUDA(cudaMalloc((void **)&d_bc, sizeof(double) * ci.bc.size()));
+    QPB_CUDA(qpb_dev_malloc((void **)&d_bc, sizeof(double) * ci.bc.size()));
     QPB_CUDA(cudaMemcpy(d_bc, ci.bc.data(), sizeof(double) * ci.bc.size(), cudaMemcpyHostToDevice));
-    QPB_CUDA(cudaMalloc((void **)&fd.d_tab, sizeof(double) * tab_elems));
-    if (pipe) QPB_CUDA(cudaMalloc((void **)&fd.d_tabg, sizeof(double) * tab_elems));
+    QPB_CUDA(qpb_dev_malloc((void **)&fd.d_tab, sizeof(double) * tab_elems));
+    if (pipe) QPB_CUDA(qpb_dev_malloc((void **)&fd.d_tabg, sizeof(double) * tab_elems));
     const long long total = (long long)cf.ne * s.jmax * ci.nclass;
     unsigned long long *d_amax = nullptr;
-    QPB_CUDA(cudaMalloc((void **)&d_amax, sizeof(unsigned long long)));
+    QPB_CUDA(qpb_dev_malloc((void **)&d_amax, sizeof(unsigned long long)));
     QPB_CUDA(cudaMemsetAsync(d_amax, 0, sizeof(unsigned long long), c->stream));
     k_factor<<<(int)ceil_div64(total, 64), 64, 0, c->stream>>>(cf.ne, s.jmax, ci.nclass, fd.npad, fd.S, interleave ? 1 : 0,
                                                               direct ? 1.0 : 0.5, s.d_a, s.d_shift, s.d_jlen,
@@ -687,7 +687,7 @@ static int setup_dir(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir, bo
     unsigned long long bits = 0;
     QPB_CUDA(cudaMemcpyAsync(&bits, d_amax, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));
-    cudaFree(d_amax);
+    qpb_dev_free(d_amax);
     {   // how many neighbouring chunks a carry can reach before it drops below one part in 1e18
         double am;
         memcpy(&am, &bits, sizeof(am));
@@ -696,7 +696,7 @@ static int setup_dir(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir, bo
         else if (am < 1.0) depth = (int)std::ceil(std::log(1e-18) / std::log(am));
         fd.carry_depth = std::max(1, std::min(depth, fd.Q));
     }
-    cudaFree(d_bc);
+    qpb_dev_free(d_bc);
     return 0;
 }
 

@@ -359,7 +359,7 @@ def weak_tiling(world: int) -> tuple[int, int]:
     return ty, world // ty
 
 
-def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT):
+def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT, emit=None):
     import json
     import sys
 
@@ -453,6 +453,9 @@ def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT):
                     "note": "per rank: host state+phonons upload, K sharded steps, integrated field download"},
             "max_occupation": max(r[0] for r in merged),
         }
-        print(json.dumps(line))
+        if emit is not None:
+            emit(line)
+        else:
+            print(json.dumps(line))
     stages.close()
     dist.destroy_process_group()

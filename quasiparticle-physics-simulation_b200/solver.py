@@ -286,7 +286,9 @@ def run_2d_crank_nicolson(
 
     omega_bins, idx_diff, idx_sum, diff_sign = physics.phonon_frequency_map(E_bins)
     n_ph_eq = physics.thermal_phonon_occupation(omega_bins, bath_temperature)
-    phonon_state = n_ph_eq[:, None] * np.ones((1, n), dtype=float)
+    # default initial phonons: the bath occupation in every cell (solver.py:1183-1185).  The (Nw, N) host array is
+    # only materialised when somebody needs it; the device broadcasts the Nw values itself.
+    phonon_state = None
     if initial_condition_spec is not None:
         ic = _reference_module("initial_conditions")
         phonon_state = ic.build_initial_phonon_energy_state(
@@ -385,15 +387,20 @@ def run_2d_crank_nicolson(
         ctx.upload_collision(Kr_tab, Ks_tab, rho_tab, gap_id,
                              idx_diff if collisions else None, idx_sum if collisions else None,
                              diff_sign if collisions else None)
-        ctx.set_state(state, phonon_state if collisions else None)
+        if collisions and phonon_state is None:
+            ctx.set_state_uniform_phonons(state, n_ph_eq)
+        else:
+            ctx.set_state(state, phonon_state if collisions else None)
         policy.check(ctx.pauli(), 0, 0.0)
 
         if want_ph_hist:
+            if phonon_state is None:
+                phonon_state = n_ph_eq[:, None] * np.ones((1, n), dtype=float)
             snapshot_phonons(phonon_state)
         integrated = np.sum(state, axis=0) * dE
         times = [0.0]
         frames = [reconstruct_field(mask_b, integrated)]
-        energy_frames = [[reconstruct_field(mask_b, state[i]) for i in range(ne)]] if store_energy_frames else [None]
+        energy_frames = [list(ctx.get_frames())] if store_energy_frames else [None]
         mass = [float(np.sum(integrated) * dx * dx)]
         _callback(progress_callback, 0.0, frames[0])
 
@@ -424,16 +431,11 @@ def run_2d_crank_nicolson(
                 times.append(float(current_time))
                 frame = reconstruct_field(mask_b, integrated)
                 frames.append(frame)
-                if store_energy_frames or want_ph_hist:
-                    st, ph = ctx.get_state(want_phonons=want_ph_hist and collisions)
-                    if store_energy_frames:
-                        energy_frames.append([reconstruct_field(mask_b, st[i]) for i in range(ne)])
-                    else:
-                        energy_frames.append(None)
-                    if want_ph_hist:
-                        snapshot_phonons(ph if ph is not None else phonon_state)
-                else:
-                    energy_frames.append(None)
+                # NE NaN-padded frames assembled on the device (one dense download instead of NE host scatters)
+                energy_frames.append(list(ctx.get_frames()) if store_energy_frames else None)
+                if want_ph_hist:
+                    ph = ctx.get_state(want_qp=False, want_phonons=True)[1] if collisions else None
+                    snapshot_phonons(ph if ph is not None else phonon_state)
                 mass.append(float(np.sum(integrated) * dx * dx))
                 _callback(progress_callback, float(current_time), frame)
         info.update(ctx.diag())

@@ -14,7 +14,17 @@ kw = dict(mask=mask, edges=edges, edge_conditions=bcs, initial_field=w["initial_
           enable_scattering=True, dynes_gamma=w["dynes_gamma"], tau_0=w["tau_0"], T_c=w["T_c"], bath_temperature=w["bath_temperature"],
           external_generation=gen)
 warnings.simplefilter("ignore")
-for rep in range(2):
-    t0 = time.perf_counter(); Q.run_2d_crank_nicolson(**kw); print("run", rep, time.perf_counter() - t0)
+from qpsim_b200 import capi
+acc = {}
+def wrap(name):
+    f = getattr(capi.Context, name)
+    def g(self, *a, **k):
+        t0 = time.perf_counter(); r = f(self, *a, **k); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0; return r
+    setattr(capi.Context, name, g)
+for nm in ("__init__", "close", "upload_geometry", "upload_diffusion", "prepare_diffusion", "upload_collision", "set_state", "get_state", "get_frames", "get_integrated", "advance", "pauli"):
+    wrap(nm)
+for rep in range(4):
+    acc.clear()
+    t0 = time.perf_counter(); Q.run_2d_crank_nicolson(**kw); print("run", rep, round(time.perf_counter() - t0, 4), {k: round(v, 4) for k, v in acc.items()})
 pr = cProfile.Profile(); pr.enable(); Q.run_2d_crank_nicolson(**kw); pr.disable()
 pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
