@@ -75,6 +75,10 @@ typedef struct qpb_diag {
     int64_t kernel_launches; /* CUDA kernels launched by the library since creation                     */
     double  last_advance_ms; /* device time of the most recent qpb_advance step loop (CUDA events on the
                                 library's stream, first launch to last kernel)                          */
+    int32_t sweep_path;      /* kernels of the prepared CN solve: 0 generic (one thread per line), 1 chunked table
+                                kernels, 2 persistent TMA-pipelined kernels (x and y), 3 the same with lines cut
+                                into overlapping segments (lines longer than 512 cells)                  */
+    int32_t reserved;
 } qpb_diag;
 
 /* one record per time step, mirrors _pauli_occupancy_stats (solver.py:967-996) */

@@ -54,6 +54,7 @@ class Diag(C.Structure):
         ("steps_done", C.c_int64), ("sweeps", C.c_int64), ("bin_sweeps", C.c_int64),
         ("pr_iterations", C.c_int64), ("last_delta", C.c_double), ("direct_mode", C.c_int32),
         ("commuting", C.c_int32), ("kernel_launches", C.c_int64), ("last_advance_ms", C.c_double),
+        ("sweep_path", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

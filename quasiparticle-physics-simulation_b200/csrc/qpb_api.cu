@@ -621,6 +621,9 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
     }
     c->diag.direct_mode = s.mode != 0;
     c->diag.commuting = s.commuting;
+    c->diag.sweep_path = !s.fast ? 0
+                         : !(s.pipe.x_ok && s.pipe.y_ok) ? 1
+                         : (s.pipe.x_nseg > 1 || s.pipe.y_nseg > 1) ? 3 : 2;
     return QPB_OK;
 }
 

@@ -285,6 +285,26 @@ int qpbk_diffuse(qpb_ctx *c, DiffSlot &s) {
                       c->maxit);
         return QPB_E_NOCONV;
     }
+    if (const char *dbg = getenv("QPB_DEBUG_RES")) {   // residual history of the first and last bin (diagnostics)
+        if (dbg[0] == '1') {
+            std::vector<unsigned long long> hr((size_t)it * ne), hu((size_t)it * ne);
+            cudaMemcpy(hr.data(), c->d_res, sizeof(unsigned long long) * hr.size(), cudaMemcpyDeviceToHost);
+            cudaMemcpy(hu.data(), c->d_unorm, sizeof(unsigned long long) * hu.size(), cudaMemcpyDeviceToHost);
+            fprintf(stderr, "[qpb] iterations per bin:");
+            for (int b = 0; b < ne; ++b) fprintf(stderr, " %d", h_done[ne + b]);
+            fprintf(stderr, "  (launched %d)\n", it);
+            for (int b : {0, ne - 1}) {
+                fprintf(stderr, "[qpb] bin %d done at %d:", b, h_done[ne + b]);
+                for (int k = 0; k < it; ++k) {
+                    double r, u;
+                    memcpy(&r, &hr[(size_t)k * ne + b], 8);
+                    memcpy(&u, &hu[(size_t)k * ne + b], 8);
+                    fprintf(stderr, " %.1e", u > 0 ? r / u : -1.0);
+                }
+                fprintf(stderr, "\n");
+            }
+        }
+    }
     int kmax = 0;
     long long bs = 0;
     for (int b = 0; b < ne; ++b) {

@@ -754,7 +754,11 @@ int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s) {
     const auto &cf = c->cfg;
     if (getenv("QPB_FORCE_GENERIC") && getenv("QPB_FORCE_GENERIC")[0] == '1') return QPB_OK;
     if (cf.flags & QPB_F_VARIABLE_D) return QPB_OK;
-    if (cf.nx > 1024 || cf.ny > 512) return QPB_OK;  // longer lines: generic kernels (cluster version: next round)
+    // lines beyond the older chunked kernels: only the segmented pipelined kernels (iterated solves) take them
+    const bool long_lines = cf.nx > 1024 || cf.ny > 512;
+    if (long_lines && (s.mode != 0 || cf.nx % 16 != 0 || cf.ne > 2048 ||
+                       (getenv("QPB_NO_PIPE") && getenv("QPB_NO_PIPE")[0] == '1')))
+        return QPB_OK;
     // flag bits for non-zero boundary diagonals (read by the x sweep)
     static_assert(QPB_BCXNZ == 32u && QPB_BCYNZ == 64u, "flag bits");
     std::vector<uint8_t> fl = c->h_flags;
@@ -794,6 +798,7 @@ int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s) {
     // tables chunked for the pipelined kernels cannot be walked by the older kernels: generic sweeps instead
     if (s.mode == 0 && !s.pipe.x_ok && s.fx.d_tabg && (s.fx.S != pick_S(cf.nx, 0))) s.fast = false;
     if (s.mode == 0 && !s.pipe.y_ok && s.fy.d_tabg && (s.fy.S != pick_S(cf.ny, 1) || s.fy.Q > 16)) s.fast = false;
+    if (long_lines && !(s.pipe.x_ok && s.pipe.y_ok)) s.fast = false;
     return QPB_OK;
 }
 

@@ -23,6 +23,8 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace {
@@ -98,7 +100,15 @@ struct PipeArgs {
     const int *jlen;
     const int *cls;              // class of every line
     const double *tabm, *tabg;   // [ne][jmax][nclass][npad]
-    int nclass, npad, Q;         // Q = chunks per line
+    int nclass, npad, Q;         // Q = chunks per line (table layout), npad = Q * S
+    // Lines longer than 32 chunks are cut into segments of `qi` chunks that are solved with `halo` extra chunks on
+    // either side and zero carries at the cut: the carry reach (FastDir::carry_depth, products of g below 1e-18)
+    // bounds the influence of everything farther away, so the interior of a segment is exact to that level.
+    int qs, qi, halo, nseg;      // chunks per tile (halo included), interior chunks, halo chunks, segments per line
+    // 1: the x sweep stores u* - u and the y sweep solves for it directly (both sweeps pipelined).  The y sweep updates
+    // u in place, so its halo rows may already hold a neighbouring tile's new values: with the difference coming
+    // from the x sweep, the old u is only read where this tile alone writes.
+    int delta;
     int tiles_per_bin, ntiles;
     int depth;                   // carry reach in chunks (see FastDir::carry_depth)
     int check_all;               // 1: every bin measures / tests the residual in this iteration
@@ -220,7 +230,9 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
     constexpr int UPC = S / 2;           // 16-byte units per chunk
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int Q = A.Q;                   // chunks per row
-    const int Q16 = A.nx / 16;           // 128-byte units per row
+    const int QS = A.qs, QI = A.qi, H = A.halo, nseg = A.nseg;
+    const int Q16 = QS * S / 16;         // 128-byte units per tile row
+    const int QI16 = QI * S / 16;        // ... of the interior (what is stored)
     const int u_bytes = ((R + 2) * Q16 * 128 + 1023) / 1024 * 1024;
     const int b_bytes = (R * Q16 * 128 + 1023) / 1024 * 1024;
     const int stage_bytes = u_bytes + b_bytes;
@@ -245,12 +257,15 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         while (pt < A.ntiles) {
             const int bin = pt / tpb;
             if (s_j[bin] >= 0) {
-                const int y0 = (pt - bin * tpb) * R;
+                const int rem = pt - bin * tpb;
+                const int rblk = rem / nseg, sg = rem - rblk * nseg;
+                const int y0 = rblk * R;
+                const int c1 = (sg * QI - H) * S / 16;   // first 128-byte unit of the tile (negative: zero filled)
                 const int s = pk % NS;
                 const uint32_t dst = smem_u32(smraw + (size_t)s * stage_bytes);
                 mbar_expect(full0 + 8 * s, (uint32_t)((R + 2) * Q16 * 128 + R * Q16 * 128));
-                tma_load_4d(dst, &maps.u, full0 + 8 * s, 0, 0, y0 - 1, bin);
-                tma_load_4d(dst + u_bytes, &maps.b, full0 + 8 * s, 0, 0, y0, bin);
+                tma_load_4d(dst, &maps.u, full0 + 8 * s, 0, c1, y0 - 1, bin);
+                tma_load_4d(dst + u_bytes, &maps.b, full0 + 8 * s, 0, c1, y0, bin);
                 ++pk;
                 pt += gridDim.x;
                 return;
@@ -263,14 +278,16 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         for (int i = 0; i < NS - 1; ++i) produce();
     }
     const int g = tid / QP, q = tid - g * QP;
-    const bool qok = q < Q;
-    const int qc = qok ? q : Q - 1;
+    const int ql = min(q, QS - 1);             // chunk slot inside the tile
     const int reach = A.depth + 1;           // an inclusive scan over offsets < reach covers `depth` earlier chunks
-    const int r16 = (qc * S) >> 4;             // 128-byte unit of this chunk within its row
-    const int ubase = ((qc * S) & 15) >> 1;    // first 16-byte unit of the chunk inside that 128-byte unit
+    const int r16 = (ql * S) >> 4;             // 128-byte unit of this chunk within its tile row
+    const int ubase = ((ql * S) & 15) >> 1;    // first 16-byte unit of the chunk inside that 128-byte unit
+    const int r16o = r16 - ((H * S) >> 4);     // ... within the stored interior
     const int nx = A.nx;
     int k = 0;
-    int cur_y = -1;
+    int cur_key = -1;
+    bool qok = false, inter = false;
+    int qc = 0;
     double cx[S], cy[S];
     unsigned flw[S / 4];
 #pragma unroll
@@ -283,19 +300,25 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         if (jraw < 0) continue;
         const int jidx = jraw & 0xffff;
         const bool chk = (jraw & 0x10000) != 0;
-        const int y0 = (t - bin * tpb) * R;
+        const int rem = t - bin * tpb;
+        const int rblk = rem / nseg, sg = rem - rblk * nseg;
+        const int y0 = rblk * R;
         const int y = y0 + g;
         // every thread finished reading the stage of tile k-1 before the last named barrier of that iteration
         if (tid == 0) produce();
-        if (y != cur_y) {   // geometry of this thread's chunk (constant while the CTA stays on one row block)
-            cur_y = y;
+        if (y * nseg + sg != cur_key) {   // geometry of this thread's chunk (constant while the CTA stays on one block)
+            cur_key = y * nseg + sg;
+            const int qa = sg * QI - H + q;            // chunk of the row this thread solves
+            qok = q < QS && qa >= 0 && qa < Q;
+            inter = qok && q >= H && q < H + QI;       // ... and stores / measures
+            qc = min(max(qa, 0), Q - 1);
             rowok = y < A.ny && qok;
             const int yc = min(y, A.ny - 1);
             cls = A.cls[yc];
             const size_t o = (size_t)yc * nx + qc * S;
             const unsigned *pf = reinterpret_cast<const unsigned *>(A.flags + o);
 #pragma unroll
-            for (int i = 0; i < S / 4; ++i) flw[i] = rowok ? pf[i] : 0u;
+            for (int i = 0; i < S / 4; ++i) flw[i] = (rowok && inter) ? pf[i] : 0u;
             const double2 *px = reinterpret_cast<const double2 *>(A.cx + o);
             const double2 *py = reinterpret_cast<const double2 *>(A.cy + o);
 #pragma unroll
@@ -390,17 +413,28 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         const int ob = k & 1;
         double *so = reinterpret_cast<double *>(out_base + (size_t)ob * b_bytes);
         cta_bar<NT>(1);   // thread 0 has seen the store of tile k-2 finish reading this buffer
-        if (qok) {
-            const int rb = g * Q16 + r16;
+        if (inter) {
+            const int rb = g * QI16 + r16o;
             double2 *dst = reinterpret_cast<double2 *>(so + (size_t)rb * 16);
             const int swb = rb & 7;
+            if (A.delta) {
+                const int ru = (g + 1) * Q16 + r16;
+                const double2 *pc = reinterpret_cast<const double2 *>(su + (size_t)ru * 16);
+                const int swc = ru & 7;
 #pragma unroll
-            for (int un = 0; un < UPC; ++un) dst[(ubase + un) ^ swb] = make_double2(ch.v[2 * un], ch.v[2 * un + 1]);
+                for (int un = 0; un < UPC; ++un) {
+                    const double2 u2 = pc[(ubase + un) ^ swc];
+                    dst[(ubase + un) ^ swb] = make_double2(ch.v[2 * un] - u2.x, ch.v[2 * un + 1] - u2.y);
+                }
+            } else {
+#pragma unroll
+                for (int un = 0; un < UPC; ++un) dst[(ubase + un) ^ swb] = make_double2(ch.v[2 * un], ch.v[2 * un + 1]);
+            }
         }
         fence_async_smem();
         cta_bar<NT>(2);
         if (tid == 0) {
-            tma_store_4d(&maps.out, smem_u32(so), 0, 0, y0, bin);
+            tma_store_4d(&maps.out, smem_u32(so), 0, sg * QI * S / 16, y0, bin);
             bulk_commit();
             bulk_wait_read<1>();
         }
@@ -421,9 +455,11 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
     constexpr int NT = 4096 / S;
     constexpr int NCH = NT / CW;      // chunk slots per column
     extern __shared__ __align__(1024) unsigned char smraw[];
-    const int Q = A.Q;                // real chunks per column (<= NCH)
-    const int npad = A.npad;
-    const int strip_bytes = (npad * CW * 8 + 127) / 128 * 128;
+    const int Q = A.Q;                // chunks per column
+    const int QS = A.qs, QI = A.qi, H = A.halo, nseg = A.nseg;
+    const int npad = A.npad;          // rows of a factor table
+    const int trows = QS * S;         // rows of a tile (halo included)
+    const int strip_bytes = (trows * CW * 8 + 127) / 128 * 128;
     const int stage_bytes = 2 * strip_bytes;
     unsigned char *out_base = smraw + (size_t)NS * stage_bytes;
     double *carry = reinterpret_cast<double *>(out_base + 2 * (size_t)strip_bytes);   // [2][NCH][CW]
@@ -441,20 +477,26 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
     load_bin_params<1, NT>(A, s_a, s_rho, s_j);
     __syncthreads();
     const int tpb = A.tiles_per_bin;
-    const int nbox = (npad + 255) / 256;          // TMA boxes per strip (box rows <= 256)
-    const int box_rows = npad / nbox;             // host guarantees divisibility
+    const int nbox = (trows + 255) / 256;         // TMA boxes per strip (box rows <= 256)
+    const int box_rows = trows / nbox;            // host guarantees divisibility
+    const int orows = QI * S;                     // stored rows
+    const int nbox_o = (orows + 255) / 256;
+    const int box_rows_o = orows / nbox_o;
     int pt = blockIdx.x, pk = 0;
     auto produce = [&]() {
         while (pt < A.ntiles) {
             const int bin = pt / tpb;
             if (s_j[bin] >= 0) {
-                const int x0 = (pt - bin * tpb) * CW;
+                const int rem = pt - bin * tpb;
+                const int strip = rem / nseg, sg = rem - strip * nseg;
+                const int x0 = strip * CW;
+                const int row0 = (sg * QI - H) * S;     // negative / beyond the grid: zero filled
                 const int s = pk % NS;
                 const uint32_t dst = smem_u32(smraw + (size_t)s * stage_bytes);
-                mbar_expect(full0 + 8 * s, (uint32_t)(2 * npad * CW * 8));
+                mbar_expect(full0 + 8 * s, (uint32_t)(2 * trows * CW * 8));
                 for (int bx = 0; bx < nbox; ++bx) {
-                    tma_load_3d(dst + bx * box_rows * CW * 8, &maps.u, full0 + 8 * s, x0, bx * box_rows, bin);
-                    tma_load_3d(dst + strip_bytes + bx * box_rows * CW * 8, &maps.w, full0 + 8 * s, x0, bx * box_rows, bin);
+                    tma_load_3d(dst + bx * box_rows * CW * 8, &maps.u, full0 + 8 * s, x0, row0 + bx * box_rows, bin);
+                    tma_load_3d(dst + strip_bytes + bx * box_rows * CW * 8, &maps.w, full0 + 8 * s, x0, row0 + bx * box_rows, bin);
                 }
                 ++pk;
                 pt += gridDim.x;
@@ -468,8 +510,8 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         for (int i = 0; i < NS - 1; ++i) produce();
     }
     const int q = tid / CW, c = tid - q * CW;
-    const bool qok = q < Q;
-    const int r0 = (qok ? q : 0) * S;
+    const int r0 = (q < QS ? q : 0) * S;            // first row of this thread's chunk inside the tile
+    bool qok = false, inter = false;
     auto next_tile = [&](int t) {
         while (t < A.ntiles && s_j[t / tpb] < 0) t += gridDim.x;
         return t;
@@ -477,9 +519,15 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
     double mN[S], gN[S];
     auto load_factors = [&](int t) {   // factors of this thread's chunk for tile t
         const int bin = t / tpb;
-        const int x = min((t - bin * tpb) * CW + c, A.nx - 1);
+        const int rem = t - bin * tpb;
+        const int strip = rem / nseg, sg = rem - strip * nseg;
+        const int qa = sg * QI - H + q;               // chunk of the column this thread solves
+        qok = q < QS && qa >= 0 && qa < Q;
+        inter = qok && q >= H && q < H + QI;
+        const int x = min(strip * CW + c, A.nx - 1);
         const int cls = A.cls[x];
-        const size_t base = (((size_t)bin * A.jmax + (s_j[bin] & 0xffff)) * A.nclass + cls) * npad + r0;
+        const size_t base = (((size_t)bin * A.jmax + (s_j[bin] & 0xffff)) * A.nclass + cls) * npad +
+                            (size_t)min(max(qa, 0), Q - 1) * S;
         const double2 *pm = reinterpret_cast<const double2 *>(A.tabm + base);
         const double2 *pg = reinterpret_cast<const double2 *>(A.tabg + base);
 #pragma unroll
@@ -495,7 +543,9 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
     int t = next_tile(blockIdx.x);
     while (t < A.ntiles) {
         const int bin = t / tpb;
-        const int x0 = (t - bin * tpb) * CW;
+        const int rem = t - bin * tpb;
+        const int strip = rem / nseg, sg = rem - strip * nseg;
+        const int x0 = strip * CW;
         const int tn = next_tile(t + gridDim.x);
         if (tid == 0) produce();
         const double rho2 = 2.0 * s_rho[bin];
@@ -514,7 +564,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
 #pragma unroll
         for (int tt = 0; tt < S; ++tt) {
             uold[tt] = su[tt * CW];
-            ch.v[tt] = sw[tt * CW] - uold[tt];
+            ch.v[tt] = A.delta ? sw[tt * CW] : sw[tt * CW] - uold[tt];
         }
         double Am, Bm;
         ch.forward(Am, Bm);
@@ -535,15 +585,16 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         ch.backward_fix(cin);
         const int ob = k & 1;
         double *so = reinterpret_cast<double *>(out_base + (size_t)ob * strip_bytes) + (size_t)r0 * CW + c;
-        if (qok) {
+        if (inter) {
 #pragma unroll
             for (int tt = 0; tt < S; ++tt) so[tt * CW] = fma(rho2, ch.v[tt], uold[tt]);
         }
         fence_async_smem();
         cta_bar<NT>(5);
         if (tid == 0) {
-            const uint32_t src = smem_u32(out_base + (size_t)ob * strip_bytes);
-            for (int bx = 0; bx < nbox; ++bx) tma_store_3d(&maps.out, src + bx * box_rows * CW * 8, x0, bx * box_rows, bin);
+            const uint32_t src = smem_u32(out_base + (size_t)ob * strip_bytes) + H * S * CW * 8;
+            for (int bx = 0; bx < nbox_o; ++bx)
+                tma_store_3d(&maps.out, src + bx * box_rows_o * CW * 8, x0, sg * orows + bx * box_rows_o, bin);
             bulk_commit();
             bulk_wait_read<1>();
         }
@@ -622,13 +673,13 @@ int launch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    kern<<<grid, 4096 / S, x_smem(S, QP, A.nx / 16, NS) + param_smem(A.ne), c->stream>>>(A, maps);
+    kern<<<grid, 4096 / S, x_smem(S, QP, A.qs * S / 16, NS) + param_smem(A.ne), c->stream>>>(A, maps);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
 }
 
-size_t y_smem(int S, int cw, int npad, int ns) {
-    const size_t sb = ((size_t)npad * cw * 8 + 127) / 128 * 128;
+size_t y_smem(int S, int cw, int trows, int ns) {
+    const size_t sb = ((size_t)trows * cw * 8 + 127) / 128 * 128;
     return ns * 2 * sb + 2 * sb + sizeof(double) * 2 * (4096 / S) + 64;
 }
 
@@ -640,7 +691,7 @@ int launch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    kern<<<grid, 4096 / S, y_smem(S, CW, A.npad, NS) + param_smem(A.ne), c->stream>>>(A, maps);
+    kern<<<grid, 4096 / S, y_smem(S, CW, A.qs * S, NS) + param_smem(A.ne), c->stream>>>(A, maps);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
 }
@@ -662,8 +713,25 @@ int qpbp_chunk(int n, int dir) {
     // per x/y sweep; QPB_PIPE_S=8 selects the short chunks for experiments
     const char *e = getenv("QPB_PIPE_S");
     if (e && e[0] == '8' && n <= 256) return 8;
-    if (n <= 512) return 16;
-    return 0;
+    return 16;   // lines longer than 512 cells are solved in overlapping segments of 32 chunks
+}
+
+// segments of a line of Q chunks whose carries reach `depth` chunks: false when the halo would eat the tile
+static bool plan_segments(int Q, int depth, int &qs, int &qi, int &halo, int &nseg) {
+    if (Q <= 32) {
+        qs = qi = Q;
+        halo = 0;
+        nseg = 1;
+        return true;
+    }
+    halo = std::max(1, depth);
+    if (const char *e = getenv("QPB_HALO_EXTRA")) halo += atoi(e);
+    if (getenv("QPB_DEBUG_RES")) fprintf(stderr, "[qpb] segments: Q %d depth %d halo %d\n", Q, depth, halo);
+    qs = 32;
+    qi = qs - 2 * halo;
+    if (qi < 8) return false;
+    nseg = (Q + qi - 1) / qi;
+    return true;
 }
 
 int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
@@ -676,42 +744,50 @@ int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     p.nsm = nsm;
     // x sweep: rows cut into S-cell chunks owned by adjacent lanes (<= 32 chunks), TMA boxes of whole 128-byte units
-    if (cf.nx % 16 == 0 && s.fx.d_tabg && s.fx.S == qpbp_chunk(cf.nx, 0) && s.fx.S > 0) {
-        const int S = s.fx.S, Q = s.fx.Q, QP = std::max(4, next_pow2(Q)), R = (4096 / S) / QP;
+    int qs = 0, qi = 0, halo = 0, nseg = 1;
+    if (cf.nx % 16 == 0 && s.fx.d_tabg && s.fx.S == qpbp_chunk(cf.nx, 0) && s.fx.S > 0 &&
+        (s.fx.Q <= 32 || s.fx.S == 16) && plan_segments(s.fx.Q, s.fx.carry_depth, qs, qi, halo, nseg)) {
+        const int S = s.fx.S, QP = std::max(4, next_pow2(qs)), R = (4096 / S) / QP;
+        const int u16 = qs * S / 16, o16 = qi * S / 16;   // 128-byte units per tile row: loaded, stored
         int ns = 0;
         for (int cand = 3; cand >= 2 && !ns; --cand)
-            if (x_smem(S, QP, cf.nx / 16, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
+            if (x_smem(S, QP, u16, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
         XMaps maps;
-        if (QP <= 32 && ns && make_xmap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, cf.nx / 16, R + 2) &&
-            make_xmap(&maps.b, c->d_B, cf.ne, cf.ny, cf.nx, cf.nx / 16, R) &&
-            make_xmap(&maps.out, c->d_T1, cf.ne, cf.ny, cf.nx, cf.nx / 16, R)) {
+        if (QP <= 32 && ns && make_xmap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, u16, R + 2) &&
+            make_xmap(&maps.b, c->d_B, cf.ne, cf.ny, cf.nx, u16, R) &&
+            make_xmap(&maps.out, c->d_T1, cf.ne, cf.ny, cf.nx, o16, R)) {
             p.x_ok = true;
             p.x_qp = QP;
             p.x_ns = ns;
-            p.x_tpb = (cf.ny + R - 1) / R;
+            p.x_qs = qs; p.x_qi = qi; p.x_halo = halo; p.x_nseg = nseg;
+            p.x_tpb = ((cf.ny + R - 1) / R) * nseg;
             p.xmaps.resize(sizeof(XMaps));
             memcpy(p.xmaps.data(), &maps, sizeof(XMaps));
         }
     }
     // y sweep: strips of CW columns, columns cut into S-row chunks (<= NT/CW chunks)
-    if (cf.nx % 2 == 0 && s.fy.d_tabg && s.fy.S == qpbp_chunk(cf.ny, 1) && s.fy.S > 0) {
-        const int S = s.fy.S, Q = s.fy.Q, npad = s.fy.npad, NT = 4096 / S;
-        int cw = std::min(32, NT / next_pow2(Q));
+    if (cf.nx % 2 == 0 && s.fy.d_tabg && s.fy.S == qpbp_chunk(cf.ny, 1) && s.fy.S > 0 &&
+        plan_segments(s.fy.Q, s.fy.carry_depth, qs, qi, halo, nseg)) {
+        const int S = s.fy.S, NT = 4096 / S;
+        const int trows = qs * S, orows = qi * S;     // rows of a tile: loaded, stored
+        int cw = std::min(32, NT / next_pow2(qs));
         while (cw > 4 && cw / 2 >= cf.nx) cw /= 2;    // narrow grids: do not load columns that do not exist
-        const int nbox = (npad + 255) / 256;
-        if (cw >= 4 && npad % nbox == 0 && (npad / nbox) <= 256 && ((npad / nbox) * cw) % 16 == 0) {
+        const int nbox = (trows + 255) / 256, nbox_o = (orows + 255) / 256;
+        if (cw >= 4 && trows % nbox == 0 && orows % nbox_o == 0 && ((trows / nbox) * cw) % 16 == 0 &&
+            ((orows / nbox_o) * cw) % 16 == 0 && (halo * S * cw * 8) % 128 == 0) {
             int ns = 0;
             for (int cand = 3; cand >= 2 && !ns; --cand)
-                if (y_smem(S, cw, npad, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
+                if (y_smem(S, cw, trows, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
             YMaps maps;
-            const int rows = npad / nbox;
+            const int rows = trows / nbox;
             if (ns && make_ymap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, cw, rows) &&
                 make_ymap(&maps.w, c->d_T1, cf.ne, cf.ny, cf.nx, cw, rows) &&
-                make_ymap(&maps.out, c->d_S, cf.ne, cf.ny, cf.nx, cw, rows)) {
+                make_ymap(&maps.out, c->d_S, cf.ne, cf.ny, cf.nx, cw, orows / nbox_o)) {
                 p.y_ok = true;
                 p.y_cw = cw;
                 p.y_ns = ns;
-                p.y_tpb = (cf.nx + cw - 1) / cw;
+                p.y_qs = qs; p.y_qi = qi; p.y_halo = halo; p.y_nseg = nseg;
+                p.y_tpb = ((cf.nx + cw - 1) / cw) * nseg;
                 p.ymaps.resize(sizeof(YMaps));
                 memcpy(p.ymaps.data(), &maps, sizeof(YMaps));
             }
@@ -756,10 +832,15 @@ int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check) {
     A.tabm = fd.d_tab; A.tabg = fd.d_tabg; A.nclass = fd.nclass; A.npad = fd.npad; A.Q = fd.Q;
     A.res = c->d_res; A.unorm = c->d_unorm; A.done = c->d_done; A.iters_out = c->d_done + cf.ne;
     A.depth = std::max(1, fd.carry_depth);
+    A.delta = (p.x_ok && p.y_ok) ? 1 : 0;
     A.check_all = check ? 1 : 0;
     A.known = s.d_known;
     ScopedTimer tm(c, dir == 0 ? 0 : 1);
     c->diag.kernel_launches++;
+    A.qs = dir == 0 ? p.x_qs : p.y_qs;
+    A.qi = dir == 0 ? p.x_qi : p.y_qi;
+    A.halo = dir == 0 ? p.x_halo : p.y_halo;
+    A.nseg = dir == 0 ? p.x_nseg : p.y_nseg;
     if (dir == 0) {
         A.tiles_per_bin = p.x_tpb;
         A.ntiles = p.x_tpb * cf.ne;

@@ -179,6 +179,27 @@ def test_pipelined_sweeps_match_oracle(shape, bc):
     assert info["direct_mode"] == 0 and info["pr_iterations"] > 0
 
 
+@pytest.mark.parametrize("shape", [(40, 1040), (1050, 48), (530, 544)])
+@pytest.mark.parametrize("bc", ["reflective", "mixed"])
+def test_segmented_sweeps_match_oracle(shape, bc):
+    """Lines longer than 512 cells: the pipelined kernels solve them in overlapping segments (halo = carry reach of
+    the factor tables).  Rows only, columns only, and both directions segmented; masked geometry with slots."""
+    ny, nx = shape
+    case = cases.meander_c2(ny=ny, nx=nx, ne=3, steps=2, bc=bc, pad=3, pitch=max(9, ny // 12),
+                            gap_len=max(6, nx // 5))
+    case["enable_recombination"] = case["enable_scattering"] = False
+    case["generation"] = None
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = helpers.run_dropin(case, enforce_pauli=False)
+    info = dict(Q.solver.last_run_info)
+    want = helpers.run_oracle(case)
+    helpers.assert_close(got["state"], want["state"], "n(E,cell)")
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
+    assert info["sweep_path"] == 3, info
+
+
 def test_pipelined_and_legacy_sweeps_agree(monkeypatch):
     """Same run with QPB_NO_PIPE=1 (chunked table kernels of qpb_sweep_fast.cu): both solve the same linear
     system to the same residual tolerance."""
