@@ -299,7 +299,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     dev_free(c->d_Kr); dev_free(c->d_Ks); dev_free(c->d_KrT); dev_free(c->d_KsT); dev_free(c->d_rho);
     dev_free(c->d_gapid); dev_free(c->d_idxd); dev_free(c->d_idxs); dev_free(c->d_idxdT);
     dev_free(c->d_sign); dev_free(c->d_signT); dev_free(c->d_dmap); dev_free(c->d_smap);
-    dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_scratch); dev_free(c->d_gen);
+    dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_Mg); dev_free(c->d_Xn); dev_free(c->d_Xp); dev_free(c->d_scratch); dev_free(c->d_gen);
     dev_free(c->d_integrated); dev_free(c->d_pauli);
     if (c->d_pauli_part) qpb_dev_free(c->d_pauli_part);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -619,6 +619,7 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
         int rc = qpbk_prepare_fast(c, s);
         if (rc != QPB_OK) return rc;
     }
+    QPB_CUDA(cudaDeviceSynchronize());   // blocking legacy-stream copies of the table setup (see qpb_upload_collision)
     c->diag.direct_mode = s.mode != 0;
     c->diag.commuting = s.commuting;
     c->diag.sweep_path = !s.fast ? 0
@@ -757,7 +758,11 @@ extern "C" int qpb_upload_collision(qpb_ctx *c, const double *K_r0, const double
         }
     }
     c->have_coll = true;
-    return qpbk_collision_setup(c);
+    const int rcs = qpbk_collision_setup(c);
+    // the setup code uses blocking copies on the legacy stream, which the context's non-blocking stream is not
+    // ordered against: everything has landed before the caller can enqueue a step
+    QPB_CUDA(cudaDeviceSynchronize());
+    return rcs;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -775,7 +780,11 @@ extern "C" int qpb_set_state(qpb_ctx *c, const double *n, const double *n_ph) {
         QPB_CUDA(cudaMemcpyAsync(c->d_P, n_ph, sizeof(double) * (size_t)cf.nw * cf.ncell, cudaMemcpyHostToDevice,
                                  c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));
-    if (cf.nw > 0 && n_ph) return qpbk_uniform_setup(c, n_ph);
+    if (cf.nw > 0 && n_ph) {
+        const int rcu = qpbk_uniform_setup(c, n_ph);
+        QPB_CUDA(cudaDeviceSynchronize());
+        return rcu;
+    }
     return QPB_OK;
 }
 
@@ -797,7 +806,9 @@ extern "C" int qpb_set_state_uniform_phonons(qpb_ctx *c, const double *n, const 
         QPB_CUDA(cudaStreamSynchronize(c->stream));
         dev_free(d_bins);
         if (rc != QPB_OK) return rc;
-        return qpbk_uniform_setup(c, n_ph_bins, true);
+        rc = qpbk_uniform_setup(c, n_ph_bins, true);
+        QPB_CUDA(cudaDeviceSynchronize());
+        return rc;
     }
     QPB_CUDA(cudaStreamSynchronize(c->stream));
     return QPB_OK;

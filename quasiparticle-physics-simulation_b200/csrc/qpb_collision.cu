@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(128) k_collide_generic(GenericArgs A) {
 
 #include "qpb_collide_struct.cuh"
 #include "qpb_collide_uniform.cuh"
+#include "qpb_collide_gemm.cuh"
 
 struct StructTables {
     double2 *K2 = nullptr;
@@ -343,6 +344,65 @@ int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin) {
     QPB_CUDA(cudaMemcpy(c->d_K4, K4.data(), sizeof(double) * K4.size(), cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMemcpy(c->d_K4 + K4.size(), rhop.data(), sizeof(double) * nep, cudaMemcpyHostToDevice));
     c->uniform_ph = true;
+    // ---- tensor-core form (qpb_collide_gemm.cuh) where the bin count makes the products a real GEMM ----
+    if (c->d_Mg) qpb_dev_free(c->d_Mg);
+    if (c->d_Xn) qpb_dev_free(c->d_Xn);
+    if (c->d_Xp) qpb_dev_free(c->d_Xp);
+    c->d_Mg = c->d_Xn = c->d_Xp = nullptr;
+    c->gemm_ready = false;
+    int min_ne = 64;
+    if (const char *e = getenv("QPB_GEMM_MIN_NE")) min_ne = atoi(e);
+    if (ne >= min_ne && !(getenv("QPB_NO_GEMM") && getenv("QPB_NO_GEMM")[0] == '1')) {
+        const int ng = ((ne + GM_BM - 1) / GM_BM) * GM_BM;
+        const size_t npadc = ((size_t)cf.ncell + GM_BN - 1) / GM_BN * GM_BN;
+        std::vector<double> M((size_t)4 * ng * ng + ng, 0.0);
+        for (int i = 0; i < ne; ++i) {
+            M[(size_t)4 * ng * ng + i] = rho[i];
+            for (int j = 0; j < ne; ++j) {
+                const double *o = &K4[((size_t)i * nep + j) * 4];   // (dE Ke_ij, dE Ke_ji, 2dE Kb_ij, 2dE Ka_ij)
+                M[((size_t)0 * ng + i) * ng + j] = o[0];
+                M[((size_t)1 * ng + i) * ng + j] = o[2];
+                M[((size_t)2 * ng + i) * ng + j] = o[3];
+                M[((size_t)3 * ng + i) * ng + j] = o[1];
+            }
+        }
+        QPB_CUDA(qpb_dev_malloc((void **)&c->d_Mg, sizeof(double) * M.size()));
+        QPB_CUDA(qpb_dev_malloc((void **)&c->d_Xn, sizeof(double) * ng * npadc));
+        QPB_CUDA(qpb_dev_malloc((void **)&c->d_Xp, sizeof(double) * ng * npadc));
+        QPB_CUDA(cudaMemcpy(c->d_Mg, M.data(), sizeof(double) * M.size(), cudaMemcpyHostToDevice));
+        // the padding stays zero for good (ordered on the context's stream: the legacy stream does not order it)
+        QPB_CUDA(cudaMemsetAsync(c->d_Xn, 0, sizeof(double) * ng * npadc, c->stream));
+        QPB_CUDA(cudaMemsetAsync(c->d_Xp, 0, sizeof(double) * ng * npadc, c->stream));
+        QPB_CUDA(cudaStreamSynchronize(c->stream));
+        c->gemm_nep = ng;
+        c->gemm_npadc = (long long)npadc;
+        c->gemm_ready = true;
+    }
+    return QPB_OK;
+}
+
+static int launch_gemm(qpb_ctx *c, double dt) {
+    const auto &cf = c->cfg;
+    GemmArgs G;
+    G.ne = cf.ne; G.nep = c->gemm_nep; G.ncell = cf.ncell; G.npadc = (int)c->gemm_npadc; G.ncd = c->ncd;
+    G.S = c->d_S; G.c2d = c->d_cell2dense; G.M = c->d_Mg; G.Xn = c->d_Xn; G.Xp = c->d_Xp;
+    G.rho = c->d_Mg + (size_t)4 * G.nep * G.nep;
+    G.dt = dt;
+    static bool configured = false;
+    const size_t smem = (size_t)GM_ST * GM_STAGE_BYTES;
+    if (!configured) {
+        QPB_CUDA(cudaFuncSetAttribute(k_collide_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long long total = (long long)cf.ne * cf.ncell;
+    const int pack_blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    k_gemm_pack<<<pack_blocks, 256, 0, c->stream>>>(G);
+    QPB_CHECK_LAUNCH();
+    // cell blocks along x so that CTAs running together share the row block's matrix tiles in L2
+    dim3 grid((unsigned)(c->gemm_npadc / GM_BN), (unsigned)(G.nep / GM_BM));
+    k_collide_gemm<<<grid, 256, smem, c->stream>>>(G);
+    QPB_CHECK_LAUNCH();
+    c->diag.kernel_launches++;
     return QPB_OK;
 }
 
@@ -375,6 +435,7 @@ int qpbk_collide(qpb_ctx *c, double dt) {
         U.K4 = reinterpret_cast<const double4 *>(c->d_K4);
         U.rho = c->d_K4 + (size_t)4 * U.nep * U.nep;
         U.dt = dt;
+        if (c->gemm_ready) return launch_gemm(c, dt);
         int rc = launch_uniform<32, 512>(c, U);
         if (rc <= 0) return rc;
         rc = launch_uniform<8, 256>(c, U);

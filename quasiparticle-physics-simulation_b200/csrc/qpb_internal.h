@@ -129,6 +129,11 @@ struct qpb_ctx {
     double *d_P = nullptr;            // phonon state [nw][ncell]
     bool uniform_ph = false;          // frozen phonons, identical in every cell: packed effective kernels in d_K4
     double *d_K4 = nullptr;           // [nep][nep][4] + rho[nep]
+    // tensor-core form of the same products (qpb_collide_gemm.cuh): 4 padded row-major matrices + rho, packed operands
+    bool gemm_ready = false;
+    double *d_Mg = nullptr, *d_Xn = nullptr, *d_Xp = nullptr;
+    int gemm_nep = 0;
+    long long gemm_npadc = 0;
     double *d_scratch = nullptr;      // collision scratch
     size_t scratch_bytes = 0;
     // generation array

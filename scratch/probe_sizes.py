@@ -56,7 +56,7 @@ def collision_probe(ne, ncell, fmax, frozen=False):
         ctx.synchronize()
         ms, nl = ctx.timer(2)
     ms /= nl
-    fl = (12.0 if frozen else 21.0) * ne * ne * ncell
+    fl = (8.0 if frozen else 21.0) * ne * ne * ncell   # 8 NE^2 on the GEMM form
     print(f"collision ne={ne} nw={om.size} cells={ncell} frozen={frozen}: {ms:.3f} ms/call  {fl/(ms*1e-3)/1e12:.2f} TFLOP/s (algorithmic)", flush=True)
 
 if __name__ == "__main__":
@@ -66,6 +66,12 @@ if __name__ == "__main__":
         collision_probe(256, 32768, 3.0)
         collision_probe(512, 16384, 10.0)
         collision_probe(512, 16384, 10.0, frozen=True)
+        collision_probe(512, 131072, 10.0, frozen=True)
+        collision_probe(128, 45952, 5.0, frozen=True)
+        os.environ["QPB_NO_GEMM"] = "1"
+        collision_probe(512, 16384, 10.0, frozen=True)
+        collision_probe(128, 45952, 5.0, frozen=True)
+        del os.environ["QPB_NO_GEMM"]
         collision_probe(64, 65536, 3.0)
     if "diff" in what:
         diffusion_probe(256, 256, 128, dt=0.5, fmax=5.0)

@@ -237,3 +237,38 @@ def test_frozen_uniform_phonons_use_packed_kernels_and_match(flags, monkeypatch)
     O.collide(s_ref, p_ref, Kr, Ks, rho, idd, ids, sg, dE, 0.4, recomb=rec, scat=sc, update_phonons=False)
     helpers.assert_close(outs[0].T, s_ref.T, "packed kernels vs oracle", rtol=1e-11)
     helpers.assert_close(outs[0].T, outs[1].T, "packed vs structured kernel", rtol=1e-11)
+
+
+@pytest.mark.parametrize("flags", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("shape", [(72, 300), (128, 257)])
+def test_frozen_uniform_phonons_tensor_core_gemm(flags, shape, monkeypatch):
+    """From 64 energy bins on, the frozen cell-independent products run as one FP64 tensor-core GEMM
+    (qpb_collide_gemm.cuh: mma.m8n8k4.f64, 64 x 128 CTA tiles).  Bin and cell counts that are not multiples of the
+    tile sizes; compared with the oracle, the fused GEMV kernel and the general structured kernel."""
+    rec, sc = flags
+    ne, n = shape
+    rng = np.random.default_rng(23)
+    E, dE = Q.build_energy_grid(cases.GAP, 1.0, 6.0, ne)
+    om, idd, ids, sg = Q.phonon_frequency_map(E)
+    rho = Q.density_of_states(E, cases.GAP, 0.18)
+    Kr = Q.recombination_kernel_base(E, cases.GAP, 300.0, 1.2)
+    Ks = Q.scattering_kernel_base(E, cases.GAP, 500.0, 1.2)
+    state0 = rho[:, None] * rng.uniform(0, 0.6, (ne, n))
+    ph0 = Q.thermal_phonon_occupation(om, 0.35)[:, None] * np.ones((1, n))
+    outs = {}
+    for tag, env in (("gemm", {}), ("gemv", {"QPB_NO_GEMM": "1"}), ("struct", {"QPB_NO_UNIFORM": "1"})):
+        for k in ("QPB_NO_GEMM", "QPB_NO_UNIFORM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        s, p = state0.copy(), ph0.copy()
+        Q.apply_collision_step_fischer_catelani_uniform(s, p, Kr, Ks, rho, idd, ids, sg, dE, 0.4, enable_recombination=rec,
+                                                        enable_scattering=sc, update_phonons=False)
+        assert np.array_equal(p, ph0)
+        outs[tag] = s
+    s_ref, p_ref = state0.copy(), ph0.copy()
+    O.collide(s_ref, p_ref, Kr, Ks, rho, idd, ids, sg, dE, 0.4, recomb=rec, scat=sc, update_phonons=False)
+    helpers.assert_close(outs["gemm"].T, s_ref.T, "tensor-core GEMM vs oracle", rtol=1e-11)
+    helpers.assert_close(outs["gemm"].T, outs["gemv"].T, "GEMM vs fused GEMV", rtol=1e-11)
+    helpers.assert_close(outs["gemm"].T, outs["struct"].T, "GEMM vs structured kernel", rtol=1e-11)
+    assert not np.array_equal(outs["gemm"], state0)
