@@ -43,6 +43,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -113,6 +117,53 @@ __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const do
     }
 }
 
+// quasiparticle tile that contains the diagonal: i0 is a multiple of TI and j0 of TJ, so kb = i0 - j0 is 0 or -TJ and
+// every element's side of the diagonal is known at compile time (the diagonal itself carries Ks = 0)
+template <int CC, bool SC, bool RC, int KB>
+__device__ __forceinline__ void qp_tile_diag(const double2 *__restrict__ kt, const double *__restrict__ cn,
+                                             const double *__restrict__ cp, const double *__restrict__ cnd,
+                                             const double *__restrict__ cns, int i0, int j0, double (&L)[TI],
+                                             double (&G)[TI]) {
+    double nj[TJ], pj[TJ];
+#pragma unroll
+    for (int s = 0; s < TJ; ++s) {
+        nj[s] = cn[(j0 + s) * CC];
+        pj[s] = cp[(j0 + s) * CC];
+    }
+    double nsw[TI + TJ - 1], nda[TI];   // nda[m] = n_ph at |i-j| = m, m < TI covers both values of KB
+    if (RC) {
+#pragma unroll
+        for (int t = 0; t < TI + TJ - 1; ++t) nsw[t] = cns[(i0 + j0 + t) * CC];
+    }
+    if (SC) {
+#pragma unroll
+        for (int m = 1; m < TI; ++m) nda[m] = cnd[m * CC];
+    }
+#pragma unroll
+    for (int r = 0; r < TI; ++r) {
+#pragma unroll
+        for (int s = 0; s < TJ; ++s) {
+            const double2 kv = kt[r * TJ + s];
+            const int k = KB + r - s;   // compile-time after unrolling
+            if (SC && k != 0) {
+                const double e = kv.x * nda[k > 0 ? k : -k];
+                if (k > 0) {
+                    L[r] = fma(e + kv.x, pj[s], L[r]);
+                    G[r] = fma(e, nj[s], G[r]);
+                } else {
+                    L[r] = fma(e, pj[s], L[r]);
+                    G[r] = fma(e + kv.x, nj[s], G[r]);
+                }
+            }
+            if (RC) {
+                const double g = kv.y * nsw[r + s];
+                L[r] = fma(g + kv.y, nj[s], L[r]);
+                G[r] = fma(g, pj[s], G[r]);
+            }
+        }
+    }
+}
+
 // CC = cells per CTA; NT = threads per CTA.
 template <int CC, int NT, bool SC, bool RC, bool PH>
 __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const __grid_constant__ StructArgs A) {
@@ -141,55 +192,39 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
     // column load below is independent of the others (8 in flight per thread).
     static_assert(NT % CC == 0, "threads per CTA must be a multiple of the cells per CTA");
     {
+        // Every element goes global -> shared with an 8-byte cp.async (no register staging): all loads of the thread
+        // are in flight together, one memory round trip for the whole staging instead of one per batch.
         constexpr int RPT = NT / CC;   // columns covered by one pass of the CTA
-        constexpr int UN = 10;
         const int c_me = tid % CC, row_me = tid / CC;
         const int q_me = cell0 + c_me;
         const bool live_me = q_me < ncell;
         const long long d_me = live_me ? A.c2d[q_me] : 0;
-        for (int col0 = row_me; col0 < ncol; col0 += RPT * UN) {
-            double nv[UN], rv[UN];
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int i = col0 + u * RPT - PADF;
-                const bool ok = live_me && i >= 0 && i < A.ne;
-                nv[u] = ok ? A.S[(long long)i * A.ncd + d_me] : 0.0;
-                rv[u] = ok ? A.rho[i] : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < UN; ++u) {
-                const int col = col0 + u * RPT;
-                if (col < ncol) {
-                    sn[col * CC + c_me] = nv[u];
-                    sp[col * CC + c_me] = rv[u] * fmax(1.0 - nv[u] / fmax(rv[u], 1e-30), 0.0);
-                }
-            }
+        for (int col = row_me; col < ncol; col += RPT) {
+            const int i = col - PADF;
+            if (live_me && i >= 0 && i < A.ne) cp_async8(&sn[col * CC + c_me], &A.S[(long long)i * A.ncd + d_me]);
+            else sn[col * CC + c_me] = 0.0;
         }
-        // phonon occupations of the two index families (snd and sns are contiguous: 3*nep rows).  All index lookups of
-        // a batch are issued first, then all occupation loads: two memory round trips per 12 rows
-        constexpr int UP = 12;
-        for (int idx0 = row_me; idx0 < 3 * nep; idx0 += RPT * UP) {
-            int om[UP];
-#pragma unroll
-            for (int u = 0; u < UP; ++u) {
-                const int idx = idx0 + u * RPT;
-                om[u] = -1;
-                if (live_me && idx < 3 * nep) {
-                    if (idx < nep) {
-                        if (idx < A.ne) om[u] = A.dmap[idx];
-                    } else if (idx - nep < 2 * A.ne - 1) {
-                        om[u] = A.smap[idx - nep];
-                    }
+        // phonon occupations of the two index families (snd and sns are contiguous: 3*nep rows)
+        for (int idx = row_me; idx < 3 * nep; idx += RPT) {
+            int om = -1;
+            if (live_me) {
+                if (idx < nep) {
+                    if (idx < A.ne) om = A.dmap[idx];
+                } else if (idx - nep < 2 * A.ne - 1) {
+                    om = A.smap[idx - nep];
                 }
             }
-            double v[UP];
-#pragma unroll
-            for (int u = 0; u < UP; ++u) v[u] = om[u] >= 0 ? A.P[(long long)om[u] * ncell + q_me] : 0.0;
-#pragma unroll
-            for (int u = 0; u < UP; ++u) {
-                const int idx = idx0 + u * RPT;
-                if (idx < 3 * nep) snd[idx * CC + c_me] = v[u];
-            }
+            if (om >= 0) cp_async8(&snd[idx * CC + c_me], &A.P[(long long)om * ncell + q_me]);
+            else snd[idx * CC + c_me] = 0.0;
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        // p = rho * max(1 - n / max(rho, 1e-30), 0) of the thread's own elements (solver.py:719-721, 738)
+        for (int col = row_me; col < ncol; col += RPT) {
+            const int i = col - PADF;
+            const double rv = (i >= 0 && i < A.ne) ? A.rho[i] : 0.0;
+            const double nv = sn[col * CC + c_me];
+            sp[col * CC + c_me] = rv * fmax(1.0 - nv / fmax(rv, 1e-30), 0.0);
         }
     }
     __syncthreads();
@@ -234,6 +269,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 const int kb = i0 - j0;
                 if (kb >= TJ) qp_tile<CC, SC, RC, 0>(kt, cn, cp, cnd, cns, i0, j0, L, G);
                 else if (kb <= -TI) qp_tile<CC, SC, RC, 1>(kt, cn, cp, cnd, cns, i0, j0, L, G);
+                else if (kb == 0) qp_tile_diag<CC, SC, RC, 0>(kt, cn, cp, cnd, cns, i0, j0, L, G);
+                else if (kb == -TJ) qp_tile_diag<CC, SC, RC, -TJ>(kt, cn, cp, cnd, cns, i0, j0, L, G);
                 else qp_tile<CC, SC, RC, 2>(kt, cn, cp, cnd, cns, i0, j0, L, G);
             }
             cp_async_wait<0>();

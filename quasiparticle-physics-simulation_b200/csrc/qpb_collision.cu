@@ -30,8 +30,10 @@ namespace {
 // (solver.py:661, 697), which amplify a 1-ulp difference in exp(x) by 1/|x|.  glibc's exp is correctly rounded
 // for all but near-tie inputs; for small |x| the correctly rounded value is fl(1 + expm1(x)), so this form agrees
 // with it bit for bit where the amplification matters, while CUDA's 1-ulp exp() would not.
+// One code path for every argument (lanes are different cells: a branch on |x| would run both sides): beyond the
+// small-|x| range 1 + expm1(x) is exp(x) to an ulp, where nothing amplifies the difference.
 __device__ __forceinline__ double exp_ref(double x) {
-    return fabs(x) < 0.25 ? 1.0 + expm1(x) : exp(x);
+    return 1.0 + expm1(x);
 }
 
 __device__ __forceinline__ double relax_update(double n, double gain, double loss, double dt) {

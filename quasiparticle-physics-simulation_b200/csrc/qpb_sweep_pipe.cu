@@ -832,7 +832,7 @@ int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check) {
     A.tabm = fd.d_tab; A.tabg = fd.d_tabg; A.nclass = fd.nclass; A.npad = fd.npad; A.Q = fd.Q;
     A.res = c->d_res; A.unorm = c->d_unorm; A.done = c->d_done; A.iters_out = c->d_done + cf.ne;
     A.depth = std::max(1, fd.carry_depth);
-    A.delta = (p.x_ok && p.y_ok) ? 1 : 0;
+    A.delta = (p.x_ok && p.y_ok && p.y_nseg > 1) ? 1 : 0;   // only a segmented y sweep reads rows it does not own
     A.check_all = check ? 1 : 0;
     A.known = s.d_known;
     ScopedTimer tm(c, dir == 0 ? 0 : 1);
