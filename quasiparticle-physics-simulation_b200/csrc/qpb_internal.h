@@ -39,11 +39,13 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 struct PipePlan {
     bool x_ok = false, y_ok = false;
     int nsm = 148;
+    int nt = 256;                           // threads per CTA of both kernels
     int x_qp = 0, x_ns = 0, x_tpb = 0;      // lanes per row (power of two), input stages, tiles per bin
     int y_cw = 0, y_ns = 0, y_tpb = 0;      // columns per strip, input stages, tiles per bin
     // segmentation of long lines (PipeArgs::qs ...): chunks per tile, interior chunks, halo chunks, segments per line
     int x_qs = 0, x_qi = 0, x_halo = 0, x_nseg = 1;
     int y_qs = 0, y_qi = 0, y_halo = 0, y_nseg = 1;
+    bool x_inplace = false, y_inplace = false;   // output over an input tile of the stage (PipeArgs::inplace)
     std::vector<unsigned char> xmaps, ymaps;  // host copies of the CUtensorMap triples
 };
 

@@ -109,6 +109,10 @@ struct PipeArgs {
     // u in place, so its halo rows may already hold a neighbouring tile's new values: with the difference coming
     // from the x sweep, the old u is only read where this tile alone writes.
     int delta;
+    // 1: the result of a tile is written over one of its own input tiles and stored from there (no separate output
+    // buffers; the stage is refilled in the middle of the next iteration, after its store has read it);
+    // 0: double-buffered output tiles, the stage is refilled at the top of the next iteration.
+    int inplace;
     int tiles_per_bin, ntiles;
     int depth;                   // carry reach in chunks (see FastDir::carry_depth)
     int check_all;               // 1: every bin measures / tests the residual in this iteration
@@ -222,10 +226,9 @@ __device__ __forceinline__ void load_bin_params(const PipeArgs &A, double *s_a, 
 // Tile = (bin, R = NT/QP consecutive rows), NT = 4096/S threads; smem stage = u tile with one halo row above and
 // below + b tile, both as 128-byte-swizzled boxes (16 doubles | nx/16 | rows | 1 bin).  Thread (g, q) owns the
 // S-cell chunk q of tile row g; the chunks of a row sit in QP adjacent lanes.
-template <int S, int QP, int NS>
-__global__ void __launch_bounds__(4096 / S, 1)
+template <int S, int QP, int NS, int NT>
+__global__ void __launch_bounds__(NT, NT <= 128 ? 2 : 1)
 k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
-    constexpr int NT = 4096 / S;
     constexpr int R = NT / QP;
     constexpr int UPC = S / 2;           // 16-byte units per chunk
     extern __shared__ __align__(1024) unsigned char smraw[];
@@ -236,8 +239,9 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
     const int u_bytes = ((R + 2) * Q16 * 128 + 1023) / 1024 * 1024;
     const int b_bytes = (R * Q16 * 128 + 1023) / 1024 * 1024;
     const int stage_bytes = u_bytes + b_bytes;
+    // in-place mode: the result of a tile is written over its own b tile (dead once the right-hand side is formed)
     unsigned char *out_base = smraw + (size_t)NS * stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + 2 * (size_t)b_bytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + (A.inplace ? 0 : 2 * (size_t)b_bytes));
     const int tid = threadIdx.x;
     const uint32_t full0 = smem_u32(bars);
     if (tid == 0) {
@@ -304,8 +308,9 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         const int rblk = rem / nseg, sg = rem - rblk * nseg;
         const int y0 = rblk * R;
         const int y = y0 + g;
-        // every thread finished reading the stage of tile k-1 before the last named barrier of that iteration
-        if (tid == 0) produce();
+        // separate output tiles: every thread finished reading the stage of tile k-1 before the last named barrier of
+        // that iteration, so it is refilled right away
+        if (tid == 0 && !A.inplace) produce();
         if (y * nseg + sg != cur_key) {   // geometry of this thread's chunk (constant while the CTA stays on one block)
             cur_key = y * nseg + sg;
             const int qa = sg * QI - H + q;            // chunk of the row this thread solves
@@ -402,6 +407,12 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
                 atomicMax(&A.unorm[(long long)A.iter * A.ne + bin], ((unsigned long long)(unsigned)uhi) << 32);
             }
         }
+        // Refill the stage of tile k-1 with tile k+NS-1: every thread finished with it before the last named barrier of
+        // the previous iteration, and by now (a right-hand side later) its store has read the shared memory.
+        if (tid == 0 && A.inplace) {
+            bulk_wait_read<0>();
+            produce();
+        }
         double Am, Bm;
         ch.forward(Am, Bm);
         const double yin = warp_carry<QP, false>(Am, Bm, q, reach);
@@ -410,9 +421,10 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         const double xin = warp_carry<QP, true>(Am, Bm, q, reach);
         ch.backward_fix(xin);
         // ---- out tile ----
-        const int ob = k & 1;
-        double *so = reinterpret_cast<double *>(out_base + (size_t)ob * b_bytes);
-        cta_bar<NT>(1);   // thread 0 has seen the store of tile k-2 finish reading this buffer
+        double *so = A.inplace ? const_cast<double *>(sb)
+                               : reinterpret_cast<double *>(out_base + (size_t)(k & 1) * b_bytes);
+        // in place: everybody has formed its right-hand side; else: thread 0 has seen the store of tile k-2 finish reading
+        cta_bar<NT>(1);
         if (inter) {
             const int rb = g * QI16 + r16o;
             double2 *dst = reinterpret_cast<double2 *>(so + (size_t)rb * 16);
@@ -436,7 +448,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         if (tid == 0) {
             tma_store_4d(&maps.out, smem_u32(so), 0, sg * QI * S / 16, y0, bin);
             bulk_commit();
-            bulk_wait_read<1>();
+            if (!A.inplace) bulk_wait_read<1>();
         }
         ++k;
     }
@@ -449,10 +461,9 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
 // Tile = (bin, strip of CW columns, all rows), NT = 4096/S threads.  smem stage = u strip + u* strip as
 // [npad rows][CW] (no swizzle: the CW lanes of a row read one contiguous segment).  Thread (q, c): chunk q (S rows) of
 // column c.  
-template <int S, int CW, int NS>
-__global__ void __launch_bounds__(4096 / S, 1)
+template <int S, int CW, int NS, int NT>
+__global__ void __launch_bounds__(NT, NT <= 128 ? 2 : 1)
 k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
-    constexpr int NT = 4096 / S;
     constexpr int NCH = NT / CW;      // chunk slots per column
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int Q = A.Q;                // chunks per column
@@ -461,8 +472,10 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
     const int trows = QS * S;         // rows of a tile (halo included)
     const int strip_bytes = (trows * CW * 8 + 127) / 128 * 128;
     const int stage_bytes = 2 * strip_bytes;
+    // in-place mode: the new u of a tile is written over its own u* strip (every thread has both strips of its chunk in
+    // registers by then)
     unsigned char *out_base = smraw + (size_t)NS * stage_bytes;
-    double *carry = reinterpret_cast<double *>(out_base + 2 * (size_t)strip_bytes);   // [2][NCH][CW]
+    double *carry = reinterpret_cast<double *>(out_base + (A.inplace ? 0 : 2 * (size_t)strip_bytes));   // [2][NCH][CW]
     uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * NCH * CW);
     const int tid = threadIdx.x;
     const uint32_t full0 = smem_u32(bars);
@@ -547,7 +560,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         const int strip = rem / nseg, sg = rem - strip * nseg;
         const int x0 = strip * CW;
         const int tn = next_tile(t + gridDim.x);
-        if (tid == 0) produce();
+        if (tid == 0 && !A.inplace) produce();
         const double rho2 = 2.0 * s_rho[bin];
         ChunkSolve<S> ch;
         load_factors(t);   // issued before the wait on the tile (a register prefetch of the next tile measured slower)
@@ -566,10 +579,15 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
             uold[tt] = su[tt * CW];
             ch.v[tt] = A.delta ? sw[tt * CW] : sw[tt * CW] - uold[tt];
         }
+        // refill the stage of tile k-1 with tile k+NS-1 (its store, issued an iteration ago, has read the shared memory)
+        if (tid == 0 && A.inplace) {
+            bulk_wait_read<0>();
+            produce();
+        }
         double Am, Bm;
         ch.forward(Am, Bm);
         double *cA = carry, *cB = carry + NCH * CW;
-        cta_bar<NT>(1);   // previous tile's carries are consumed; also orders thread 0's wait on the store of tile k-2
+        cta_bar<NT>(1);   // previous tile's carries are consumed
         cA[q * CW + c] = Am;
         cB[q * CW + c] = Bm;
         cta_bar<NT>(2);
@@ -583,8 +601,9 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         cin = 0.0;
         for (int kk = min(NCH - 1, q + A.depth); kk > q; --kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
         ch.backward_fix(cin);
-        const int ob = k & 1;
-        double *so = reinterpret_cast<double *>(out_base + (size_t)ob * strip_bytes) + (size_t)r0 * CW + c;
+        unsigned char *obuf = A.inplace ? smraw + (size_t)s * stage_bytes + strip_bytes
+                                        : out_base + (size_t)(k & 1) * strip_bytes;
+        double *so = reinterpret_cast<double *>(obuf) + (size_t)r0 * CW + c;   // in place: this thread's own u* chunk
         if (inter) {
 #pragma unroll
             for (int tt = 0; tt < S; ++tt) so[tt * CW] = fma(rho2, ch.v[tt], uold[tt]);
@@ -592,11 +611,11 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         fence_async_smem();
         cta_bar<NT>(5);
         if (tid == 0) {
-            const uint32_t src = smem_u32(out_base + (size_t)ob * strip_bytes) + H * S * CW * 8;
+            const uint32_t src = smem_u32(obuf) + H * S * CW * 8;
             for (int bx = 0; bx < nbox_o; ++bx)
                 tma_store_3d(&maps.out, src + bx * box_rows_o * CW * 8, x0, sg * orows + bx * box_rows_o, bin);
             bulk_commit();
-            bulk_wait_read<1>();
+            if (!A.inplace) bulk_wait_read<1>();
         }
         ++k;
         t = tn;
@@ -658,40 +677,40 @@ constexpr int SMEM_CAP = 227 * 1024;
 size_t param_smem(int ne) { return (size_t)ne * 20 + 16; }
 
 // x: S cells per chunk, QP lanes per row, nx16 = nx/16
-size_t x_smem(int S, int QP, int nx16, int ns) {
-    const int R = (4096 / S) / QP;
+size_t x_smem(int nt, int QP, int nx16, int ns, bool inplace) {
+    const int R = nt / QP;
     const size_t ub = ((size_t)(R + 2) * nx16 * 128 + 1023) / 1024 * 1024;
     const size_t bb = ((size_t)R * nx16 * 128 + 1023) / 1024 * 1024;
-    return ns * (ub + bb) + 2 * bb + 64;
+    return ns * (ub + bb) + (inplace ? 0 : 2 * bb) + 64;
 }
 
-template <int S, int QP, int NS>
+template <int S, int QP, int NS, int NT>
 int launch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
-    auto kern = k_sweep_x_pipe<S, QP, NS>;
+    auto kern = k_sweep_x_pipe<S, QP, NS, NT>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    kern<<<grid, 4096 / S, x_smem(S, QP, A.qs * S / 16, NS) + param_smem(A.ne), c->stream>>>(A, maps);
+    kern<<<grid, NT, x_smem(NT, QP, A.qs * S / 16, NS, A.inplace != 0) + param_smem(A.ne), c->stream>>>(A, maps);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
 }
 
-size_t y_smem(int S, int cw, int trows, int ns) {
+size_t y_smem(int nt, int cw, int trows, int ns, bool inplace) {
     const size_t sb = ((size_t)trows * cw * 8 + 127) / 128 * 128;
-    return ns * 2 * sb + 2 * sb + sizeof(double) * 2 * (4096 / S) + 64;
+    return ns * 2 * sb + (inplace ? 0 : 2 * sb) + sizeof(double) * 2 * nt + 64;
 }
 
-template <int S, int CW, int NS>
+template <int S, int CW, int NS, int NT>
 int launch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
-    auto kern = k_sweep_y_pipe<S, CW, NS>;
+    auto kern = k_sweep_y_pipe<S, CW, NS, NT>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    kern<<<grid, 4096 / S, y_smem(S, CW, A.qs * S, NS) + param_smem(A.ne), c->stream>>>(A, maps);
+    kern<<<grid, NT, y_smem(NT, CW, A.qs * S, NS, A.inplace != 0) + param_smem(A.ne), c->stream>>>(A, maps);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
 }
@@ -743,15 +762,27 @@ int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     p.nsm = nsm;
+    // threads per CTA: 4096 / S, one CTA per SM (two CTAs of 128 threads per SM measured no faster: the kernels are
+    // bound by the bytes they move, not by the latency of one tile's recurrences)
+    p.nt = 4096 / std::max(qpbp_chunk(cf.nx, 0), 8);
+    const size_t smem_cap = (size_t)SMEM_CAP;
+    // measured (profiles/): short lines run fastest with separate output tiles and the deepest ring that fits,
+    // segmented long lines with in-place output and two stages
+    int max_ns = 4;
+    if (const char *e = getenv("QPB_PIPE_NS")) max_ns = std::max(2, std::min(4, atoi(e)));
+    int force_inplace = -1;
+    if (const char *e = getenv("QPB_PIPE_INPLACE")) force_inplace = atoi(e) != 0;
     // x sweep: rows cut into S-cell chunks owned by adjacent lanes (<= 32 chunks), TMA boxes of whole 128-byte units
     int qs = 0, qi = 0, halo = 0, nseg = 1;
     if (cf.nx % 16 == 0 && s.fx.d_tabg && s.fx.S == qpbp_chunk(cf.nx, 0) && s.fx.S > 0 &&
         (s.fx.Q <= 32 || s.fx.S == 16) && plan_segments(s.fx.Q, s.fx.carry_depth, qs, qi, halo, nseg)) {
-        const int S = s.fx.S, QP = std::max(4, next_pow2(qs)), R = (4096 / S) / QP;
+        const int S = s.fx.S, QP = std::max(4, next_pow2(qs)), R = p.nt / QP;
         const int u16 = qs * S / 16, o16 = qi * S / 16;   // 128-byte units per tile row: loaded, stored
+        const bool inplace = force_inplace >= 0 ? force_inplace != 0 : nseg > 1;
         int ns = 0;
-        for (int cand = 3; cand >= 2 && !ns; --cand)
-            if (x_smem(S, QP, u16, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
+        for (int cand = (inplace && force_inplace < 0 && !getenv("QPB_PIPE_NS")) ? 2 : max_ns; cand >= 2 && !ns; --cand)
+            if (x_smem(p.nt, QP, u16, cand, inplace) + param_smem(cf.ne) <= smem_cap) ns = cand;
+        p.x_inplace = inplace;
         XMaps maps;
         if (QP <= 32 && ns && make_xmap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, u16, R + 2) &&
             make_xmap(&maps.b, c->d_B, cf.ne, cf.ny, cf.nx, u16, R) &&
@@ -768,16 +799,18 @@ int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
     // y sweep: strips of CW columns, columns cut into S-row chunks (<= NT/CW chunks)
     if (cf.nx % 2 == 0 && s.fy.d_tabg && s.fy.S == qpbp_chunk(cf.ny, 1) && s.fy.S > 0 &&
         plan_segments(s.fy.Q, s.fy.carry_depth, qs, qi, halo, nseg)) {
-        const int S = s.fy.S, NT = 4096 / S;
+        const int S = s.fy.S, NT = p.nt;
         const int trows = qs * S, orows = qi * S;     // rows of a tile: loaded, stored
         int cw = std::min(32, NT / next_pow2(qs));
         while (cw > 4 && cw / 2 >= cf.nx) cw /= 2;    // narrow grids: do not load columns that do not exist
         const int nbox = (trows + 255) / 256, nbox_o = (orows + 255) / 256;
         if (cw >= 4 && trows % nbox == 0 && orows % nbox_o == 0 && ((trows / nbox) * cw) % 16 == 0 &&
             ((orows / nbox_o) * cw) % 16 == 0 && (halo * S * cw * 8) % 128 == 0) {
+            const bool inplace = force_inplace >= 0 ? force_inplace != 0 : nseg > 1;
             int ns = 0;
-            for (int cand = 3; cand >= 2 && !ns; --cand)
-                if (y_smem(S, cw, trows, cand) + param_smem(cf.ne) <= (size_t)SMEM_CAP) ns = cand;
+            for (int cand = (inplace && force_inplace < 0 && !getenv("QPB_PIPE_NS")) ? 2 : max_ns; cand >= 2 && !ns; --cand)
+                if (y_smem(NT, cw, trows, cand, inplace) + param_smem(cf.ne) <= smem_cap) ns = cand;
+            p.y_inplace = inplace;
             YMaps maps;
             const int rows = trows / nbox;
             if (ns && make_ymap(&maps.u, c->d_S, cf.ne, cf.ny, cf.nx, cw, rows) &&
@@ -796,26 +829,32 @@ int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p) {
     return QPB_OK;
 }
 
-template <int S>
+template <int S, int NT>
 static int dispatch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid, int qp, int ns) {
 #define QPB_X(QP)                                                      \
     case QP:                                                           \
-        return ns == 3 ? launch_x<S, QP, 3>(c, A, maps, grid) : launch_x<S, QP, 2>(c, A, maps, grid);
+        return ns >= 4 ? launch_x<S, QP, 4, NT>(c, A, maps, grid)                                    \
+               : ns == 3 ? launch_x<S, QP, 3, NT>(c, A, maps, grid) : launch_x<S, QP, 2, NT>(c, A, maps, grid);
     switch (qp) {
         QPB_X(4) QPB_X(8) QPB_X(16)
-        default: return ns == 3 ? launch_x<S, 32, 3>(c, A, maps, grid) : launch_x<S, 32, 2>(c, A, maps, grid);
+        default:
+            return ns >= 4 ? launch_x<S, 32, 4, NT>(c, A, maps, grid)
+                   : ns == 3 ? launch_x<S, 32, 3, NT>(c, A, maps, grid) : launch_x<S, 32, 2, NT>(c, A, maps, grid);
     }
 #undef QPB_X
 }
 
-template <int S>
+template <int S, int NT>
 static int dispatch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid, int cw, int ns) {
 #define QPB_Y(CW)                                                      \
     case CW:                                                           \
-        return ns == 3 ? launch_y<S, CW, 3>(c, A, maps, grid) : launch_y<S, CW, 2>(c, A, maps, grid);
+        return ns >= 4 ? launch_y<S, CW, 4, NT>(c, A, maps, grid)                                    \
+               : ns == 3 ? launch_y<S, CW, 3, NT>(c, A, maps, grid) : launch_y<S, CW, 2, NT>(c, A, maps, grid);
     switch (cw) {
         QPB_Y(4) QPB_Y(8) QPB_Y(16)
-        default: return ns == 3 ? launch_y<S, 32, 3>(c, A, maps, grid) : launch_y<S, 32, 2>(c, A, maps, grid);
+        default:
+            return ns >= 4 ? launch_y<S, 32, 4, NT>(c, A, maps, grid)
+                   : ns == 3 ? launch_y<S, 32, 3, NT>(c, A, maps, grid) : launch_y<S, 32, 2, NT>(c, A, maps, grid);
     }
 #undef QPB_Y
 }
@@ -841,16 +880,19 @@ int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check) {
     A.qi = dir == 0 ? p.x_qi : p.y_qi;
     A.halo = dir == 0 ? p.x_halo : p.y_halo;
     A.nseg = dir == 0 ? p.x_nseg : p.y_nseg;
+    A.inplace = (dir == 0 ? p.x_inplace : p.y_inplace) ? 1 : 0;
     if (dir == 0) {
         A.tiles_per_bin = p.x_tpb;
         A.ntiles = p.x_tpb * cf.ne;
         const int grid = pick_grid(A.ntiles, p.x_tpb, p.nsm);
         const XMaps &maps = *reinterpret_cast<const XMaps *>(p.xmaps.data());
-        return fd.S == 8 ? dispatch_x<8>(c, A, maps, grid, p.x_qp, p.x_ns) : dispatch_x<16>(c, A, maps, grid, p.x_qp, p.x_ns);
+        if (fd.S == 8) return dispatch_x<8, 512>(c, A, maps, grid, p.x_qp, p.x_ns);
+        return dispatch_x<16, 256>(c, A, maps, grid, p.x_qp, p.x_ns);
     }
     A.tiles_per_bin = p.y_tpb;
     A.ntiles = p.y_tpb * cf.ne;
     const int grid = pick_grid(A.ntiles, p.y_tpb, p.nsm);
     const YMaps &maps = *reinterpret_cast<const YMaps *>(p.ymaps.data());
-    return fd.S == 8 ? dispatch_y<8>(c, A, maps, grid, p.y_cw, p.y_ns) : dispatch_y<16>(c, A, maps, grid, p.y_cw, p.y_ns);
+    if (fd.S == 8) return dispatch_y<8, 512>(c, A, maps, grid, p.y_cw, p.y_ns);
+    return dispatch_y<16, 256>(c, A, maps, grid, p.y_cw, p.y_ns);
 }
