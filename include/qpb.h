@@ -169,6 +169,11 @@ int qpb_advance(qpb_ctx *ctx, int32_t nsteps, double dt, int32_t slot, double t_
 int qpb_collide(qpb_ctx *ctx, double dt);
 int qpb_diffuse(qpb_ctx *ctx, int32_t slot);
 int qpb_pauli(qpb_ctx *ctx, qpb_pauli_rec *out);
+/* the same record taken on the stream without a host synchronisation (slot-th record of a device-side list), and the
+ * download of the first `count` records: the sharded driver checks the occupancy once per batch of steps, like
+ * qpb_advance does on one GPU */
+int qpb_pauli_record(qpb_ctx *ctx, int32_t slot);
+int qpb_pauli_fetch(qpb_ctx *ctx, int32_t count, qpb_pauli_rec *out);
 
 int qpb_get_diag(qpb_ctx *ctx, qpb_diag *out);
 int qpb_synchronize(qpb_ctx *ctx);

@@ -78,7 +78,7 @@ EXPORTED = [
     "qpb_set_state", "qpb_get_state", "qpb_get_integrated", "qpb_advance", "qpb_collide", "qpb_diffuse",
     "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
     "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
-    "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons",
+    "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons", "qpb_pauli_record", "qpb_pauli_fetch",
 ]
 
 
@@ -153,6 +153,8 @@ def load_library():
     lib.qpb_collide.argtypes = [vp, dbl]
     lib.qpb_diffuse.argtypes = [vp, i32]
     lib.qpb_pauli.argtypes = [vp, C.POINTER(PauliRec)]
+    lib.qpb_pauli_record.argtypes = [vp, i32]
+    lib.qpb_pauli_fetch.argtypes = [vp, i32, vp]
     lib.qpb_get_diag.argtypes = [vp, C.POINTER(Diag)]
     lib.qpb_synchronize.argtypes = [vp]
     lib.qpb_enable_timers.argtypes = [vp, C.c_int]
@@ -303,6 +305,14 @@ class Context:
         r = PauliRec()
         self._check(self.lib.qpb_pauli(self.handle, C.byref(r)))
         return r.max_occ, r.max_index, r.forbidden
+
+    def pauli_record(self, slot: int):
+        self._check(self.lib.qpb_pauli_record(self.handle, int(slot)))
+
+    def pauli_fetch(self, count: int):
+        recs = (PauliRec * max(1, int(count)))()
+        self._check(self.lib.qpb_pauli_fetch(self.handle, int(count), C.cast(recs, C.c_void_p)))
+        return [(recs[k].max_occ, recs[k].max_index, recs[k].forbidden) for k in range(int(count))]
 
     def diag(self) -> dict:
         d = Diag()

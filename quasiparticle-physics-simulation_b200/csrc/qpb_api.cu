@@ -891,6 +891,38 @@ extern "C" int qpb_pauli(qpb_ctx *c, qpb_pauli_rec *out) {
     return QPB_OK;
 }
 
+extern "C" int qpb_pauli_record(qpb_ctx *c, int32_t slot) {
+    QPB_ENTER(c);
+    if (!c->d_rho || slot < 0) {
+        qpb_set_error("qpb_pauli_record: density of states not uploaded or negative slot");
+        return QPB_E_INVALID;
+    }
+    if (slot >= c->pauli_cap) {   // grow, keeping the records already taken
+        const int cap = std::max(2 * c->pauli_cap, slot + 1);
+        qpb_pauli_rec *bigger = nullptr;
+        QPB_ALLOC(bigger, (size_t)cap);
+        QPB_CUDA(cudaMemcpyAsync(bigger, c->d_pauli, sizeof(qpb_pauli_rec) * c->pauli_cap, cudaMemcpyDeviceToDevice,
+                                 c->stream));
+        QPB_CUDA(cudaStreamSynchronize(c->stream));
+        dev_free(c->d_pauli);
+        c->d_pauli = bigger;
+        c->pauli_cap = cap;
+    }
+    return qpbk_pauli(c, c->d_pauli + slot);   // stream ordered, no host synchronisation
+}
+
+extern "C" int qpb_pauli_fetch(qpb_ctx *c, int32_t count, qpb_pauli_rec *out) {
+    QPB_ENTER(c);
+    if (!out || count < 0 || count > c->pauli_cap) {
+        qpb_set_error("qpb_pauli_fetch: bad count %d (capacity %d) or null output", count, c->pauli_cap);
+        return QPB_E_INVALID;
+    }
+    if (count > 0)
+        QPB_CUDA(cudaMemcpyAsync(out, c->d_pauli, sizeof(qpb_pauli_rec) * count, cudaMemcpyDeviceToHost, c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
 extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, double t_start,
                            const qpb_generation *gen, qpb_pauli_rec *pauli_out) {
     QPB_ENTER(c);

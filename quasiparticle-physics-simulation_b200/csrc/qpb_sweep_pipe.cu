@@ -226,14 +226,18 @@ __device__ __forceinline__ void load_bin_params(const PipeArgs &A, double *s_a, 
 // Tile = (bin, R = NT/QP consecutive rows), NT = 4096/S threads; smem stage = u tile with one halo row above and
 // below + b tile, both as 128-byte-swizzled boxes (16 doubles | nx/16 | rows | 1 bin).  Thread (g, q) owns the
 // S-cell chunk q of tile row g; the chunks of a row sit in QP adjacent lanes.
-template <int S, int QP, int NS, int NT>
+// SEG = false: whole lines per tile, separate output tiles (segment count, halo and output mode are compile-time
+// constants: the short-line kernels carry none of the segment arithmetic).
+template <int S, int QP, int NS, int NT, bool SEG>
 __global__ void __launch_bounds__(NT, NT <= 128 ? 2 : 1)
-k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
+k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
+    const PipeArgs &A = Ain;
+    const bool inplace = SEG && A.inplace != 0, delta = SEG && A.delta != 0;
     constexpr int R = NT / QP;
     constexpr int UPC = S / 2;           // 16-byte units per chunk
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int Q = A.Q;                   // chunks per row
-    const int QS = A.qs, QI = A.qi, H = A.halo, nseg = A.nseg;
+    const int QS = A.qs, QI = SEG ? A.qi : A.qs, H = SEG ? A.halo : 0, nseg = SEG ? A.nseg : 1;
     const int Q16 = QS * S / 16;         // 128-byte units per tile row
     const int QI16 = QI * S / 16;        // ... of the interior (what is stored)
     const int u_bytes = ((R + 2) * Q16 * 128 + 1023) / 1024 * 1024;
@@ -241,7 +245,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
     const int stage_bytes = u_bytes + b_bytes;
     // in-place mode: the result of a tile is written over its own b tile (dead once the right-hand side is formed)
     unsigned char *out_base = smraw + (size_t)NS * stage_bytes;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + (A.inplace ? 0 : 2 * (size_t)b_bytes));
+    uint64_t *bars = reinterpret_cast<uint64_t *>(out_base + (inplace ? 0 : 2 * (size_t)b_bytes));
     const int tid = threadIdx.x;
     const uint32_t full0 = smem_u32(bars);
     if (tid == 0) {
@@ -310,7 +314,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         const int y = y0 + g;
         // separate output tiles: every thread finished reading the stage of tile k-1 before the last named barrier of
         // that iteration, so it is refilled right away
-        if (tid == 0 && !A.inplace) produce();
+        if (tid == 0 && !inplace) produce();
         if (y * nseg + sg != cur_key) {   // geometry of this thread's chunk (constant while the CTA stays on one block)
             cur_key = y * nseg + sg;
             const int qa = sg * QI - H + q;            // chunk of the row this thread solves
@@ -409,7 +413,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         }
         // Refill the stage of tile k-1 with tile k+NS-1: every thread finished with it before the last named barrier of
         // the previous iteration, and by now (a right-hand side later) its store has read the shared memory.
-        if (tid == 0 && A.inplace) {
+        if (tid == 0 && inplace) {
             bulk_wait_read<0>();
             produce();
         }
@@ -421,7 +425,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         const double xin = warp_carry<QP, true>(Am, Bm, q, reach);
         ch.backward_fix(xin);
         // ---- out tile ----
-        double *so = A.inplace ? const_cast<double *>(sb)
+        double *so = inplace ? const_cast<double *>(sb)
                                : reinterpret_cast<double *>(out_base + (size_t)(k & 1) * b_bytes);
         // in place: everybody has formed its right-hand side; else: thread 0 has seen the store of tile k-2 finish reading
         cta_bar<NT>(1);
@@ -429,7 +433,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
             const int rb = g * QI16 + r16o;
             double2 *dst = reinterpret_cast<double2 *>(so + (size_t)rb * 16);
             const int swb = rb & 7;
-            if (A.delta) {
+            if (delta) {
                 const int ru = (g + 1) * Q16 + r16;
                 const double2 *pc = reinterpret_cast<const double2 *>(su + (size_t)ru * 16);
                 const int swc = ru & 7;
@@ -448,7 +452,7 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
         if (tid == 0) {
             tma_store_4d(&maps.out, smem_u32(so), 0, sg * QI * S / 16, y0, bin);
             bulk_commit();
-            if (!A.inplace) bulk_wait_read<1>();
+            if (!inplace) bulk_wait_read<1>();
         }
         ++k;
     }
@@ -461,13 +465,15 @@ k_sweep_x_pipe(PipeArgs A, const __grid_constant__ XMaps maps) {
 // Tile = (bin, strip of CW columns, all rows), NT = 4096/S threads.  smem stage = u strip + u* strip as
 // [npad rows][CW] (no swizzle: the CW lanes of a row read one contiguous segment).  Thread (q, c): chunk q (S rows) of
 // column c.  
-template <int S, int CW, int NS, int NT>
+template <int S, int CW, int NS, int NT, bool SEG>
 __global__ void __launch_bounds__(NT, NT <= 128 ? 2 : 1)
-k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
+k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
+    const PipeArgs &A = Ain;
+    const bool inplace = SEG && A.inplace != 0, delta = SEG && A.delta != 0;
     constexpr int NCH = NT / CW;      // chunk slots per column
     extern __shared__ __align__(1024) unsigned char smraw[];
     const int Q = A.Q;                // chunks per column
-    const int QS = A.qs, QI = A.qi, H = A.halo, nseg = A.nseg;
+    const int QS = A.qs, QI = SEG ? A.qi : A.qs, H = SEG ? A.halo : 0, nseg = SEG ? A.nseg : 1;
     const int npad = A.npad;          // rows of a factor table
     const int trows = QS * S;         // rows of a tile (halo included)
     const int strip_bytes = (trows * CW * 8 + 127) / 128 * 128;
@@ -475,7 +481,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
     // in-place mode: the new u of a tile is written over its own u* strip (every thread has both strips of its chunk in
     // registers by then)
     unsigned char *out_base = smraw + (size_t)NS * stage_bytes;
-    double *carry = reinterpret_cast<double *>(out_base + (A.inplace ? 0 : 2 * (size_t)strip_bytes));   // [2][NCH][CW]
+    double *carry = reinterpret_cast<double *>(out_base + (inplace ? 0 : 2 * (size_t)strip_bytes));   // [2][NCH][CW]
     uint64_t *bars = reinterpret_cast<uint64_t *>(carry + 2 * NCH * CW);
     const int tid = threadIdx.x;
     const uint32_t full0 = smem_u32(bars);
@@ -560,7 +566,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         const int strip = rem / nseg, sg = rem - strip * nseg;
         const int x0 = strip * CW;
         const int tn = next_tile(t + gridDim.x);
-        if (tid == 0 && !A.inplace) produce();
+        if (tid == 0 && !inplace) produce();
         const double rho2 = 2.0 * s_rho[bin];
         ChunkSolve<S> ch;
         load_factors(t);   // issued before the wait on the tile (a register prefetch of the next tile measured slower)
@@ -577,10 +583,10 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
 #pragma unroll
         for (int tt = 0; tt < S; ++tt) {
             uold[tt] = su[tt * CW];
-            ch.v[tt] = A.delta ? sw[tt * CW] : sw[tt * CW] - uold[tt];
+            ch.v[tt] = delta ? sw[tt * CW] : sw[tt * CW] - uold[tt];
         }
         // refill the stage of tile k-1 with tile k+NS-1 (its store, issued an iteration ago, has read the shared memory)
-        if (tid == 0 && A.inplace) {
+        if (tid == 0 && inplace) {
             bulk_wait_read<0>();
             produce();
         }
@@ -601,7 +607,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
         cin = 0.0;
         for (int kk = min(NCH - 1, q + A.depth); kk > q; --kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
         ch.backward_fix(cin);
-        unsigned char *obuf = A.inplace ? smraw + (size_t)s * stage_bytes + strip_bytes
+        unsigned char *obuf = inplace ? smraw + (size_t)s * stage_bytes + strip_bytes
                                         : out_base + (size_t)(k & 1) * strip_bytes;
         double *so = reinterpret_cast<double *>(obuf) + (size_t)r0 * CW + c;   // in place: this thread's own u* chunk
         if (inter) {
@@ -615,7 +621,7 @@ k_sweep_y_pipe(PipeArgs A, const __grid_constant__ YMaps maps) {
             for (int bx = 0; bx < nbox_o; ++bx)
                 tma_store_3d(&maps.out, src + bx * box_rows_o * CW * 8, x0, sg * orows + bx * box_rows_o, bin);
             bulk_commit();
-            if (!A.inplace) bulk_wait_read<1>();
+            if (!inplace) bulk_wait_read<1>();
         }
         ++k;
         t = tn;
@@ -684,9 +690,9 @@ size_t x_smem(int nt, int QP, int nx16, int ns, bool inplace) {
     return ns * (ub + bb) + (inplace ? 0 : 2 * bb) + 64;
 }
 
-template <int S, int QP, int NS, int NT>
-int launch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
-    auto kern = k_sweep_x_pipe<S, QP, NS, NT>;
+template <int S, int QP, int NS, int NT, bool SEG>
+int launch_x_seg(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
+    auto kern = k_sweep_x_pipe<S, QP, NS, NT, SEG>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
@@ -697,14 +703,25 @@ int launch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
     return QPB_OK;
 }
 
+template <int S, int QP, int NS, int NT>
+int launch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
+    const bool seg = A.nseg > 1 || A.inplace || A.delta;
+    if (S == 16 && seg) return launch_x_seg<S, QP, NS, NT, (S == 16)>(c, A, maps, grid);
+    if (seg) {
+        qpb_set_error("segmented x sweep planned for an unsupported tile shape");
+        return QPB_E_INVALID;
+    }
+    return launch_x_seg<S, QP, NS, NT, false>(c, A, maps, grid);
+}
+
 size_t y_smem(int nt, int cw, int trows, int ns, bool inplace) {
     const size_t sb = ((size_t)trows * cw * 8 + 127) / 128 * 128;
     return ns * 2 * sb + (inplace ? 0 : 2 * sb) + sizeof(double) * 2 * nt + 64;
 }
 
-template <int S, int CW, int NS, int NT>
-int launch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
-    auto kern = k_sweep_y_pipe<S, CW, NS, NT>;
+template <int S, int CW, int NS, int NT, bool SEG>
+int launch_y_seg(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
+    auto kern = k_sweep_y_pipe<S, CW, NS, NT, SEG>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
@@ -713,6 +730,17 @@ int launch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
     kern<<<grid, NT, y_smem(NT, CW, A.qs * S, NS, A.inplace != 0) + param_smem(A.ne), c->stream>>>(A, maps);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
+}
+
+template <int S, int CW, int NS, int NT>
+int launch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
+    const bool seg = A.nseg > 1 || A.inplace || A.delta;
+    if (S == 16 && CW <= 8 && seg) return launch_y_seg<S, CW, NS, NT, (S == 16 && CW <= 8)>(c, A, maps, grid);
+    if (seg) {
+        qpb_set_error("segmented y sweep planned for an unsupported tile shape");
+        return QPB_E_INVALID;
+    }
+    return launch_y_seg<S, CW, NS, NT, false>(c, A, maps, grid);
 }
 
 int pick_grid(int ntiles, int tpb, int nsm) {

@@ -146,7 +146,10 @@ class ShardedStepper:
         self.exchanges += 1
 
     # ---- one time step --------------------------------------------------------------------------------
-    def step(self, dt: float, slot: int = 0, gen_rate: float | None = None, want_pauli: bool = False):
+    def step(self, dt: float, slot: int = 0, gen_rate: float | None = None, want_pauli: bool = False,
+             pauli_slot: int | None = None):
+        """One time step.  want_pauli returns this rank's record (one host synchronisation); pauli_slot instead
+        records it on the device (stages.pauli_record / pauli_fetch), so a batch of steps needs no extra sync."""
         s = self.stages
         if gen_rate is not None:
             s.add_generation(dt, gen_rate)          # solver.py:1459-1464
@@ -163,6 +166,9 @@ class ShardedStepper:
                 self.to_bins()
                 s.diffuse(slot)
                 self.to_cells()
+        if pauli_slot is not None:
+            s.pauli_record(pauli_slot)
+            return None
         return s.pauli() if want_pauli else None
 
     # ---- collectives over small host values -----------------------------------------------------------
@@ -313,6 +319,12 @@ class DeviceStages:
     def pauli(self):
         return self.ctx_c.pauli()
 
+    def pauli_record(self, slot):
+        self.ctx_c.pauli_record(slot)
+
+    def pauli_fetch(self, count):
+        return self.ctx_c.pauli_fetch(count)
+
     def scatter_block(self, block, cell0, count):
         self.ctx_d.scatter_block(block.data_ptr(), cell0, count)
 
@@ -408,8 +420,8 @@ def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT, em
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stages.stream)
-        for _ in range(K):
-            recs.append(stepper.step(dt, 0, rate_at(t), want_pauli=True))
+        for k in range(K):
+            stepper.step(dt, 0, rate_at(t), pauli_slot=k)   # occupancy record per step on the device
             t += dt
         e1.record(stages.stream)
         torch.cuda.synchronize()
@@ -419,6 +431,7 @@ def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT, em
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         clocks = sampler.stop() if rank == 0 else None
         launches = stages.launches() - l0
+        recs = stages.pauli_fetch(K)
         merged = stepper.merge_pauli(recs)
         # ---- end to end: host state in, K steps, host integrated field out (rank-local slices, then a gather) ----
         import time
@@ -428,9 +441,10 @@ def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT, em
         t0 = time.perf_counter()
         stages.ctx_c.set_state(prob.state[:, c0:c1], prob.phonons[:, c0:c1])
         t = 0.0
-        for _ in range(K):
-            stepper.step(dt, 0, rate_at(t), want_pauli=True)
+        for k in range(K):
+            stepper.step(dt, 0, rate_at(t), pauli_slot=k)
             t += dt
+        stages.pauli_fetch(K)
         integ = stages.ctx_c.get_integrated()
         dist.barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
