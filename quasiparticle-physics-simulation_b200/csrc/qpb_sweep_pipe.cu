@@ -774,10 +774,11 @@ static bool plan_segments(int Q, int depth, int &qs, int &qi, int &halo, int &ns
     halo = std::max(1, depth);
     if (const char *e = getenv("QPB_HALO_EXTRA")) halo += atoi(e);
     if (getenv("QPB_DEBUG_RES")) fprintf(stderr, "[qpb] segments: Q %d depth %d halo %d\n", Q, depth, halo);
-    qs = 32;
-    qi = qs - 2 * halo;
-    if (qi < 8) return false;
-    nseg = (Q + qi - 1) / qi;
+    const int qi_max = 32 - 2 * halo;      // a tile has at most 32 chunks (one warp scans a row)
+    if (qi_max < 8) return false;
+    nseg = (Q + qi_max - 1) / qi_max;
+    qi = (Q + nseg - 1) / nseg;             // equal segments: the last tile is not mostly padding
+    qs = qi + 2 * halo;
     return true;
 }
 

@@ -363,12 +363,16 @@ def init_process_group(backend: str | None = None):
 # bench.py --gpus N
 # ------------------------------------------------------------------------------------------------------------
 def weak_tiling(world: int) -> tuple[int, int]:
-    """(tiles along y, tiles along x) of the per-GPU 256 x 256 mask: 1x1, 1x2, 2x2, 2x4."""
-    ty = 1
-    while ty * ty * 2 <= world:
-        ty *= 2
-    ty = min(ty, 2)
-    return ty, world // ty
+    """(tiles along y, tiles along x) of the per-GPU 256 x 256 mask: 1x1, 1x2, 2x2, 4x2.  Rows stay at most 512 cells
+    long (whole-line x tiles); at 8 GPUs the columns are 1024 long and take the segmented y sweep, measured faster
+    (1.68 ms per diffusion step on the full 1024 x 512 rectangle) than 512 x 1024 (2.14 ms)."""
+    table = {1: (1, 1), 2: (1, 2), 4: (2, 2), 8: (4, 2)}
+    if world in table:
+        return table[world]
+    tx = 1
+    while tx * 2 <= 2 and world % (tx * 2) == 0:
+        tx *= 2
+    return world // tx, tx
 
 
 def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT, emit=None):
