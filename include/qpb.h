@@ -215,6 +215,21 @@ int qpb_add_generation(qpb_ctx *ctx, double scale, double rate);
  * ordered (no host sync); every call that returns data to the host synchronises that stream. */
 int qpb_set_stream(qpb_ctx *ctx, void *cuda_stream);
 
+/* ---- layout exchange fused into the collision kernel (multi-GPU) -------------------------------------
+ * The cell-sharded collision context of a rank can store the updated n(E) of its cells straight into the bin-sharded
+ * diffusion states of all ranks (mode 1: collide, then scatter over NVLink peer memory) and read its cells from there
+ * (mode 2: gather, then collide), which replaces the all-to-all between the two layouts and its packing kernels.
+ *   qpb_set_exchange    peer_state[r] = device address (in THIS process) of rank r's diffusion state [rows][peer_ncd];
+ *                       bin_owner/bin_row[NE] route bin i to (rank, row); cell_dense[N] = dense grid index of my cells
+ *   qpb_ipc_export/open make another process's state array addressable (cudaIpc*); handles are 64 bytes
+ * The caller orders the phases across ranks (a barrier between writers and readers of a diffusion state). */
+int qpb_set_exchange(qpb_ctx *ctx, int32_t nranks, void *const *peer_state, int64_t peer_ncd, const int16_t *bin_owner,
+                     const int16_t *bin_row, const int32_t *cell_dense);
+int qpb_collide_exchange(qpb_ctx *ctx, double dt, int32_t mode);
+int qpb_ipc_export(qpb_ctx *ctx, int which, void *handle64);
+int qpb_ipc_open(int device, const void *handle64, void **ptr);
+int qpb_ipc_close(int device, void *ptr);
+
 /* Device buffers of destroyed contexts are parked in a bounded per-process cache (QPB_CACHE_MB, default 4096) so
  * that back-to-back runs of the same shape do not pay cudaMalloc/cudaFree again; this returns them to the driver. */
 int qpb_trim_cache(void);

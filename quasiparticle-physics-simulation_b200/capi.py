@@ -78,7 +78,8 @@ EXPORTED = [
     "qpb_set_state", "qpb_get_state", "qpb_get_integrated", "qpb_advance", "qpb_collide", "qpb_diffuse",
     "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
     "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
-    "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons", "qpb_pauli_record", "qpb_pauli_fetch",
+    "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons", "qpb_pauli_record", "qpb_pauli_fetch", "qpb_set_exchange", "qpb_collide_exchange",
+    "qpb_ipc_export", "qpb_ipc_open", "qpb_ipc_close",
 ]
 
 
@@ -154,6 +155,11 @@ def load_library():
     lib.qpb_diffuse.argtypes = [vp, i32]
     lib.qpb_pauli.argtypes = [vp, C.POINTER(PauliRec)]
     lib.qpb_pauli_record.argtypes = [vp, i32]
+    lib.qpb_set_exchange.argtypes = [vp, i32, C.POINTER(vp), i64, vp, vp, vp]
+    lib.qpb_collide_exchange.argtypes = [vp, dbl, i32]
+    lib.qpb_ipc_export.argtypes = [vp, C.c_int, vp]
+    lib.qpb_ipc_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.qpb_ipc_close.argtypes = [C.c_int, vp]
     lib.qpb_pauli_fetch.argtypes = [vp, i32, vp]
     lib.qpb_get_diag.argtypes = [vp, C.POINTER(Diag)]
     lib.qpb_synchronize.argtypes = [vp]
@@ -298,6 +304,23 @@ class Context:
     def collide(self, dt):
         self._check(self.lib.qpb_collide(self.handle, float(dt)))
 
+    # ---- layout exchange fused into the collision kernel (multi-GPU) ----------------------------------
+    def set_exchange(self, peer_ptrs, peer_ncd, bin_owner, bin_row, cell_dense):
+        n = len(peer_ptrs)
+        arr = (C.c_void_p * n)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        own = np.ascontiguousarray(bin_owner, dtype=np.int16).reshape(self.ne)
+        row = np.ascontiguousarray(bin_row, dtype=np.int16).reshape(self.ne)
+        cd = np.ascontiguousarray(cell_dense, dtype=np.int32).reshape(self.ncell)
+        self._check(self.lib.qpb_set_exchange(self.handle, n, arr, int(peer_ncd), _ptr(own), _ptr(row), _ptr(cd)))
+
+    def collide_exchange(self, dt, mode):
+        self._check(self.lib.qpb_collide_exchange(self.handle, float(dt), int(mode)))
+
+    def ipc_export(self, which=0) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        self._check(self.lib.qpb_ipc_export(self.handle, int(which), C.cast(buf, C.c_void_p)))
+        return bytes(buf)
+
     def diffuse(self, slot=0):
         self._check(self.lib.qpb_diffuse(self.handle, int(slot)))
 
@@ -349,6 +372,23 @@ class Context:
         p, n = C.c_void_p(), C.c_int64()
         self._check(self.lib.qpb_device_ptr(self.handle, int(which), C.byref(p), C.byref(n)))
         return p.value, n.value
+
+
+def ipc_open(device: int, handle: bytes) -> int:
+    lib = load_library()
+    buf = (C.c_ubyte * 64).from_buffer_copy(handle)
+    out = C.c_void_p()
+    rc = lib.qpb_ipc_open(int(device), C.cast(buf, C.c_void_p), C.byref(out))
+    if rc != 0:
+        raise QpbError(rc, lib.qpb_last_error().decode())
+    return int(out.value)
+
+
+def ipc_close(device: int, ptr: int) -> None:
+    lib = load_library()
+    rc = lib.qpb_ipc_close(int(device), C.c_void_p(int(ptr)))
+    if rc != 0:
+        raise QpbError(rc, lib.qpb_last_error().decode())
 
 
 def measure_fp64_tflops(device: int = 0) -> float:

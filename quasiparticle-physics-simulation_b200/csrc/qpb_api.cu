@@ -300,7 +300,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     dev_free(c->d_gapid); dev_free(c->d_idxd); dev_free(c->d_idxs); dev_free(c->d_idxdT);
     dev_free(c->d_sign); dev_free(c->d_signT); dev_free(c->d_dmap); dev_free(c->d_smap);
     dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_Mg); dev_free(c->d_Xn); dev_free(c->d_Xp); dev_free(c->d_scratch); dev_free(c->d_gen);
-    dev_free(c->d_integrated); dev_free(c->d_pauli);
+    dev_free(c->d_integrated); dev_free(c->d_pauli); dev_free(c->d_xdense);
     if (c->d_pauli_part) qpb_dev_free(c->d_pauli_part);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -867,6 +867,89 @@ extern "C" int qpb_collide(qpb_ctx *c, double dt) {
     }
     if (!(dt > 0.0)) return QPB_OK;  // solver.py:1385
     return qpbk_collide(c, dt);
+}
+
+extern "C" int qpb_set_exchange(qpb_ctx *c, int32_t nranks, void *const *peer_state, int64_t peer_ncd,
+                                const int16_t *bin_owner, const int16_t *bin_row, const int32_t *cell_dense) {
+    QPB_ENTER(c);
+    const auto &cf = c->cfg;
+    if (nranks < 1 || nranks > 8 || !peer_state || !bin_owner || !bin_row || !cell_dense || peer_ncd <= 0) {
+        qpb_set_error("qpb_set_exchange: bad arguments (1..8 ranks, non-null tables)");
+        return QPB_E_INVALID;
+    }
+    if (!c->have_coll || !c->structured || !(cf.flags & (QPB_F_SCATTERING | QPB_F_RECOMBINATION)) ||
+        (c->uniform_ph && (cf.flags & QPB_F_FREEZE_PHONONS))) {
+        qpb_set_error("qpb_set_exchange: only the structured collision kernel carries the exchange "
+                      "(upload the collision tables and the state first)");
+        return QPB_E_INVALID;
+    }
+    c->x_route.assign(cf.ne, 0);
+    for (int i = 0; i < cf.ne; ++i) {
+        if (bin_owner[i] < 0 || bin_owner[i] >= nranks || bin_row[i] < 0 || bin_row[i] > 1023) {
+            qpb_set_error("qpb_set_exchange: bin %d routed to rank %d row %d", i, bin_owner[i], bin_row[i]);
+            return QPB_E_INVALID;
+        }
+        c->x_route[i] = (int16_t)((bin_owner[i] << 10) | bin_row[i]);
+    }
+    for (int q = 0; q < cf.ncell; ++q)
+        if (cell_dense[q] < 0 || cell_dense[q] >= peer_ncd) {
+            qpb_set_error("qpb_set_exchange: cell %d has dense index %d outside the peer grid", q, cell_dense[q]);
+            return QPB_E_INVALID;
+        }
+    for (int r = 0; r < 8; ++r) c->x_peer[r] = r < nranks ? (double *)peer_state[r] : nullptr;
+    for (int r = 0; r < nranks; ++r)
+        if (!c->x_peer[r]) {
+            qpb_set_error("qpb_set_exchange: null state pointer for rank %d", r);
+            return QPB_E_INVALID;
+        }
+    dev_free(c->d_xdense);
+    QPB_ALLOC(c->d_xdense, cf.ncell);
+    QPB_CUDA(cudaMemcpy(c->d_xdense, cell_dense, sizeof(int32_t) * cf.ncell, cudaMemcpyHostToDevice));
+    QPB_CUDA(cudaDeviceSynchronize());
+    c->x_nranks = nranks;
+    c->x_ncd = peer_ncd;
+    return QPB_OK;
+}
+
+extern "C" int qpb_collide_exchange(qpb_ctx *c, double dt, int32_t mode) {
+    QPB_ENTER(c);
+    if (!c->have_coll || mode < 1 || mode > 2 || c->x_nranks <= 0) {
+        qpb_set_error("qpb_collide_exchange: needs collision tables, qpb_set_exchange and mode 1 or 2");
+        return QPB_E_INVALID;
+    }
+    if (!(dt > 0.0)) {
+        qpb_set_error("qpb_collide_exchange: dt must be positive (the exchange rides on the collision kernel)");
+        return QPB_E_INVALID;
+    }
+    return qpbk_collide(c, dt, mode);
+}
+
+extern "C" int qpb_ipc_export(qpb_ctx *c, int which, void *handle64) {
+    QPB_ENTER(c);
+    void *ptr = which == 0 ? (void *)c->d_S : (which == 1 ? (void *)c->d_P : nullptr);
+    if (!ptr || !handle64) {
+        qpb_set_error("qpb_ipc_export: nothing to export");
+        return QPB_E_INVALID;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    QPB_CUDA(cudaIpcGetMemHandle((cudaIpcMemHandle_t *)handle64, ptr));
+    return QPB_OK;
+}
+
+extern "C" int qpb_ipc_open(int device, const void *handle64, void **ptr) {
+    if (!handle64 || !ptr) return QPB_E_INVALID;
+    QPB_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof(h));
+    QPB_CUDA(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return QPB_OK;
+}
+
+extern "C" int qpb_ipc_close(int device, void *ptr) {
+    if (!ptr) return QPB_OK;
+    QPB_CUDA(cudaSetDevice(device));
+    QPB_CUDA(cudaIpcCloseMemHandle(ptr));
+    return QPB_OK;
 }
 
 extern "C" int qpb_diffuse(qpb_ctx *c, int32_t slot) {

@@ -22,6 +22,7 @@ constexpr int PADF = 8;   // zero padding in front of the n,p columns in shared 
 constexpr int PADB = 16;  // and behind
 constexpr int NSTAGE = 3; // cp.async ring depth
 constexpr int NEPMAX = 512; // largest padded energy grid of the structured kernel (index tables ride in the parameters)
+constexpr int QPB_MAX_RANKS = 8;
 
 struct StructArgs {
     int ne, nep, nw, ncell, ncd;
@@ -37,7 +38,22 @@ struct StructArgs {
     //   dmap[k]  phonon bin of the diagonal k = |i-j|          mofk[k]  >= 0 when that bin is also fed by an anti-diagonal
     //   smap[m]  phonon bin of the anti-diagonal m = i+j       kofm[m]  diagonal index k sharing that bin, or -1
     int16_t dmap[NEPMAX], mofk[NEPMAX], smap[2 * NEPMAX], kofm[2 * NEPMAX];
+    // Layout exchange fused into the kernel (multi-GPU).  The quasiparticle state of a run lives in two
+    // layouts: cell sharded here, bin sharded (dense grid) in the diffusion contexts of all ranks, whose state arrays are
+    // mapped into this process (peer memory over NVLink).  xmode 1: the updated n(E) of my cells is stored straight
+    // into the owning rank's diffusion state instead of my own; xmode 2: the staging loads read n(E) from there.
+    //   route[i] = owner rank << 10 | row of bin i in the owner's state;  xdense[q] = dense grid index of my cell q
+    int xmode;
+    long long xncd;
+    double *xpeer[QPB_MAX_RANKS];
+    const int32_t *xdense;
+    int16_t route[NEPMAX];
 };
+
+__device__ __forceinline__ double *exchange_slot(const StructArgs &A, int i, long long dense) {
+    const int r = A.route[i];
+    return A.xpeer[r >> 10] + (long long)(r & 1023) * A.xncd + dense;
+}
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -198,10 +214,12 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
         const int c_me = tid % CC, row_me = tid / CC;
         const int q_me = cell0 + c_me;
         const bool live_me = q_me < ncell;
-        const long long d_me = live_me ? A.c2d[q_me] : 0;
+        const long long d_me = live_me ? (A.xmode == 2 ? A.xdense[q_me] : A.c2d[q_me]) : 0;
         for (int col = row_me; col < ncol; col += RPT) {
             const int i = col - PADF;
-            if (live_me && i >= 0 && i < A.ne) cp_async8(&sn[col * CC + c_me], &A.S[(long long)i * A.ncd + d_me]);
+            if (live_me && i >= 0 && i < A.ne)
+                cp_async8(&sn[col * CC + c_me],
+                          A.xmode == 2 ? exchange_slot(A, i, d_me) : &A.S[(long long)i * A.ncd + d_me]);
             else sn[col * CC + c_me] = 0.0;
         }
         // phonon occupations of the two index families (snd and sns are contiguous: 3*nep rows)
@@ -275,12 +293,14 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
             }
             cp_async_wait<0>();
             if (live && work) {
-                const int d = A.c2d[q];
+                const long long d = A.xmode == 1 ? A.xdense[q] : A.c2d[q];
 #pragma unroll
                 for (int r = 0; r < TI; ++r) {
                     const int i = i0 + r;
-                    if (i < A.ne)
-                        A.S[(long long)i * A.ncd + d] = relax_update(cn[i * CC], cp[i * CC] * G[r], L[r], A.dt);
+                    if (i < A.ne) {
+                        double *dst = A.xmode == 1 ? exchange_slot(A, i, d) : &A.S[(long long)i * A.ncd + d];
+                        *dst = relax_update(cn[i * CC], cp[i * CC] * G[r], L[r], A.dt);
+                    }
                 }
             }
         }

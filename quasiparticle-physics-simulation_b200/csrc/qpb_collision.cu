@@ -423,13 +423,17 @@ static int launch_uniform(qpb_ctx *c, const UniformArgs &A) {
     return QPB_OK;
 }
 
-int qpbk_collide(qpb_ctx *c, double dt) {
+int qpbk_collide(qpb_ctx *c, double dt, int xmode) {
     const auto &cf = c->cfg;
     const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
     const bool ph = !(cf.flags & QPB_F_FREEZE_PHONONS);
     ScopedTimer tm(c, 2);
     c->diag.kernel_launches++;
     const size_t smem_cap = 227 * 1024;
+    if (xmode != 0 && !(c->structured && (scat || rec) && c->x_nranks > 0 && !(c->uniform_ph && !ph))) {
+        qpb_set_error("fused exchange needs the structured collision kernel and qpb_set_exchange");
+        return QPB_E_INVALID;
+    }
     if (c->uniform_ph && !ph && (scat || rec)) {
         UniformArgs U;
         U.ne = cf.ne; U.nep = ((cf.ne + TI - 1) / TI) * TI; U.ncell = cf.ncell; U.ncd = c->ncd;
@@ -461,6 +465,13 @@ int qpbk_collide(qpb_ctx *c, double dt) {
             A.kofm[m] = (int16_t)c->h_kof[c->h_smap[m]];
         }
         A.dt = dt;
+        A.xmode = xmode;
+        A.xncd = c->x_ncd;
+        A.xdense = c->d_xdense;
+        for (int r = 0; r < QPB_MAX_RANKS; ++r) A.xpeer[r] = c->x_peer[r];
+        for (int i = 0; i < NEPMAX; ++i) A.route[i] = 0;
+        if (xmode != 0)
+            for (int i = 0; i < cf.ne; ++i) A.route[i] = c->x_route[i];
         // One 32-cell, 512-thread CTA per SM measured faster (1.19 ms at C2) than two 16-cell, 256-thread CTAs
         // (1.47 ms: half-warps read different kernel-matrix tiles); QPB_COLL_CC=16 selects the narrow variant
         const char *ecc = getenv("QPB_COLL_CC");

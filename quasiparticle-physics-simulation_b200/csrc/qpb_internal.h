@@ -138,6 +138,12 @@ struct qpb_ctx {
     long long gemm_npadc = 0;
     double *d_scratch = nullptr;      // collision scratch
     size_t scratch_bytes = 0;
+    // fused layout exchange (qpb_set_exchange): peer diffusion states, routing of bins, dense index of my cells
+    int x_nranks = 0;
+    long long x_ncd = 0;
+    double *x_peer[8] = {nullptr};
+    int32_t *d_xdense = nullptr;      // [ncell]
+    std::vector<int16_t> x_route;     // [ne] owner << 10 | row
     // generation array
     double *d_gen = nullptr;          // [ne][ncell]
     // reductions
@@ -164,7 +170,7 @@ int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p);
 int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check);
 void qpbk_free_slot(DiffSlot &s);
 
-int qpbk_collide(qpb_ctx *c, double dt);
+int qpbk_collide(qpb_ctx *c, double dt, int xmode = 0);
 int qpbk_collision_setup(qpb_ctx *c);
 int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin = false);   // host phonon state [nw][ncell] ([nw] when per_bin) or null
 int qpbk_broadcast_phonons(qpb_ctx *c, const double *d_bins);  // P[o][q] = bins[o]

@@ -105,6 +105,14 @@ class ShardedStepper:
         self.buf_c = torch.empty((plan.ne, nloc), dtype=st.dtype, device=st.device)
         self.buf_d = torch.empty(sum(recv), dtype=st.dtype, device=st.device)
         self.exchanges = 0
+        # fused exchange (DeviceStages.enable_fused_exchange): the collision kernel stores into / loads from the peers'
+        # diffusion states; what is left between the stages is a barrier that orders writers and readers
+        self.fused = bool(getattr(stages, "fused", False)) and self.diffusion and self.collisions
+        self._flag = torch.zeros(1, dtype=torch.float32, device=st.device) if self.fused else None
+
+    def _rank_barrier(self):
+        if self.plan.world > 1:
+            self.dist.all_reduce(self._flag, group=self.group)   # stream ordered, no host synchronisation
 
     # ---- layout exchange ------------------------------------------------------------------------------
     def to_bins(self):
@@ -153,7 +161,15 @@ class ShardedStepper:
         s = self.stages
         if gen_rate is not None:
             s.add_generation(dt, gen_rate)          # solver.py:1459-1464
-        if self.collisions and self.diffusion:      # solver.py:1469-1472
+        if self.collisions and self.diffusion and self.fused:
+            s.collide_exchange(0.5 * dt, 1)         # collide, then store into the owners' diffusion states
+            self._rank_barrier()                    # every rank's cells have arrived
+            s.diffuse(slot)
+            self._rank_barrier()                    # every rank's bins are solved
+            s.collide_exchange(0.5 * dt, 2)         # load my cells from the owners, then collide
+            self._rank_barrier()                    # nobody still reads the diffusion states the next step overwrites
+            self.exchanges += 2
+        elif self.collisions and self.diffusion:    # solver.py:1469-1472
             s.collide(0.5 * dt)
             self.to_bins()
             s.diffuse(slot)
@@ -303,12 +319,61 @@ class DeviceStages:
         self.collisions = coll
 
     def close(self):
+        for ptr in getattr(self, "_ipc_open", []):
+            try:
+                capi.ipc_close(self.device, ptr)
+            except Exception:
+                pass
+        self._ipc_open = []
         for c in (self.ctx_d, self.ctx_c):
             if c is not None:
                 c.close()
 
+    def enable_fused_exchange(self, prob: "ShardedProblem", group=None) -> bool:
+        """Map every rank's diffusion state into this process (cudaIpc over NVLink) and route the collision kernel's
+        stores / staging loads through it (qpb_set_exchange).  Returns False (and leaves the all-to-all path in place)
+        when the run has no diffusion or collisions, or the structured collision kernel is not the one in use."""
+        import torch.distributed as dist
+
+        self.fused = False
+        self._ipc_open = []
+        if self.ctx_d is None or not self.collisions or os.environ.get("QPB_NO_FUSED_EXCHANGE") == "1":
+            return False
+        plan = self.plan
+        own_ptr, _ = self.ctx_d.device_ptr(0)
+        peers = [own_ptr] * plan.world
+        if plan.world > 1:
+            handles = [None] * plan.world
+            dist.all_gather_object(handles, self.ctx_d.ipc_export(0), group=group)
+            for r in range(plan.world):
+                if r != plan.rank:
+                    peers[r] = capi.ipc_open(self.device, handles[r])
+                    self._ipc_open.append(peers[r])
+        owner = np.empty(plan.ne, dtype=np.int16)
+        row = np.empty(plan.ne, dtype=np.int16)
+        for g in range(plan.world):
+            b = plan.bins(g)
+            owner[b] = g
+            row[b] = np.arange(b.size)
+        c0, c1 = plan.cells()
+        cell_dense = np.flatnonzero(np.asarray(prob.mask, dtype=bool).ravel())[c0:c1]
+        ok = True
+        try:
+            self.ctx_c.set_exchange(peers, prob.mask.size, owner, row, cell_dense)
+        except capi.QpbError:
+            ok = False
+        if plan.world > 1:   # all ranks or none
+            flags = [None] * plan.world
+            dist.all_gather_object(flags, ok, group=group)
+            ok = all(flags)
+        self.fused = ok
+        return ok
+
     def collide(self, dt):
         self.ctx_c.collide(dt)
+
+    def collide_exchange(self, dt, mode):
+        self.ctx_c.collide_exchange(dt, mode)
 
     def add_generation(self, scale, rate):
         self.ctx_c.add_generation(scale, rate)
@@ -404,6 +469,7 @@ def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT, em
     K, W = args.steps, args.warmup
     dt = w["dt"]
     stages = DeviceStages(plan, prob, local, dt)
+    fused = stages.enable_fused_exchange(prob)
     with torch.cuda.stream(stages.stream):
         stepper = ShardedStepper(plan, stages, diffusion=True, collisions=True)
 
@@ -462,7 +528,10 @@ def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT, em
             "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "cells": n, "energy_bins": ne, "phonon_bins": nw, "dt_ns": dt,
-                       "parallelism": f"bins/{world} (diffusion) <-> cells/{world} (collisions), NCCL all-to-all x2 per step",
+                       "parallelism": (f"bins/{world} (diffusion) <-> cells/{world} (collisions), "
+                                       + ("exchange fused into the collision kernel over NVLink peer memory, "
+                                          "3 stream-ordered barriers per step" if fused
+                                          else "NCCL all-to-all x2 per step")),
                        "exchange_bytes_per_gpu": plan.exchange_bytes(),
                        "l2": "per-GPU state + phonons + work arrays exceed the 126 MB L2"},
             "clocks": clocks, "gpu_launches": int(launches),

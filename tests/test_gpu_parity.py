@@ -115,9 +115,11 @@ def test_mass_conserved_and_medium_meander():
     assert got["frames_nan_outside"]
 
 
-def test_sharded_driver_on_one_gpu_matches_single_context():
+@pytest.mark.parametrize("fused", [False, True], ids=["all_to_all", "fused_exchange"])
+def test_sharded_driver_on_one_gpu_matches_single_context(fused):
     """multigpu.DeviceStages + ShardedStepper with world = 1 (two contexts, block scatter/gather, row permutation,
-    shared stream) against qpb_advance on one context and against the oracle."""
+    shared stream) against qpb_advance on one context and against the oracle.  fused: the collision kernel stores
+    into / loads from the diffusion context's state itself (qpb_set_exchange; here the only "peer" is this rank)."""
     from qpsim_b200 import capi
     from qpsim_b200.multigpu import DeviceStages, ShardedProblem, ShardedStepper, ShardPlan
     import torch
@@ -141,9 +143,12 @@ def test_sharded_driver_on_one_gpu_matches_single_context():
                           nw=om.size, state=state, phonons=phon)
     plan = ShardPlan(E.size, n, 1, 0, interleave=True)
     stages = DeviceStages(plan, prob, 0, case["dt"])
+    if fused:
+        assert stages.enable_fused_exchange(prob)
     g = case["generation"]
     with torch.cuda.stream(stages.stream):
         st = ShardedStepper(plan, stages, diffusion=True, collisions=True)
+        assert st.fused == fused
         t, recs = 0.0, []
         for _ in range(3):
             rate = g["pulse_rate"] if g["pulse_start"] <= t < g["pulse_start"] + g["pulse_duration"] else None
