@@ -82,8 +82,26 @@ def c2_workload(tile_y: int = 1, tile_x: int = 1, ny: int = 256, nx: int = 256, 
     )
 
 
-def build_tables(w, Q=None):
-    """Host-side setup shared by the device-resident run and the CPU baseline."""
+def c3_workload():
+    """BASELINE configs[2]: 2048 x 2048 full mask, reflective walls, 256 bins on [gap, 3 gap],
+    dt = 0.2 ns, seeded lognormal field x thermal weights, dynamic phonons.  Strong scaling: the grid is fixed and cut
+    across the ranks (bench.py --workload c3; not the default line)."""
+    import cases
+
+    ny = nx = int(os.environ.get("QPB_C3_SIDE", "2048"))
+    mask = np.ones((ny, nx), dtype=bool)
+    field = cases.lognormal_field(mask, seed=20260103, scale=1e-4)
+    return dict(
+        name=f"C3 full grid {ny}x{nx} x 256 bins", mask=mask, bc="reflective", initial_field=field,
+        diffusion_coefficient=cases.D0, dt=0.2, dx=1.0, energy_gap=cases.GAP, energy_min_factor=1.0,
+        energy_max_factor=3.0, num_energy_bins=int(os.environ.get("QPB_C3_BINS", "256")), dynes_gamma=cases.GAMMA,
+        tau_0=cases.TAU, T_c=cases.TC, bath_temperature=cases.TBATH, pulse_rate=None, weights="thermal",
+    )
+
+
+def build_tables(w, Q=None, cells=None):
+    """Host-side setup shared by the device-resident run and the CPU baseline.  cells = (c0, c1): only that slice of
+    the state is built and the phonon state stays in its per-bin form (large grids)."""
     if Q is None:
         import qpsim_b200 as Q
     mask = w["mask"]
@@ -94,12 +112,20 @@ def build_tables(w, Q=None):
     Ks = Q.scattering_kernel_base(E, w["energy_gap"], w["tau_0"], w["T_c"])
     om, idd, ids, sg = Q.phonon_frequency_map(E)
     nph = Q.thermal_phonon_occupation(om, w["bath_temperature"])
-    wts = rho / (np.sum(rho) * dE)
-    state = wts[:, None] * w["initial_field"][mask][None, :]
-    phon = nph[:, None] * np.ones((1, n))
+    if w.get("weights") == "thermal":
+        # normalised thermal quasiparticle weights rho(E) f(E, 0.3 K) (solver.py:429-460), k_B in ueV/K (solver.py:347)
+        f = 1.0 / (np.exp(np.minimum(E / (86.17333262145 * 0.3), 500.0)) + 1.0)
+        wts = rho * f / (np.sum(rho * f) * dE)
+    else:
+        wts = rho / (np.sum(rho) * dE)
+    spatial = w["initial_field"][mask]
+    if cells is not None:
+        spatial = spatial[cells[0]:cells[1]]
+    state = wts[:, None] * spatial[None, :]
+    phon = None if cells is not None else nph[:, None] * np.ones((1, n))
     D = w["diffusion_coefficient"] * np.sqrt(np.maximum(0.0, 1.0 - (w["energy_gap"] / E) ** 2))
     return dict(E=E, dE=dE, rho=rho, Kr=Kr, Ks=Ks, omega=om, idx_diff=idd, idx_sum=ids, sign=sg, state=state,
-                phonons=phon, D=D, n=n)
+                phonons=phon, phonon_bins=nph, D=D, n=n)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -402,10 +428,18 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"],
+                    help="c2 (default): BASELINE configs[1], weak scaling over --gpus; c3: configs[2], 2048^2 x 256 "
+                         "bins cut across the GPUs (strong scaling, sharded driver at every N)")
     args = ap.parse_args()
     protect_stdout()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.workload == "c3":
+        from qpsim_b200 import multigpu
+
+        multigpu.bench_main(args, c3_workload, build_tables, ClockSampler, METRIC, UNIT, emit)
         return
     if args.gpus > 1 or int(os.environ.get("WORLD_SIZE", "1")) > 1:
         from qpsim_b200 import multigpu
