@@ -29,11 +29,12 @@ from .solver import (  # noqa: F401
     run_2d_crank_nicolson,
 )
 from . import capi  # noqa: F401
+from .ensemble import parameter_grid, run_ensemble  # noqa: F401
 
 __all__ = [
     "run_2d_crank_nicolson",
     "apply_collision_step_fischer_catelani_uniform",
     "apply_collision_step_fischer_catelani_nonuniform",
     "BoundaryCondition", "BoundaryFace", "EdgeSegment", "ExternalGenerationSpec", "BoundaryAssignmentError",
-    "extract_edge_segments", "compile_boundaries", "build_energy_grid", "capi",
+    "extract_edge_segments", "compile_boundaries", "build_energy_grid", "capi", "run_ensemble", "parameter_grid",
 ]

@@ -2,6 +2,7 @@
 #include "qpb_internal.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -92,9 +93,18 @@ cudaError_t qpb_dev_malloc(void **p, size_t bytes) {
             g_cache.erase(g_cache.begin() + i);
             g_live[*p] = bytes;
             // a block from the driver arrives zeroed; keep that property for recycled ones
+            if (getenv("QPB_DEBUG_ALLOC")) {
+                auto t0 = std::chrono::steady_clock::now();
+                cudaMemsetAsync(*p, 0, bytes, 0);
+                cudaError_t e2 = cudaStreamSynchronize(0);
+                const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                if (ms > 1.0) fprintf(stderr, "[qpb] recycle %zu bytes: memset+sync %.2f ms\n", bytes, ms);
+                return e2;
+            }
             cudaMemsetAsync(*p, 0, bytes, 0);
             return cudaStreamSynchronize(0);
         }
+    if (getenv("QPB_DEBUG_ALLOC")) fprintf(stderr, "[qpb] cache miss %zu bytes (cached %zu in %zu blocks)\n", bytes, g_cache_bytes, g_cache.size());
     cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess && !g_cache.empty()) {
         cudaGetLastError();
@@ -194,6 +204,12 @@ extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
         return QPB_E_INVALID;
     }
     *out = nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (getenv("QPB_DEBUG_ALLOC"))
+            fprintf(stderr, "[qpb] create: %s at %.2f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count());
+    };
     if (cfg->abi_version != QPB_ABI_VERSION) {
         qpb_set_error("qpb_create: ABI version mismatch (caller %d, library %d)", cfg->abi_version, QPB_ABI_VERSION);
         return QPB_E_INVALID;
@@ -218,14 +234,18 @@ extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
         qpb_set_error("qpb_create: device %d out of range (0..%d)", cfg->device, ndev - 1);
         return QPB_E_NODEVICE;
     }
-    cudaDeviceProp prop;
-    QPB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
-    if (prop.major != 10) {
-        qpb_set_error("qpb_create: device %d is sm_%d%d; libqpb is built for sm_100a only", cfg->device, prop.major,
-                      prop.minor);
+    // two attribute queries instead of cudaGetDeviceProperties (measured 4-40 ms per call on this box)
+    int cc_major = 0, cc_minor = 0;
+    QPB_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, cfg->device));
+    QPB_CUDA(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, cfg->device));
+    if (cc_major != 10) {
+        qpb_set_error("qpb_create: device %d is sm_%d%d; libqpb is built for sm_100a only", cfg->device, cc_major,
+                      cc_minor);
         return QPB_E_NODEVICE;
     }
+    lap("device properties");
     QPB_CUDA(cudaSetDevice(cfg->device));
+    lap("set device");
     qpb_ctx *c = new qpb_ctx();
     c->cfg = *cfg;
     if (!(c->cfg.diff_tol > 0.0)) c->cfg.diff_tol = 1e-12;
@@ -253,6 +273,7 @@ extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
     c->stream = c->own_stream;
     TRYCUDA(cudaEventCreate(&c->ev0));
     TRYCUDA(cudaEventCreate(&c->ev1));
+    lap("stream and events");
     const size_t nstate = (size_t)cfg->ne * c->ncd;
     TRY(dev_alloc(&c->d_S, nstate));
     TRYCUDA(cudaMemsetAsync(c->d_S, 0, nstate * sizeof(double), c->stream));
@@ -280,7 +301,9 @@ extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
     }
     c->pauli_cap = 1024;
     TRY(dev_alloc(&c->d_pauli, (size_t)c->pauli_cap));
+    lap("allocations");
     TRYCUDA(cudaStreamSynchronize(c->stream));
+    lap("done");
 #undef TRY
 #undef TRYCUDA
     *out = c;

@@ -188,3 +188,24 @@ def test_pair_breaking_creates_quasiparticles_from_an_empty_state():
                                              enable_recombination=True, tau_r=100.0, T_c=1.2, bath_temperature=1.0,
                                              dynes_gamma=0.18)
     assert mass[0] == 0.0 and mass[-1] > 0.0
+
+
+def test_ensemble_runs_members_through_the_single_gpu_path():
+    """BASELINE configs[4] in miniature: a parameter sweep over bath temperature and tau_0 on one mask; every member
+    equals a direct call of run_2d_crank_nicolson with the same arguments."""
+    import cases
+    import helpers
+
+    case = cases.meander_c2(ny=24, nx=32, ne=8, steps=2)
+    edges = Q.extract_edge_segments(case["mask"])
+    bcs = cases.make_bcs(edges, case["bc"], Q.BoundaryCondition)
+    gen = Q.ExternalGenerationSpec(**case["generation"])
+    base = cases.solver_kwargs(case, edges, bcs, gen, Q.physics)
+    members = Q.parameter_grid(base, bath_temperature=[0.05, 0.3], tau_0=[100.0, 800.0])
+    res = Q.run_ensemble(members, reduce=lambda out: (out[0], out[2], np.array(out[4][-1])))
+    assert len(res) == 4
+    for kw, (times, mass, last) in zip(members, res):
+        t2, _, m2, _, ef, _ = Q.run_2d_crank_nicolson(**kw)
+        assert times == t2 and mass == m2
+        np.testing.assert_array_equal(last, np.array(ef[-1]))
+    assert len({tuple(r[1]) for r in res}) == 4   # the parameters matter

@@ -146,3 +146,53 @@ def test_sharded_steps_equal_single_process_oracle(world, interleave, tmp_path):
         assert abs(got["pauli"][k][0] - mo) <= 1e-12 * mo
         assert int(got["pauli"][k][1]) == i * n + q
         assert int(got["pauli"][k][2]) == (-1 if forb is None else forb[0] * n + forb[1])
+
+
+# ---- ensembles (BASELINE configs[4]: independent runs, replicas only) ---------------------------------------
+def _fake_run(mask=None, dt=1.0, total_time=1.0, tag=0, device=0, **_):
+    """Stand-in for run_2d_crank_nicolson with the same return structure (times, frames, mass, limits, eframes, E)."""
+    times = [0.0, float(total_time)]
+    return times, [None, None], [float(tag), float(tag) * dt], [0.0, 1.0], None, None
+
+
+def _ensemble_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from qpsim_b200.ensemble import parameter_grid, run_ensemble
+
+        members = parameter_grid(dict(total_time=2.0), tag=range(1, 6), dt=[0.5, 0.25])
+        ran = []
+
+        def runner(**kw):
+            ran.append(kw["tag"] * 100 + int(kw["dt"] * 100))
+            assert kw["device"] == rank     # default device = LOCAL_RANK
+            return _fake_run(**kw)
+
+        res = run_ensemble(members, runner=runner)
+        np.savez(out + f".{rank}.npz", mass=np.array([r[1] for r in res]), ran=np.array(ran))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ensemble_members_are_dealt_round_robin_and_gathered(tmp_path):
+    from qpsim_b200.ensemble import member_indices, parameter_grid, run_ensemble
+
+    assert member_indices(10, 4, 1) == [1, 5, 9]
+    assert sorted(sum((member_indices(64, 8, r) for r in range(8)), [])) == list(range(64))
+    with pytest.raises(ValueError):
+        member_indices(4, 2, 2)
+    grid = parameter_grid(dict(a=1), b=[1, 2], c=[3, 4, 5])
+    assert len(grid) == 6 and grid[0] == dict(a=1, b=1, c=3) and grid[-1] == dict(a=1, b=2, c=5)
+    # single process: every member runs here, in order
+    single = run_ensemble(parameter_grid(dict(total_time=2.0), tag=range(1, 6), dt=[0.5, 0.25]), runner=_fake_run)
+    out = str(tmp_path / "ens")
+    world = 3
+    mp.spawn(_ensemble_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    ran_all = []
+    for r in range(world):
+        z = np.load(out + f".{r}.npz")
+        np.testing.assert_array_equal(z["mass"], np.array([s[1] for s in single]))   # every rank has the full list
+        ran_all += z["ran"].tolist()
+    assert len(ran_all) == 10 and len(set(ran_all)) == 10                           # each member ran exactly once
