@@ -266,10 +266,11 @@ def load_profile_traffic():
     with open(path) as f:
         k = json.load(f)
     out = {}
-    sw = [v["dram_bytes"] for n, v in k.items() if "k_sweep" in n]
+    # the captures of the bench workload itself (the file also holds the 512-bin GEMM and the segmented 2048^2 sweeps)
+    sw = [v["dram_bytes"] for n, v in k.items() if n.endswith("[k_sweep_x_pipe]") or n.endswith("[k_sweep_y_pipe]")]
     if sw:
         out["sweep"] = float(np.mean(sw))
-    co = [v["dram_bytes"] for n, v in k.items() if "k_collide" in n]
+    co = [v["dram_bytes"] for n, v in k.items() if n.endswith("[k_collide_struct]")]
     if co:
         out["collide"] = float(np.mean(co))
     return out

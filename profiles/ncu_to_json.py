@@ -15,6 +15,12 @@ KEEP = {
     "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
     "lts__t_sector_hit_rate.pct": "l2_hit_pct",
     "smsp__inst_executed.sum": "warp_instructions",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": "fp64_pipe_active_pct",
+    "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pipe_active_pct",
+    "dram__cycles_active.avg.pct_of_peak_sustained_elapsed": "dram_busy_pct",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "smem_wavefronts_pct",
+    "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum": "smem_bank_conflicts",
 }
 UNIT = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0, "us": 1.0, "ms": 1e3, "ns": 1e-3, "s": 1e6}
 out = {}
@@ -31,6 +37,7 @@ for path in sys.argv[2:]:
             if "average_warps_issue_stalled" in h and h.endswith("per_issue_active.ratio") and r[i] and float(r[i]) >= 0.2:
                 d.setdefault("stalls_per_issue", {})[h.split("stalled_")[1].split("_per_issue")[0]] = round(float(r[i]), 2)
         d["dram_bytes"] = d.get("dram_read", 0) + d.get("dram_write", 0)
-        out[name] = d
+        tag = path.split("/")[-1].replace("_raw.csv", "").replace("full_", "")
+        out[f"{name} [{tag}]"] = d
 json.dump(out, open(sys.argv[1], "w"), indent=1, sort_keys=True)
 print(json.dumps({k: (v["duration_us"], v["dram_bytes"]) for k, v in out.items()}))
