@@ -323,7 +323,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     dev_free(c->d_gapid); dev_free(c->d_idxd); dev_free(c->d_idxs); dev_free(c->d_idxdT);
     dev_free(c->d_sign); dev_free(c->d_signT); dev_free(c->d_dmap); dev_free(c->d_smap);
     dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_Mg); dev_free(c->d_Xn); dev_free(c->d_Xp); dev_free(c->d_scratch); dev_free(c->d_gen);
-    dev_free(c->d_integrated); dev_free(c->d_pauli); dev_free(c->d_xdense);
+    dev_free(c->d_integrated); dev_free(c->d_pauli); dev_free(c->d_xdense); dev_free(c->d_cperm); dev_free(c->d_ggid);
     if (c->d_pauli_part) qpb_dev_free(c->d_pauli_part);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -694,7 +694,9 @@ extern "C" int qpb_upload_collision(qpb_ctx *c, const double *K_r0, const double
     QPB_ALLOC(c->d_rho, (size_t)ng * ne);
     QPB_CUDA(cudaMemcpy(c->d_rho, rho, sizeof(double) * ng * ne, cudaMemcpyHostToDevice));
     dev_free(c->d_gapid);
+    c->h_gapid.clear();
     if (gap_id && ng > 1) {
+        c->h_gapid.assign(gap_id, gap_id + cf.ncell);
         for (int q = 0; q < cf.ncell; ++q)
             if (gap_id[q] < 0 || gap_id[q] >= ng) {
                 qpb_set_error("qpb_upload_collision: gap_id[%d]=%d out of range", q, gap_id[q]);

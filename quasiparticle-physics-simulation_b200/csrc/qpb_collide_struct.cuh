@@ -43,6 +43,11 @@ struct StructArgs {
     // mapped into this process (peer memory over NVLink).  xmode 1: the updated n(E) of my cells is stored straight
     // into the owning rank's diffusion state instead of my own; xmode 2: the staging loads read n(E) from there.
     //   route[i] = owner rank << 10 | row of bin i in the owner's state;  xdense[q] = dense grid index of my cell q
+    // Several gap tables (non-uniform gap): the cells are regrouped so that a CTA's CC cells share one table.
+    //   cperm[group * CC + lane] = cell index or -1 (padding);  ggid[group] = table of the group;  tables of gap g
+    //   start at K2 + g*nep^2, KsD + g*nep^2, KrA + g*2*nep^2, rho + g*nep.  cperm == nullptr: cells in order, one table.
+    const int32_t *cperm;
+    const int32_t *ggid;
     int xmode;
     long long xncd;
     double *xpeer[QPB_MAX_RANKS];
@@ -202,6 +207,13 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
     char *ring = ring_all + (size_t)(warp * SUBS + sub) * NSTAGE * STAGE_BYTES;
     const int cell0 = blockIdx.x * CC;
     const int ncell = A.ncell;
+    const int gid = A.cperm ? A.ggid[blockIdx.x] : 0;
+    const double2 *tK2 = A.K2 + (size_t)gid * nep * nep;
+    const double *tKsD = A.KsD + (size_t)gid * nep * nep;
+    const double *tKrA = A.KrA + (size_t)gid * 2 * nep * nep;
+    const double *trho = A.rho + (size_t)gid * nep;
+    // cell of a lane / staging thread (regrouped by gap table when there are several)
+    auto cell_of = [&](int lane_cell) { return A.cperm ? A.cperm[cell0 + lane_cell] : cell0 + lane_cell; };
 
     // ---- stage the per-cell columns -------------------------------------------------------------------
     // NT is a multiple of CC, so a thread always serves the same cell: its dense index is read once and every
@@ -212,8 +224,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
         // are in flight together, one memory round trip for the whole staging instead of one per batch.
         constexpr int RPT = NT / CC;   // columns covered by one pass of the CTA
         const int c_me = tid % CC, row_me = tid / CC;
-        const int q_me = cell0 + c_me;
-        const bool live_me = q_me < ncell;
+        const int q_me = cell_of(c_me);
+        const bool live_me = q_me >= 0 && q_me < ncell;
         const long long d_me = live_me ? (A.xmode == 2 ? A.xdense[q_me] : A.c2d[q_me]) : 0;
         for (int col = row_me; col < ncol; col += RPT) {
             const int i = col - PADF;
@@ -240,7 +252,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
         // p = rho * max(1 - n / max(rho, 1e-30), 0) of the thread's own elements (solver.py:719-721, 738)
         for (int col = row_me; col < ncol; col += RPT) {
             const int i = col - PADF;
-            const double rv = (i >= 0 && i < A.ne) ? A.rho[i] : 0.0;
+            const double rv = (i >= 0 && i < A.ne) ? trho[i] : 0.0;
             const double nv = sn[col * CC + c_me];
             sp[col * CC + c_me] = rv * fmax(1.0 - nv / fmax(rv, 1e-30), 0.0);
         }
@@ -250,8 +262,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
     const double *cp = sp + (size_t)PADF * CC + cl;
     const double *cnd = snd + cl;
     const double *cns = sns + cl;
-    const int q = cell0 + cl;
-    const bool live = q < ncell;
+    const int q = cell_of(cl);
+    const bool live = q >= 0 && q < ncell;
 
     // ---- pass 1: rows ------------------------------------------------------------------------------------
     {
@@ -266,7 +278,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
             double L[TI], G[TI];
 #pragma unroll
             for (int r = 0; r < TI; ++r) L[r] = G[r] = 0.0;
-            const char *gk = reinterpret_cast<const char *>(A.K2 + (size_t)i0 * nep);
+            const char *gk = reinterpret_cast<const char *>(tK2 + (size_t)i0 * nep);
             const size_t rstride = (size_t)nep * 16;
             __syncwarp();  // the previous round's last tile is no longer being read
 #pragma unroll
@@ -342,7 +354,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 int ntile = mytiles;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ntile = max(ntile, __shfl_xor_sync(0xffffffffu, ntile, o));
-                const char *gk = reinterpret_cast<const char *>(A.KsD + (size_t)k0 * nep + (size_t)t_lo * TJ);
+                const char *gk = reinterpret_cast<const char *>(tKsD + (size_t)k0 * nep + (size_t)t_lo * TJ);
                 const size_t rstride = (size_t)nep * 8;
                 __syncwarp();
 #pragma unroll
@@ -410,8 +422,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
             // the pieces have met: every thread finishes its share of (diagonal, cell) pairs
             __syncthreads();
             constexpr int RPT = NT / CC;
-            const int c_me = tid % CC, q_me = cell0 + c_me;
-            if (q_me < ncell) {
+            const int c_me = tid % CC, q_me = cell_of(c_me);
+            if (q_me >= 0 && q_me < ncell) {
                 for (int k = tid / CC; k < A.ne; k += RPT) {
                     const int om = A.dmap[k];
                     if (RC && A.mofk[k] >= 0) continue;   // also fed by an anti-diagonal: stays in the stash for pass 3
@@ -447,7 +459,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 int ntile = mytiles;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ntile = max(ntile, __shfl_xor_sync(0xffffffffu, ntile, o));
-                const char *gk = reinterpret_cast<const char *>(A.KrA + (size_t)m0 * nep + jlo);
+                const char *gk = reinterpret_cast<const char *>(tKrA + (size_t)m0 * nep + jlo);
                 const size_t rstride = (size_t)nep * 8;
                 __syncwarp();
 #pragma unroll

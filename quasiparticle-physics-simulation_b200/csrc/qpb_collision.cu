@@ -191,50 +191,104 @@ struct StructTables {
 static StructTables carve_tables(qpb_ctx *c) {
     StructTables t;
     const int nep = ((c->cfg.ne + TI - 1) / TI) * TI;
+    const size_t ng = (size_t)c->cfg.ngap;
     t.nep = nep;
     char *base = (char *)c->d_scratch;
     t.K2 = (double2 *)base;
-    base += sizeof(double2) * (size_t)nep * nep;
+    base += sizeof(double2) * ng * nep * nep;
     t.KsD = (double *)base;
-    base += sizeof(double) * (size_t)nep * nep;
+    base += sizeof(double) * ng * nep * nep;
     t.KrA = (double *)base;
-    base += sizeof(double) * (size_t)2 * nep * nep;
+    base += sizeof(double) * ng * 2 * nep * nep;
     t.rho = (double *)base;
     return t;
+}
+
+// cells per CTA of the structured kernel for a padded energy grid (0: does not fit)
+static int struct_cells_per_cta(int nep) {
+    const size_t cap = 227 * 1024;
+    auto need = [&](int cc, int nt) {
+        return sizeof(double) * (size_t)cc * (2 * (nep + PADF + PADB) + 3 * nep) +
+               (size_t)(nt / 32) * (32 / cc) * NSTAGE * (TI * TJ * 16);
+    };
+    if (need(32, 512) <= cap) return 32;
+    if (need(16, 256) <= cap) return 16;
+    if (need(8, 256) <= cap) return 8;
+    if (need(4, 128) <= cap) return 4;
+    return 0;
+}
+
+static void dev_free_groups(qpb_ctx *c) {
+    if (c->d_cperm) qpb_dev_free(c->d_cperm);
+    if (c->d_ggid) qpb_dev_free(c->d_ggid);
+    c->d_cperm = c->d_ggid = nullptr;
+    c->ngroups = 0;
+    c->group_cc = 0;
 }
 
 int qpbk_collision_setup(qpb_ctx *c) {
     const auto &cf = c->cfg;
     const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
+    dev_free_groups(c);
     if (!(scat || rec)) return QPB_OK;
-    if (!(c->structured && cf.ngap == 1) || ((cf.ne + TI - 1) / TI) * TI > NEPMAX || cf.nw > 32767) {
+    const int ne = cf.ne, ng = cf.ngap;
+    const int nep = ((ne + TI - 1) / TI) * TI;
+    if (!c->structured || nep > NEPMAX || cf.nw > 32767) {
         c->structured = false;
         return QPB_OK;
     }
-    const int ne = cf.ne;
-    const int nep = ((ne + TI - 1) / TI) * TI;
-    const size_t bytes = sizeof(double2) * (size_t)nep * nep + sizeof(double) * (size_t)3 * nep * nep +
-                         sizeof(double) * (size_t)nep;
+    const size_t per_gap = sizeof(double2) * (size_t)nep * nep + sizeof(double) * (size_t)3 * nep * nep +
+                           sizeof(double) * (size_t)nep;
+    const size_t bytes = per_gap * ng;
+    // Several gap tables: the structured kernel needs the CC cells of a CTA to share one table, so the cells are
+    // regrouped by gap id (padded to CC per group).  Not worth it when the padding more than doubles the work or the
+    // tables outgrow 2 GB: the generic kernel (per-cell table lookups) takes those.
+    std::vector<int32_t> cperm, ggid;
+    if (ng > 1) {
+        const int cc = struct_cells_per_cta(nep);
+        if (cc == 0 || c->h_gapid.size() != (size_t)cf.ncell || bytes > ((size_t)2 << 30)) {
+            c->structured = false;
+            return QPB_OK;
+        }
+        std::vector<std::vector<int32_t>> members(ng);
+        for (int q = 0; q < cf.ncell; ++q) members[c->h_gapid[q]].push_back(q);
+        for (int g = 0; g < ng; ++g)
+            for (size_t o = 0; o < members[g].size(); o += cc) {
+                ggid.push_back(g);
+                for (int l = 0; l < cc; ++l)
+                    cperm.push_back(o + l < members[g].size() ? members[g][o + l] : -1);
+            }
+        if (cperm.size() > (size_t)2 * cf.ncell + (size_t)cc) {
+            c->structured = false;
+            return QPB_OK;
+        }
+        c->group_cc = cc;
+    }
     if (c->d_scratch) qpb_dev_free(c->d_scratch);
     c->d_scratch = nullptr;
     QPB_CUDA(qpb_dev_malloc((void **)&c->d_scratch, bytes));
     c->scratch_bytes = bytes;
-    // pull the uploaded matrices back (they are tiny) and build the padded / skewed copies
-    std::vector<double> Ks((size_t)ne * ne, 0.0), Kr((size_t)ne * ne, 0.0), rho(ne);
-    if (scat) QPB_CUDA(cudaMemcpy(Ks.data(), c->d_Ks, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost));
-    if (rec) QPB_CUDA(cudaMemcpy(Kr.data(), c->d_Kr, sizeof(double) * ne * ne, cudaMemcpyDeviceToHost));
-    QPB_CUDA(cudaMemcpy(rho.data(), c->d_rho, sizeof(double) * ne, cudaMemcpyDeviceToHost));
-    std::vector<double2> K2((size_t)nep * nep, make_double2(0.0, 0.0));
-    std::vector<double> KsD((size_t)nep * nep, 0.0), KrA((size_t)2 * nep * nep, 0.0), rhop(nep, 0.0);
+    // pull the uploaded matrices back (they are small) and build the padded / skewed copies, one set per gap table
+    const size_t nn = (size_t)ne * ne;
+    std::vector<double> Ks(nn * ng, 0.0), Kr(nn * ng, 0.0), rho((size_t)ne * ng);
+    if (scat) QPB_CUDA(cudaMemcpy(Ks.data(), c->d_Ks, sizeof(double) * nn * ng, cudaMemcpyDeviceToHost));
+    if (rec) QPB_CUDA(cudaMemcpy(Kr.data(), c->d_Kr, sizeof(double) * nn * ng, cudaMemcpyDeviceToHost));
+    QPB_CUDA(cudaMemcpy(rho.data(), c->d_rho, sizeof(double) * ne * ng, cudaMemcpyDeviceToHost));
+    const size_t np2 = (size_t)nep * nep;
+    std::vector<double2> K2(np2 * ng, make_double2(0.0, 0.0));
+    std::vector<double> KsD(np2 * ng, 0.0), KrA(2 * np2 * ng, 0.0), rhop((size_t)nep * ng, 0.0);
     const double dE = cf.dE;
-    for (int i = 0; i < ne; ++i) {
-        rhop[i] = rho[i];
-        for (int j = 0; j < ne; ++j) {
-            K2[(size_t)i * nep + j] = make_double2(dE * Ks[(size_t)i * ne + j], 2.0 * dE * Kr[(size_t)i * ne + j]);
-            if (i >= j) KsD[(size_t)(i - j) * nep + j] = dE * Ks[(size_t)i * ne + j];
-            if (j <= i) {
-                const double wgt = j < i ? 2.0 : 1.0;
-                KrA[(size_t)(i + j) * nep + j] = wgt * dE * Kr[(size_t)i * ne + j];
+    for (int g = 0; g < ng; ++g) {
+        const double *ks = Ks.data() + nn * g, *kr = Kr.data() + nn * g;
+        for (int i = 0; i < ne; ++i) {
+            rhop[(size_t)g * nep + i] = rho[(size_t)g * ne + i];
+            for (int j = 0; j < ne; ++j) {
+                K2[np2 * g + (size_t)i * nep + j] = make_double2(dE * ks[(size_t)i * ne + j], 2.0 * dE * kr[(size_t)i * ne + j]);
+                if (i >= j) KsD[np2 * g + (size_t)(i - j) * nep + j] = dE * ks[(size_t)i * ne + j];
+                if (j <= i) {
+                    const double wgt = j < i ? 2.0 : 1.0;
+                    KrA[2 * np2 * g + (size_t)(i + j) * nep + j] = wgt * dE * kr[(size_t)i * ne + j];
+                }
             }
         }
     }
@@ -242,7 +296,14 @@ int qpbk_collision_setup(qpb_ctx *c) {
     QPB_CUDA(cudaMemcpy(t.K2, K2.data(), sizeof(double2) * K2.size(), cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMemcpy(t.KsD, KsD.data(), sizeof(double) * KsD.size(), cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMemcpy(t.KrA, KrA.data(), sizeof(double) * KrA.size(), cudaMemcpyHostToDevice));
-    QPB_CUDA(cudaMemcpy(t.rho, rhop.data(), sizeof(double) * nep, cudaMemcpyHostToDevice));
+    QPB_CUDA(cudaMemcpy(t.rho, rhop.data(), sizeof(double) * rhop.size(), cudaMemcpyHostToDevice));
+    if (ng > 1) {
+        QPB_CUDA(qpb_dev_malloc((void **)&c->d_cperm, sizeof(int32_t) * cperm.size()));
+        QPB_CUDA(qpb_dev_malloc((void **)&c->d_ggid, sizeof(int32_t) * ggid.size()));
+        QPB_CUDA(cudaMemcpy(c->d_cperm, cperm.data(), sizeof(int32_t) * cperm.size(), cudaMemcpyHostToDevice));
+        QPB_CUDA(cudaMemcpy(c->d_ggid, ggid.data(), sizeof(int32_t) * ggid.size(), cudaMemcpyHostToDevice));
+        c->ngroups = (int)ggid.size();
+    }
     return QPB_OK;
 }
 
@@ -264,7 +325,7 @@ static int launch_struct(qpb_ctx *c, const StructArgs &A, size_t smem) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    const int blocks = (A.ncell + CC - 1) / CC;
+    const int blocks = A.cperm ? c->ngroups : (A.ncell + CC - 1) / CC;
     kern<<<blocks, NT, smem, c->stream>>>(A);
     QPB_CHECK_LAUNCH();
     return QPB_OK;
@@ -465,6 +526,8 @@ int qpbk_collide(qpb_ctx *c, double dt, int xmode) {
             A.kofm[m] = (int16_t)c->h_kof[c->h_smap[m]];
         }
         A.dt = dt;
+        A.cperm = c->d_cperm;
+        A.ggid = c->d_ggid;
         A.xmode = xmode;
         A.xncd = c->x_ncd;
         A.xdense = c->d_xdense;
@@ -478,6 +541,14 @@ int qpbk_collide(qpb_ctx *c, double dt, int xmode) {
         const bool narrow = ecc && ecc[0] == '1';
         if (narrow && 2 * (StructCfg<16>::smem(t.nep) + 1024) <= 228 * 1024)
             return dispatch_struct<16>(c, A, StructCfg<16>::smem(t.nep), scat, rec, ph);
+        if (c->d_cperm) {   // regrouped cells: the group width was fixed at setup
+            switch (c->group_cc) {
+                case 32: return dispatch_struct<32>(c, A, StructCfg<32>::smem(t.nep), scat, rec, ph);
+                case 16: return dispatch_struct<16>(c, A, StructCfg<16>::smem(t.nep), scat, rec, ph);
+                case 8: return dispatch_struct<8>(c, A, StructCfg<8>::smem(t.nep), scat, rec, ph);
+                default: return dispatch_struct<4>(c, A, StructCfg<4>::smem(t.nep), scat, rec, ph);
+            }
+        }
         if (StructCfg<32>::smem(t.nep) <= smem_cap) return dispatch_struct<32>(c, A, StructCfg<32>::smem(t.nep), scat, rec, ph);
         if (StructCfg<16>::smem(t.nep) <= smem_cap) return dispatch_struct<16>(c, A, StructCfg<16>::smem(t.nep), scat, rec, ph);
         if (StructCfg<8>::smem(t.nep) <= smem_cap) return dispatch_struct<8>(c, A, StructCfg<8>::smem(t.nep), scat, rec, ph);

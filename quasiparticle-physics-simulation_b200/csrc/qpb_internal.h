@@ -136,6 +136,11 @@ struct qpb_ctx {
     double *d_Mg = nullptr, *d_Xn = nullptr, *d_Xp = nullptr;
     int gemm_nep = 0;
     long long gemm_npadc = 0;
+    // several gap tables on the structured kernel: cells regrouped by table (qpbk_collision_setup)
+    std::vector<int32_t> h_gapid;     // [ncell] host copy
+    int32_t *d_cperm = nullptr;       // [ngroups * group_cc] cell index or -1
+    int32_t *d_ggid = nullptr;        // [ngroups] gap table of the group
+    int ngroups = 0, group_cc = 0;
     double *d_scratch = nullptr;      // collision scratch
     size_t scratch_bytes = 0;
     // fused layout exchange (qpb_set_exchange): peer diffusion states, routing of bins, dense index of my cells

@@ -73,13 +73,19 @@ def test_collision_accuracy_against_extended_precision(generic, monkeypatch):
                 assert np.max(e_gpu) <= 4.0 * np.max(e_ref) + 1e-13, (tag, c, np.max(e_gpu), np.max(e_ref))
 
 
-def test_generic_collision_kernel_nonuniform_tables():
-    """Per-pixel tables (solver.py:834-875) go through the generic kernel."""
+@pytest.mark.parametrize("path,ne,n,ngaps", [("generic", 12, 23, 2), ("grouped", 12, 23, 2), ("grouped", 40, 300, 7),
+                                             ("grouped", 136, 150, 3), ("generic", 40, 60, 60)])
+def test_collision_kernels_nonuniform_tables(path, ne, n, ngaps, monkeypatch):
+    """Per-pixel tables (solver.py:834-875).  "generic": per-cell table lookups with shared-memory atomics (forced, or
+    chosen because every cell has its own gap).  "grouped": the structured kernel with the cells regrouped so that a
+    CTA's cells share one gap table (ragged groups, padding lanes, 32- and 16-cell CTAs)."""
+    if path == "generic" and ngaps < n:
+        monkeypatch.setenv("QPB_FORCE_GENERIC", "1")
     rng = np.random.default_rng(5)
-    ne, n = 12, 23
     E, dE = Q.build_energy_grid(cases.GAP, 1.0, 4.0, ne)
     om, idd, ids, sg = Q.phonon_frequency_map(E)
-    gaps = np.where(np.arange(n) % 3 == 0, cases.GAP, 0.93 * cases.GAP)
+    gaps = cases.GAP * (1.0 - 0.07 * rng.integers(0, ngaps, n) / max(1, ngaps - 1)) if ngaps < n else \
+        cases.GAP * (1.0 - 0.07 * np.arange(n) / n)
     rho_all = np.stack([Q.density_of_states(E, g, 0.18) for g in gaps])
     Kr_all = np.stack([Q.recombination_kernel_base(E, g, 440.0, 1.2) for g in gaps])
     Ks_all = np.stack([Q.scattering_kernel_base(E, g, 440.0, 1.2) for g in gaps])
