@@ -215,6 +215,12 @@ int qpb_add_generation(qpb_ctx *ctx, double scale, double rate);
  * ordered (no host sync); every call that returns data to the host synchronises that stream. */
 int qpb_set_stream(qpb_ctx *ctx, void *cuda_stream);
 
+/* Fixed-bath forward-Euler collision forms of the reference (apply_scattering_step, solver.py:551-581;
+ * apply_recombination_step, solver.py:584-605) on the context's state: the K(E,E') contraction and the n.R.n form as
+ * one FP64 tensor-core GEMM from 64 bins on, a fused GEMV below.
+ *   kind 1: K = K_s [NE][NE], vec = rho_bins [NE];   kind 2: K = K_r [NE][NE], vec = G_therm [NE] */
+int qpb_euler_step(qpb_ctx *ctx, int32_t kind, const double *K, const double *vec, double dt);
+
 /* ---- layout exchange fused into the collision kernel (multi-GPU) -------------------------------------
  * The cell-sharded collision context of a rank can store the updated n(E) of its cells straight into the bin-sharded
  * diffusion states of all ranks (mode 1: collide, then scatter over NVLink peer memory) and read its cells from there

@@ -376,6 +376,49 @@ def collide(state, phonons, Kr, Ks, rho, idx_diff, idx_sum, sign, dE, dt, *,
 
 
 # --------------------------------------------------------------------------
+# Fixed-bath forward-Euler collision forms (solver.py:551-605) with the bath-dressed kernels
+# (solver.py:493-548).  state is (NE, N), modified in place like the reference's helpers.
+# --------------------------------------------------------------------------
+def kr_dressed(E: np.ndarray, gap: float, tau: float, Tc: float, T_bath: float) -> np.ndarray:
+    """solver.py:493-516 recombination_kernel."""
+    kT = KB_UEV_PER_K * T_bath
+    es = E[:, None] + E[None, :]
+    n_p = 1.0 / (np.exp(np.minimum(es / kT, 500.0)) - 1.0) + 1.0 if kT > 0 else np.ones_like(es)
+    return kr0(E, gap, tau, Tc) * n_p
+
+
+def ks_dressed(E: np.ndarray, gap: float, tau: float, Tc: float, T_bath: float) -> np.ndarray:
+    """solver.py:519-548 scattering_kernel."""
+    kT = KB_UEV_PER_K * T_bath
+    ed = E[:, None] - E[None, :]
+    if kT > 0:
+        with np.errstate(divide="ignore", invalid="ignore"):
+            nbe = 1.0 / (np.exp(np.minimum(np.abs(ed) / kT, 500.0)) - 1.0)
+        n_p = np.where(ed > 0, 1.0 + nbe, nbe)
+    else:
+        n_p = np.where(ed > 0, 1.0, 0.0)
+    np.fill_diagonal(n_p, 0.0)
+    return ks0(E, gap, tau, Tc) * n_p
+
+
+def euler_scattering_step(state: np.ndarray, K_s: np.ndarray, rho_bins: np.ndarray, dE: float, dt: float) -> None:
+    """solver.py:551-581 apply_scattering_step."""
+    rho = rho_bins[:, None]
+    one_minus_f = np.maximum(1.0 - state / np.maximum(rho, 1e-30), 0.0)
+    scat_in = dE * rho * one_minus_f * (K_s.T @ state)
+    scat_out = state * dE * ((K_s * rho_bins[None, :]) @ one_minus_f)
+    state += dt * (scat_in - scat_out)
+    np.maximum(state, 0.0, out=state)
+
+
+def euler_recombination_step(state: np.ndarray, K_r: np.ndarray, G_therm: np.ndarray, dE: float, dt: float) -> None:
+    """solver.py:584-605 apply_recombination_step."""
+    recomb_rate = 2.0 * state * dE * (K_r @ state)
+    state += dt * (G_therm[:, None] - recomb_rate)
+    np.maximum(state, 0.0, out=state)
+
+
+# --------------------------------------------------------------------------
 # A8: Pauli diagnostics  (solver.py:967-996)
 # --------------------------------------------------------------------------
 def pauli_stats(state, rho_state, floor=1e-18):

@@ -19,12 +19,17 @@ from .physics import (  # noqa: F401
     phonon_frequency_map,
     recombination_kernel_base,
     scattering_kernel_base,
+    recombination_kernel,
+    scattering_kernel,
+    thermal_generation,
     thermal_phonon_occupation,
     thermal_qp_weights,
 )
 from .solver import (  # noqa: F401
     apply_collision_step_fischer_catelani_nonuniform,
     apply_collision_step_fischer_catelani_uniform,
+    apply_recombination_step,
+    apply_scattering_step,
     reconstruct_field,
     run_2d_crank_nicolson,
 )
@@ -35,6 +40,7 @@ __all__ = [
     "run_2d_crank_nicolson",
     "apply_collision_step_fischer_catelani_uniform",
     "apply_collision_step_fischer_catelani_nonuniform",
+    "apply_scattering_step", "apply_recombination_step",
     "BoundaryCondition", "BoundaryFace", "EdgeSegment", "ExternalGenerationSpec", "BoundaryAssignmentError",
     "extract_edge_segments", "compile_boundaries", "build_energy_grid", "capi", "run_ensemble", "parameter_grid",
 ]

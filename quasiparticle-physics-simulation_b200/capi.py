@@ -79,7 +79,7 @@ EXPORTED = [
     "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
     "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
     "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons", "qpb_pauli_record", "qpb_pauli_fetch", "qpb_set_exchange", "qpb_collide_exchange",
-    "qpb_ipc_export", "qpb_ipc_open", "qpb_ipc_close",
+    "qpb_ipc_export", "qpb_ipc_open", "qpb_ipc_close", "qpb_euler_step",
 ]
 
 
@@ -157,6 +157,7 @@ def load_library():
     lib.qpb_pauli_record.argtypes = [vp, i32]
     lib.qpb_set_exchange.argtypes = [vp, i32, C.POINTER(vp), i64, vp, vp, vp]
     lib.qpb_collide_exchange.argtypes = [vp, dbl, i32]
+    lib.qpb_euler_step.argtypes = [vp, i32, vp, vp, dbl]
     lib.qpb_ipc_export.argtypes = [vp, C.c_int, vp]
     lib.qpb_ipc_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
     lib.qpb_ipc_close.argtypes = [C.c_int, vp]
@@ -320,6 +321,13 @@ class Context:
         buf = (C.c_ubyte * 64)()
         self._check(self.lib.qpb_ipc_export(self.handle, int(which), C.cast(buf, C.c_void_p)))
         return bytes(buf)
+
+    def euler_step(self, kind: int, K, vec, dt: float):
+        """Fixed-bath forward-Euler form on the context's state: kind 1 scattering (K_s, rho), 2 recombination
+        (K_r, G_therm)."""
+        k = _f64(K, (self.ne, self.ne))
+        v = _f64(vec, (self.ne,))
+        self._check(self.lib.qpb_euler_step(self.handle, int(kind), _ptr(k), _ptr(v), float(dt)))
 
     def diffuse(self, slot=0):
         self._check(self.lib.qpb_diffuse(self.handle, int(slot)))

@@ -323,7 +323,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     dev_free(c->d_gapid); dev_free(c->d_idxd); dev_free(c->d_idxs); dev_free(c->d_idxdT);
     dev_free(c->d_sign); dev_free(c->d_signT); dev_free(c->d_dmap); dev_free(c->d_smap);
     dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_Mg); dev_free(c->d_Xn); dev_free(c->d_Xp); dev_free(c->d_scratch); dev_free(c->d_gen);
-    dev_free(c->d_integrated); dev_free(c->d_pauli); dev_free(c->d_xdense); dev_free(c->d_cperm); dev_free(c->d_ggid);
+    dev_free(c->d_integrated); dev_free(c->d_pauli); dev_free(c->d_xdense); dev_free(c->d_cperm); dev_free(c->d_ggid); dev_free(c->d_euler);
     if (c->d_pauli_part) qpb_dev_free(c->d_pauli_part);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -892,6 +892,15 @@ extern "C" int qpb_collide(qpb_ctx *c, double dt) {
     }
     if (!(dt > 0.0)) return QPB_OK;  // solver.py:1385
     return qpbk_collide(c, dt);
+}
+
+extern "C" int qpb_euler_step(qpb_ctx *c, int32_t kind, const double *K, const double *vec, double dt) {
+    QPB_ENTER(c);
+    if (kind < 1 || kind > 2 || !K || !vec || !c->have_geom) {
+        qpb_set_error("qpb_euler_step: kind 1 (scattering) or 2 (recombination), non-null tables, geometry uploaded");
+        return QPB_E_INVALID;
+    }
+    return qpbk_euler_step(c, kind, K, vec, dt);
 }
 
 extern "C" int qpb_set_exchange(qpb_ctx *c, int32_t nranks, void *const *peer_state, int64_t peer_ncd,

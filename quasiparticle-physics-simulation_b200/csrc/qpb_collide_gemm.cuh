@@ -25,7 +25,19 @@ struct GemmArgs {
     double *Xn, *Xp;     // [nep][npadc]
     const double *rho;   // [nep] zero padded
     double dt;
+    // epilogue: 0 relaxation update of the coupled solver (solver.py:655-665);
+    //           1 forward-Euler scattering  n + dt (p G - n L)   (solver.py:551-581, M = [dE Ks | 0 | 0 | dE Ks^T]);
+    //           2 forward-Euler recombination  n + dt (gth - n L)   (solver.py:584-605, M = [0 | 2dE Kr | 0 | 0])
+    int mode;
+    const double *gth;   // [nep] thermal generation (mode 2)
 };
+
+__device__ __forceinline__ double collision_epilogue(int mode, double n, double p, double G, double L, double gth,
+                                                     double dt) {
+    if (mode == 0) return relax_update(n, p * G, L, dt);
+    if (mode == 1) return fmax(n + dt * (p * G - n * L), 0.0);
+    return fmax(n + dt * (gth - n * L), 0.0);
+}
 
 constexpr int GM_BM = 64, GM_BN = 128, GM_BK = 16, GM_ST = 3;
 constexpr int GM_AP = GM_BK + 4;     // matrix tile pitch (doubles)
@@ -129,15 +141,18 @@ __global__ void __launch_bounds__(256, 1) k_collide_gemm(GemmArgs A) {
     for (int rt = 0; rt < 2; ++rt) {
         const int i = i0 + wr * 16 + rt * 8 + (lane >> 2);
         if (i >= A.ne) continue;
+        const double gth = A.mode == 2 ? A.gth[i] : 0.0;
 #pragma unroll
         for (int ct = 0; ct < 8; ++ct) {
             const int q = c0 + wc * 64 + ct * 8 + 2 * (lane & 3);
             if (q >= A.ncell) continue;
             const double2 n2 = *reinterpret_cast<const double2 *>(A.Xn + (size_t)i * npadc + q);
             const double2 p2 = *reinterpret_cast<const double2 *>(A.Xp + (size_t)i * npadc + q);
-            A.S[(long long)i * A.ncd + A.c2d[q]] = relax_update(n2.x, p2.x * G[rt][ct][0], L[rt][ct][0], A.dt);
+            A.S[(long long)i * A.ncd + A.c2d[q]] =
+                collision_epilogue(A.mode, n2.x, p2.x, G[rt][ct][0], L[rt][ct][0], gth, A.dt);
             if (q + 1 < A.ncell)
-                A.S[(long long)i * A.ncd + A.c2d[q + 1]] = relax_update(n2.y, p2.y * G[rt][ct][1], L[rt][ct][1], A.dt);
+                A.S[(long long)i * A.ncd + A.c2d[q + 1]] =
+                    collision_epilogue(A.mode, n2.y, p2.y, G[rt][ct][1], L[rt][ct][1], gth, A.dt);
         }
     }
 }

@@ -18,6 +18,8 @@ struct UniformArgs {
     const double4 *K4;   // [nep][nep]  (dE Ke_ij, dE Ke_ji, 2dE Kb_ij, 2dE Ka_ij)
     const double *rho;   // [nep] zero padded
     double dt;
+    int mode;            // epilogue, see GemmArgs::mode
+    const double *gth;   // [nep] thermal generation (mode 2)
 };
 
 template <int CC, int NT>
@@ -119,7 +121,9 @@ __global__ void __launch_bounds__(NT, 1) k_collide_uniform(UniformArgs A) {
 #pragma unroll
             for (int r = 0; r < TI; ++r) {
                 const int i = i0 + r;
-                if (i < A.ne) A.S[(long long)i * A.ncd + d] = relax_update(cn[i * CC], cp[i * CC] * G[r], L[r], A.dt);
+                if (i < A.ne)
+                    A.S[(long long)i * A.ncd + d] = collision_epilogue(A.mode, cn[i * CC], cp[i * CC], G[r], L[r],
+                                                                       A.mode == 2 ? A.gth[i] : 0.0, A.dt);
             }
         }
     }

@@ -176,8 +176,8 @@ __global__ void __launch_bounds__(128) k_collide_generic(GenericArgs A) {
 }
 
 #include "qpb_collide_struct.cuh"
-#include "qpb_collide_uniform.cuh"
 #include "qpb_collide_gemm.cuh"
+#include "qpb_collide_uniform.cuh"
 
 struct StructTables {
     double2 *K2 = nullptr;
@@ -444,6 +444,8 @@ int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin) {
     return QPB_OK;
 }
 
+static int launch_gemm_args(qpb_ctx *c, const GemmArgs &G);
+
 static int launch_gemm(qpb_ctx *c, double dt) {
     const auto &cf = c->cfg;
     GemmArgs G;
@@ -451,6 +453,13 @@ static int launch_gemm(qpb_ctx *c, double dt) {
     G.S = c->d_S; G.c2d = c->d_cell2dense; G.M = c->d_Mg; G.Xn = c->d_Xn; G.Xp = c->d_Xp;
     G.rho = c->d_Mg + (size_t)4 * G.nep * G.nep;
     G.dt = dt;
+    G.mode = 0;
+    G.gth = nullptr;
+    return launch_gemm_args(c, G);
+}
+
+static int launch_gemm_args(qpb_ctx *c, const GemmArgs &G) {
+    const auto &cf = c->cfg;
     static bool configured = false;
     const size_t smem = (size_t)GM_ST * GM_STAGE_BYTES;
     if (!configured) {
@@ -462,7 +471,7 @@ static int launch_gemm(qpb_ctx *c, double dt) {
     k_gemm_pack<<<pack_blocks, 256, 0, c->stream>>>(G);
     QPB_CHECK_LAUNCH();
     // cell blocks along x so that CTAs running together share the row block's matrix tiles in L2
-    dim3 grid((unsigned)(c->gemm_npadc / GM_BN), (unsigned)(G.nep / GM_BM));
+    dim3 grid((unsigned)(G.npadc / GM_BN), (unsigned)(G.nep / GM_BM));
     k_collide_gemm<<<grid, 256, smem, c->stream>>>(G);
     QPB_CHECK_LAUNCH();
     c->diag.kernel_launches++;
@@ -484,6 +493,95 @@ static int launch_uniform(qpb_ctx *c, const UniformArgs &A) {
     return QPB_OK;
 }
 
+// ---- fixed-bath forward-Euler forms (solver.py:551-605): the same products with other matrices and epilogues ------
+int qpbk_euler_step(qpb_ctx *c, int kind, const double *K, const double *vec, double dt) {
+    const auto &cf = c->cfg;
+    const int ne = cf.ne;
+    const double dE = cf.dE;
+    int min_ne = 64;
+    if (const char *e = getenv("QPB_GEMM_MIN_NE")) min_ne = atoi(e);
+    const bool gemm = ne >= min_ne && !(getenv("QPB_NO_GEMM") && getenv("QPB_NO_GEMM")[0] == '1');
+    c->diag.kernel_launches++;
+    ScopedTimer tm(c, 2);
+    if (gemm) {
+        const int ng = ((ne + GM_BM - 1) / GM_BM) * GM_BM;
+        const size_t npadc = ((size_t)cf.ncell + GM_BN - 1) / GM_BN * GM_BN;
+        // [4 matrices | rho | gth], operands Xn, Xp
+        std::vector<double> M((size_t)4 * ng * ng + 2 * ng, 0.0);
+        double *rho = M.data() + (size_t)4 * ng * ng, *gth = rho + ng;
+        for (int i = 0; i < ne; ++i) {
+            if (kind == 1) rho[i] = vec[i]; else gth[i] = vec[i];
+            for (int j = 0; j < ne; ++j) {
+                if (kind == 1) {
+                    M[((size_t)0 * ng + i) * ng + j] = dE * K[(size_t)i * ne + j];        // L: dE Ks_ij p_j
+                    M[((size_t)3 * ng + i) * ng + j] = dE * K[(size_t)j * ne + i];        // G: dE Ks_ji n_j
+                } else {
+                    M[((size_t)1 * ng + i) * ng + j] = 2.0 * dE * K[(size_t)i * ne + j];  // L: 2dE Kr_ij n_j
+                }
+            }
+        }
+        const size_t need = sizeof(double) * (M.size() + 2 * (size_t)ng * npadc);
+        if (c->euler_bytes < need) {
+            if (c->d_euler) qpb_dev_free(c->d_euler);
+            c->d_euler = nullptr;
+            QPB_CUDA(qpb_dev_malloc((void **)&c->d_euler, need));
+            c->euler_bytes = need;
+            QPB_CUDA(cudaMemsetAsync(c->d_euler, 0, need, c->stream));   // operand padding stays zero
+        }
+        QPB_CUDA(cudaMemcpyAsync(c->d_euler, M.data(), sizeof(double) * M.size(), cudaMemcpyHostToDevice, c->stream));
+        QPB_CUDA(cudaStreamSynchronize(c->stream));   // M is a local vector
+        GemmArgs G;
+        G.ne = ne; G.nep = ng; G.ncell = cf.ncell; G.npadc = (int)npadc; G.ncd = c->ncd;
+        G.S = c->d_S; G.c2d = c->d_cell2dense; G.M = c->d_euler;
+        G.rho = c->d_euler + (size_t)4 * ng * ng;
+        G.gth = G.rho + ng;
+        G.Xn = c->d_euler + M.size();
+        G.Xp = G.Xn + (size_t)ng * npadc;
+        G.dt = dt;
+        G.mode = kind;
+        return launch_gemm_args(c, G);
+    }
+    // fused GEMV: packed [nep][nep][4] = (L<-p, G<-n, L<-n, G<-p) + rho + gth
+    const int nep = ((ne + TI - 1) / TI) * TI;
+    std::vector<double> K4((size_t)4 * nep * nep + 2 * nep, 0.0);
+    double *rho = K4.data() + (size_t)4 * nep * nep, *gth = rho + nep;
+    for (int i = 0; i < ne; ++i) {
+        if (kind == 1) rho[i] = vec[i]; else gth[i] = vec[i];
+        for (int j = 0; j < ne; ++j) {
+            double *o = &K4[((size_t)i * nep + j) * 4];
+            if (kind == 1) {
+                o[0] = dE * K[(size_t)i * ne + j];
+                o[1] = dE * K[(size_t)j * ne + i];
+            } else {
+                o[2] = 2.0 * dE * K[(size_t)i * ne + j];
+            }
+        }
+    }
+    const size_t need = sizeof(double) * K4.size();
+    if (c->euler_bytes < need) {
+        if (c->d_euler) qpb_dev_free(c->d_euler);
+        c->d_euler = nullptr;
+        QPB_CUDA(qpb_dev_malloc((void **)&c->d_euler, need));
+        c->euler_bytes = need;
+    }
+    QPB_CUDA(cudaMemcpyAsync(c->d_euler, K4.data(), need, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    UniformArgs U;
+    U.ne = ne; U.nep = nep; U.ncell = cf.ncell; U.ncd = c->ncd;
+    U.S = c->d_S; U.c2d = c->d_cell2dense;
+    U.K4 = reinterpret_cast<const double4 *>(c->d_euler);
+    U.rho = c->d_euler + (size_t)4 * nep * nep;
+    U.gth = U.rho + nep;
+    U.dt = dt;
+    U.mode = kind;
+    int rc = launch_uniform<32, 512>(c, U);
+    if (rc <= 0) return rc;
+    rc = launch_uniform<8, 256>(c, U);
+    if (rc <= 0) return rc;
+    qpb_set_error("qpb_euler_step: %d energy bins do not fit the fused GEMV kernel", ne);
+    return QPB_E_INVALID;
+}
+
 int qpbk_collide(qpb_ctx *c, double dt, int xmode) {
     const auto &cf = c->cfg;
     const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
@@ -502,6 +600,8 @@ int qpbk_collide(qpb_ctx *c, double dt, int xmode) {
         U.K4 = reinterpret_cast<const double4 *>(c->d_K4);
         U.rho = c->d_K4 + (size_t)4 * U.nep * U.nep;
         U.dt = dt;
+        U.mode = 0;
+        U.gth = nullptr;
         if (c->gemm_ready) return launch_gemm(c, dt);
         int rc = launch_uniform<32, 512>(c, U);
         if (rc <= 0) return rc;

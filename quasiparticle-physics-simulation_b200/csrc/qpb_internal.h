@@ -149,6 +149,8 @@ struct qpb_ctx {
     double *x_peer[8] = {nullptr};
     int32_t *d_xdense = nullptr;      // [ncell]
     std::vector<int16_t> x_route;     // [ne] owner << 10 | row
+    double *d_euler = nullptr;        // tables + operands of the fixed-bath Euler forms (qpbk_euler_step)
+    size_t euler_bytes = 0;
     // generation array
     double *d_gen = nullptr;          // [ne][ncell]
     // reductions
@@ -177,6 +179,7 @@ void qpbk_free_slot(DiffSlot &s);
 
 int qpbk_collide(qpb_ctx *c, double dt, int xmode = 0);
 int qpbk_collision_setup(qpb_ctx *c);
+int qpbk_euler_step(qpb_ctx *c, int kind, const double *K, const double *vec, double dt);
 int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin = false);   // host phonon state [nw][ncell] ([nw] when per_bin) or null
 int qpbk_broadcast_phonons(qpb_ctx *c, const double *d_bins);  // P[o][q] = bins[o]
 

@@ -85,6 +85,37 @@ def scattering_kernel_base(E: np.ndarray, gap: float, tau_0: float, T_c: float) 
     return out
 
 
+def recombination_kernel(E: np.ndarray, gap: float, tau_0: float, T_c: float, bath_temperature: float) -> np.ndarray:
+    """Bath-dressed K^r (solver.py:493-516): base kernel x (1 + n_BE(E_i + E_j)) at the phonon bath temperature."""
+    kT = KB_UEV_PER_K * bath_temperature
+    e_sum = E[:, None] + E[None, :]
+    if kT > 0:
+        n_p = 1.0 / (np.exp(np.minimum(e_sum / kT, 500.0)) - 1.0) + 1.0
+    else:
+        n_p = np.ones_like(e_sum, dtype=float)
+    return recombination_kernel_base(E, gap, tau_0, T_c) * n_p
+
+
+def scattering_kernel(E: np.ndarray, gap: float, tau_0: float, T_c: float, bath_temperature: float) -> np.ndarray:
+    """Bath-dressed K^s (solver.py:519-548): emission 1 + n_BE, absorption n_BE, zero diagonal."""
+    kT = KB_UEV_PER_K * bath_temperature
+    e_diff = E[:, None] - E[None, :]
+    if kT > 0:
+        arg = np.minimum(np.abs(e_diff) / kT, 500.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            n_be = 1.0 / (np.exp(arg) - 1.0)
+        n_p = np.where(e_diff > 0, 1.0 + n_be, n_be)
+    else:
+        n_p = np.where(e_diff > 0, 1.0, 0.0)
+    np.fill_diagonal(n_p, 0.0)
+    return scattering_kernel_base(E, gap, tau_0, T_c) * n_p
+
+
+def thermal_generation(n_eq: np.ndarray, K_r: np.ndarray, dE: float) -> np.ndarray:
+    """G_therm = 2 n_eq dE (K_r n_eq): the generation that balances recombination at n_eq (precompute.py:240)."""
+    return 2.0 * n_eq * dE * (K_r @ n_eq)
+
+
 def phonon_frequency_map(E: np.ndarray):
     """omega grid = unique(round(|Ei-Ej| U Ei+Ej, 12)); index maps into it; sign(Ei-Ej)."""
     E = np.asarray(E, dtype=float)

@@ -545,3 +545,36 @@ def apply_collision_step_fischer_catelani_nonuniform(state, phonon_state, K_r0_a
     Ks = None if K_s0_all is None else np.stack([np.asarray(K_s0_all[p], dtype=float) for p in first])
     _collide_in_place(state, phonon_state, Kr, Ks, rho_tab, gap_id, omega_idx_diff, omega_idx_sum, diff_sign, dE, dt,
                       enable_recombination, enable_scattering, update_phonons, device)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# fixed-bath forward-Euler collision forms (solver.py:551-605)
+# --------------------------------------------------------------------------------------------------------------
+def _euler_in_place(state, kind, K, vec, dE, dt, device):
+    state_arr = np.asarray(state)
+    if state_arr.ndim != 2:
+        raise ValueError("state must have shape (num_energy_bins, num_spatial_pts).")
+    ne, n = state_arr.shape
+    K = np.asarray(K, dtype=float)
+    vec = np.asarray(vec, dtype=float)
+    if K.shape != (ne, ne) or vec.shape != (ne,):
+        raise ValueError("kernel / per-bin vector shapes do not match the state.")
+    with capi.Context(ny=1, nx=n, ne=ne, nw=0, ncell=n, flags=0, dx=1.0, dE=float(dE), device=device) as ctx:
+        ctx.upload_geometry(np.ones((1, n), dtype=np.uint8))
+        ctx.set_state(state_arr)
+        ctx.euler_step(kind, K, vec, dt)
+        new_state, _ = ctx.get_state(want_phonons=False)
+    state[...] = new_state
+
+
+def apply_scattering_step(state, K_s, rho_bins, dE, dt, *, device=0):
+    """GPU version of solver.py:551-581: one forward-Euler step of quasiparticle-phonon scattering against a fixed
+    bath, in place.  scat_in = dE rho (1-f) (K_s^T n), scat_out = n dE (K_s rho (1-f)): the K(E,E') contraction over all
+    cells as one FP64 tensor-core GEMM (64 bins and more) or a fused GEMV."""
+    _euler_in_place(state, 1, K_s, rho_bins, dE, dt, device)
+
+
+def apply_recombination_step(state, K_r, G_therm, dE, dt, *, device=0):
+    """GPU version of solver.py:584-605: one forward-Euler step of recombination + thermal generation, in place:
+    n += dt (G_therm - 2 n dE (K_r n)), the bilinear form n.R.n per cell."""
+    _euler_in_place(state, 2, K_r, G_therm, dE, dt, device)

@@ -283,3 +283,26 @@ def test_frozen_uniform_phonons_tensor_core_gemm(flags, shape, monkeypatch):
     helpers.assert_close(outs["gemm"].T, outs["gemv"].T, "GEMM vs fused GEMV", rtol=1e-11)
     helpers.assert_close(outs["gemm"].T, outs["struct"].T, "GEMM vs structured kernel", rtol=1e-11)
     assert not np.array_equal(outs["gemm"], state0)
+
+
+@pytest.mark.parametrize("tag", ["small", "gemm", "wide"])
+@pytest.mark.parametrize("no_gemm", [False, True], ids=["auto", "gemv"])
+def test_euler_fixed_bath_forms_match_reference_fixture(tag, no_gemm, monkeypatch):
+    """apply_scattering_step / apply_recombination_step (solver.py:551-605) against the reference's own outputs
+    (tests/golden/euler_steps.npz): 24 bins (fused GEMV), 72 and 130 bins (tensor-core GEMM; GEMV when forced)."""
+    if no_gemm:
+        monkeypatch.setenv("QPB_NO_GEMM", "1")
+    g = helpers.load_golden("euler_steps")
+    dE, dt = float(g[f"{tag}_dE"]), float(g[f"{tag}_dt"])
+    Ks, Kr, rho, gth = g[f"{tag}_Ks"], g[f"{tag}_Kr"], g[f"{tag}_rho"], g[f"{tag}_G_therm"]
+    s = g[f"{tag}_state"].copy()
+    Q.apply_scattering_step(s, Ks, rho, dE, dt)
+    helpers.assert_close(s, g[f"{tag}_after_scattering"], "scattering step", rtol=1e-12)
+    s = g[f"{tag}_state"].copy()
+    Q.apply_recombination_step(s, Kr, gth, dE, dt)
+    helpers.assert_close(s, g[f"{tag}_after_recombination"], "recombination step", rtol=1e-12)
+    s = g[f"{tag}_state"].copy()
+    for _ in range(3):
+        Q.apply_scattering_step(s, Ks, rho, dE, dt)
+        Q.apply_recombination_step(s, Kr, gth, dE, dt)
+    helpers.assert_close(s, g[f"{tag}_after_3_pairs"], "three scattering + recombination pairs", rtol=1e-11)

@@ -5,6 +5,7 @@ import pytest
 
 import cases
 import helpers
+import qpsim_b200 as Q
 from oracle import qp_oracle as O
 from refimport import load_reference
 
@@ -68,3 +69,33 @@ def test_oracle_against_live_reference():
         O.collide(s2, p2, Kr, Ks, rho, idd, ids, sg, dE, 0.4, recomb=rec, scat=sc)
         helpers.assert_close(s2.T, s1.T, "n", rtol=1e-13)
         helpers.assert_close(p2.T, p1.T, "n_ph", rtol=1e-13)
+
+
+@pytest.mark.parametrize("tag", ["small", "gemm", "wide"])
+def test_oracle_euler_forms_match_reference_fixture(tag):
+    """Fixed-bath Euler forms and the bath-dressed kernels against tests/golden/euler_steps.npz (generated from the
+    unmodified reference by tests/golden/make_golden_euler.py)."""
+    g = helpers.load_golden("euler_steps")
+    ne, ncell, fmax, tbath = g[f"{tag}_params"]
+    E, dE = O.energy_grid(cases.GAP, 1.0, float(fmax), int(ne))
+    np.testing.assert_array_equal(E, g[f"{tag}_E"])
+    Kr = O.kr_dressed(E, cases.GAP, cases.TAU, cases.TC, float(tbath))
+    Ks = O.ks_dressed(E, cases.GAP, cases.TAU, cases.TC, float(tbath))
+    np.testing.assert_allclose(Kr, g[f"{tag}_Kr"], rtol=1e-14)
+    np.testing.assert_allclose(Ks, g[f"{tag}_Ks"], rtol=1e-14, atol=0)
+    np.testing.assert_allclose(Q.physics.recombination_kernel(E, cases.GAP, cases.TAU, cases.TC, float(tbath)), g[f"{tag}_Kr"], rtol=1e-14)
+    np.testing.assert_allclose(Q.physics.scattering_kernel(E, cases.GAP, cases.TAU, cases.TC, float(tbath)), g[f"{tag}_Ks"], rtol=1e-14)
+    n_eq = O.thermal_weights(E, cases.GAP, float(tbath), cases.GAMMA)
+    np.testing.assert_allclose(Q.physics.thermal_generation(n_eq, g[f"{tag}_Kr"], dE), g[f"{tag}_G_therm"], rtol=1e-14)
+    dt = float(g[f"{tag}_dt"])
+    s = g[f"{tag}_state"].copy()
+    O.euler_scattering_step(s, g[f"{tag}_Ks"], g[f"{tag}_rho"], dE, dt)
+    np.testing.assert_allclose(s, g[f"{tag}_after_scattering"], rtol=1e-13, atol=0)
+    s = g[f"{tag}_state"].copy()
+    O.euler_recombination_step(s, g[f"{tag}_Kr"], g[f"{tag}_G_therm"], dE, dt)
+    np.testing.assert_allclose(s, g[f"{tag}_after_recombination"], rtol=1e-13, atol=0)
+    s = g[f"{tag}_state"].copy()
+    for _ in range(3):
+        O.euler_scattering_step(s, g[f"{tag}_Ks"], g[f"{tag}_rho"], dE, dt)
+        O.euler_recombination_step(s, g[f"{tag}_Kr"], g[f"{tag}_G_therm"], dE, dt)
+    np.testing.assert_allclose(s, g[f"{tag}_after_3_pairs"], rtol=1e-12, atol=0)
