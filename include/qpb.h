@@ -135,6 +135,11 @@ int qpb_get_state(qpb_ctx *ctx, double *n, double *n_ph);
 /* same as qpb_set_state for the reference's default initial phonon state n_ph_eq[:, None] * ones((1, N))
  * (solver.py:1183-1185): one occupation per phonon bin [Nw], broadcast over the cells on the device */
 int qpb_set_state_uniform_phonons(qpb_ctx *ctx, const double *n, const double *n_ph_bins);
+/* the reference's default initial quasiparticle state  state[i] = spatial_values * weights[i]  (solver.py:1281-1283)
+ * formed on the device from its two factors (weights: [NE], spatial: [N]; one fp64 multiply per element, the same
+ * rounding as the host product), together with the default phonon state of qpb_set_state_uniform_phonons
+ * (n_ph_bins: [Nw], NULL when nw == 0): the call uploads NE + N + Nw doubles instead of NE*N */
+int qpb_set_state_separable(qpb_ctx *ctx, const double *weights, const double *spatial, const double *n_ph_bins);
 /* energy-integrated field  sum_i n[i][cell]*dE  (solver.py:1480), [N] */
 int qpb_get_integrated(qpb_ctx *ctx, double *out);
 /* the NE stored energy frames of one snapshot, dense [NE][ny][nx] with NaN outside the mask: what the reference

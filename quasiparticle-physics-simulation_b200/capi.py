@@ -79,7 +79,7 @@ EXPORTED = [
     "qpb_pauli", "qpb_get_diag", "qpb_synchronize", "qpb_enable_timers", "qpb_reset_timers", "qpb_get_timer",
     "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
     "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons", "qpb_pauli_record", "qpb_pauli_fetch", "qpb_set_exchange", "qpb_collide_exchange",
-    "qpb_ipc_export", "qpb_ipc_open", "qpb_ipc_close", "qpb_euler_step",
+    "qpb_ipc_export", "qpb_ipc_open", "qpb_ipc_close", "qpb_euler_step", "qpb_set_state_separable",
 ]
 
 
@@ -99,22 +99,43 @@ def library_is_current() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every CUDA source of the package for sm_100a into lib/libqpb.so (cross-compiles without a GPU)."""
+    """Compile every CUDA source of the package for sm_100a into lib/libqpb.so (cross-compiles without a GPU).
+    The translation units are compiled in parallel into lib/obj/ and only when they (or a header) changed."""
     if not force and library_is_current():
         return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [
+    from concurrent.futures import ThreadPoolExecutor
+
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    headers = [os.path.join(CSRC_DIR, f) for f in os.listdir(CSRC_DIR) if f.endswith((".h", ".cuh"))]
+    headers.append(os.path.join(INCLUDE_DIR, "qpb.h"))
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    base = [
         _nvcc(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-        "-Xcompiler", "-fPIC", "-shared", "-I", INCLUDE_DIR, "-I", CSRC_DIR,
+        "-Xcompiler", "-fPIC", "-I", INCLUDE_DIR, "-I", CSRC_DIR,
     ]
     if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC_DIR, s) for s in SOURCES] + ["-o", LIB_PATH]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        base += ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        path = os.path.join(CSRC_DIR, src)
+        if (not force and not verbose and os.path.exists(obj)
+                and os.path.getmtime(obj) >= max(os.path.getmtime(path), newest_header)):
+            return obj, ""
+        res = subprocess.run(base + ["-c", path, "-o", obj], capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        results = list(pool.map(compile_one, SOURCES))
     if verbose:
-        print(res.stderr)
+        print("".join(log for _, log in results))
+    res = subprocess.run([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"]
+                         + [obj for obj, _ in results] + ["-o", LIB_PATH], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 
@@ -147,6 +168,7 @@ def load_library():
     lib.qpb_set_state.argtypes = [vp, vp, vp]
     lib.qpb_get_state.argtypes = [vp, vp, vp]
     lib.qpb_set_state_uniform_phonons.argtypes = [vp, vp, vp]
+    lib.qpb_set_state_separable.argtypes = [vp, vp, vp, vp]
     lib.qpb_get_integrated.argtypes = [vp, vp]
     lib.qpb_get_frames.argtypes = [vp, vp]
     lib.qpb_trim_cache.argtypes = []
@@ -268,6 +290,14 @@ class Context:
         a = _f64(n, (self.ne, self.ncell))
         p = None if self.nw == 0 else _f64(n_ph_bins, (self.nw,))
         self._check(self.lib.qpb_set_state_uniform_phonons(self.handle, _ptr(a), _ptr(p)))
+
+    def set_state_separable(self, weights, spatial, n_ph_bins=None):
+        """Default initial state ``state[i] = spatial * weights[i]`` (solver.py:1281-1283) formed on the device from its
+        factors, with the bath phonon occupations broadcast over the cells (NE + N + Nw doubles uploaded)."""
+        w = _f64(weights, (self.ne,))
+        sp = _f64(spatial, (self.ncell,))
+        p = None if self.nw == 0 else _f64(n_ph_bins, (self.nw,))
+        self._check(self.lib.qpb_set_state_separable(self.handle, _ptr(w), _ptr(sp), _ptr(p)))
 
     def get_state(self, want_phonons=True, want_qp=True):
         n = np.empty((self.ne, self.ncell)) if want_qp else None

@@ -10,6 +10,7 @@
 #include <cstring>
 #include <mutex>
 #include <random>
+#include <thread>
 #include <unordered_map>
 
 static thread_local std::string g_err;
@@ -791,6 +792,75 @@ extern "C" int qpb_upload_collision(qpb_ctx *c, const double *K_r0, const double
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// ---- staged device -> host copies --------------------------------------------------------------------------
+// The caller's buffers are fresh pageable numpy arrays: a plain cudaMemcpy of a 64 MiB snapshot ran at ~5 GB/s
+// (driver-side staging plus the first-touch page faults of the destination, all on one thread).  Large downloads go
+// through two process-wide pinned chunks instead: chunk k+1 crosses PCIe while chunk k is copied out by a few host
+// threads (which also spreads the page faults).  QPB_STAGED_D2H=0 restores the plain copy.
+namespace {
+constexpr size_t kStageChunk = (size_t)8 << 20;
+std::mutex g_stage_mu;
+void *g_stage_pin[2] = {nullptr, nullptr};
+
+void host_copy_parallel(char *dst, const char *src, size_t bytes) {
+    const int nthr = 4;
+    const size_t per = ((bytes / nthr) + 4095) & ~(size_t)4095;
+    std::thread th[nthr - 1];
+    int started = 0;
+    for (int t = 1; t < nthr; ++t) {
+        const size_t off = per * t;
+        if (off >= bytes) break;
+        const size_t len = std::min(per, bytes - off);
+        th[started++] = std::thread([=]() { memcpy(dst + off, src + off, len); });
+    }
+    memcpy(dst, src, std::min(per, bytes));
+    for (int t = 0; t < started; ++t) th[t].join();
+}
+}  // namespace
+
+// copy `bytes` from device memory to a pageable host buffer, ordered on `stream`; returns after the data has landed
+static cudaError_t d2h_staged(void *dst, const void *dsrc, size_t bytes, cudaStream_t stream) {
+    static const bool enabled = !(getenv("QPB_STAGED_D2H") && getenv("QPB_STAGED_D2H")[0] == '0');
+    if (!enabled || bytes < 2 * kStageChunk) {
+        cudaError_t e = cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, stream);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(stream);
+    }
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    if (!g_stage_pin[0]) {
+        for (int b = 0; b < 2; ++b) {
+            cudaError_t e = cudaHostAlloc(&g_stage_pin[b], kStageChunk, cudaHostAllocPortable);
+            if (e != cudaSuccess) {
+                g_stage_pin[0] = nullptr;
+                return e;
+            }
+        }
+    }
+    cudaEvent_t ev[2];   // events belong to the current device: made per call, the pinned chunks are portable
+    for (int b = 0; b < 2; ++b) {
+        cudaError_t e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t rc = cudaSuccess;
+    const size_t nchunk = (bytes + kStageChunk - 1) / kStageChunk;
+    for (size_t k = 0; k <= nchunk && rc == cudaSuccess; ++k) {
+        if (k < nchunk) {   // chunk k-2, the previous user of this pinned buffer, was copied out an iteration ago
+            const size_t off = k * kStageChunk, len = std::min(kStageChunk, bytes - off);
+            rc = cudaMemcpyAsync(g_stage_pin[k & 1], (const char *)dsrc + off, len, cudaMemcpyDeviceToHost, stream);
+            if (rc == cudaSuccess) rc = cudaEventRecord(ev[k & 1], stream);
+            if (rc != cudaSuccess) break;
+        }
+        if (k >= 1) {
+            const size_t off = (k - 1) * kStageChunk, len = std::min(kStageChunk, bytes - off);
+            rc = cudaEventSynchronize(ev[(k - 1) & 1]);
+            if (rc != cudaSuccess) break;
+            host_copy_parallel((char *)dst + off, (const char *)g_stage_pin[(k - 1) & 1], len);
+        }
+    }
+    if (rc != cudaSuccess) cudaStreamSynchronize(stream);   // nothing may still target the pinned chunks
+    for (int b = 0; b < 2; ++b) cudaEventDestroy(ev[b]);
+    return rc;
+}
+
 extern "C" int qpb_set_state(qpb_ctx *c, const double *n, const double *n_ph) {
     QPB_ENTER(c);
     if (!c->have_geom || !n) {
@@ -839,18 +909,51 @@ extern "C" int qpb_set_state_uniform_phonons(qpb_ctx *c, const double *n, const 
     return QPB_OK;
 }
 
+extern "C" int qpb_set_state_separable(qpb_ctx *c, const double *weights, const double *spatial,
+                                       const double *n_ph_bins) {
+    QPB_ENTER(c);
+    const auto &cf = c->cfg;
+    if (!c->have_geom || !weights || !spatial || (cf.nw > 0 && !n_ph_bins)) {
+        qpb_set_error("qpb_set_state_separable: upload the geometry first and pass weights, spatial values and "
+                      "(with collisions) the phonon occupations");
+        return QPB_E_INVALID;
+    }
+    // the factors ride in the front of the work array T1 (free between steps): [weights | spatial | phonon bins];
+    // tiny grids (a 1 x 1 mask with one bin) take a block of their own
+    const size_t nfac = (size_t)cf.ne + cf.ncell + cf.nw;
+    double *d_own = nullptr;
+    if (nfac > (size_t)cf.ne * c->ncd) QPB_ALLOC(d_own, nfac);
+    struct Release {
+        double *p;
+        ~Release() { dev_free(p); }
+    } release{d_own};
+    double *d_w = d_own ? d_own : c->d_T1, *d_sp = d_w + cf.ne, *d_bins = d_sp + cf.ncell;
+    QPB_CUDA(cudaMemcpyAsync(d_w, weights, sizeof(double) * cf.ne, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaMemcpyAsync(d_sp, spatial, sizeof(double) * cf.ncell, cudaMemcpyHostToDevice, c->stream));
+    int rc = qpbk_outer_state(c, d_w, d_sp);
+    if (rc != QPB_OK) return rc;
+    if (cf.nw > 0) {
+        QPB_CUDA(cudaMemcpyAsync(d_bins, n_ph_bins, sizeof(double) * cf.nw, cudaMemcpyHostToDevice, c->stream));
+        rc = qpbk_broadcast_phonons(c, d_bins);
+        QPB_CUDA(cudaStreamSynchronize(c->stream));
+        if (rc != QPB_OK) return rc;
+        rc = qpbk_uniform_setup(c, n_ph_bins, true);
+        QPB_CUDA(cudaDeviceSynchronize());
+        return rc;
+    }
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    return QPB_OK;
+}
+
 extern "C" int qpb_get_state(qpb_ctx *c, double *n, double *n_ph) {
     QPB_ENTER(c);
     const auto &cf = c->cfg;
     if (n) {
         int rc = qpbk_gather_state(c, c->d_T1);
         if (rc != QPB_OK) return rc;
-        QPB_CUDA(cudaMemcpyAsync(n, c->d_T1, sizeof(double) * (size_t)cf.ne * cf.ncell, cudaMemcpyDeviceToHost,
-                                 c->stream));
+        QPB_CUDA(d2h_staged(n, c->d_T1, sizeof(double) * (size_t)cf.ne * cf.ncell, c->stream));
     }
-    if (n_ph && cf.nw > 0)
-        QPB_CUDA(cudaMemcpyAsync(n_ph, c->d_P, sizeof(double) * (size_t)cf.nw * cf.ncell, cudaMemcpyDeviceToHost,
-                                 c->stream));
+    if (n_ph && cf.nw > 0) QPB_CUDA(d2h_staged(n_ph, c->d_P, sizeof(double) * (size_t)cf.nw * cf.ncell, c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));
     return QPB_OK;
 }
@@ -876,8 +979,7 @@ extern "C" int qpb_get_frames(qpb_ctx *c, double *frames) {
     }
     int rc = qpbk_frames(c, c->d_T1);   // T1 is free between solves (it also stages qpb_get_state)
     if (rc != QPB_OK) return rc;
-    QPB_CUDA(cudaMemcpyAsync(frames, c->d_T1, sizeof(double) * (size_t)c->cfg.ne * c->ncd, cudaMemcpyDeviceToHost,
-                             c->stream));
+    QPB_CUDA(d2h_staged(frames, c->d_T1, sizeof(double) * (size_t)c->cfg.ne * c->ncd, c->stream));
     // no NaN may survive in a work array: 0 * NaN would leak into cells outside the mask
     QPB_CUDA(cudaMemsetAsync(c->d_T1, 0, sizeof(double) * (size_t)c->cfg.ne * c->ncd, c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));

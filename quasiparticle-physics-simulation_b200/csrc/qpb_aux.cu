@@ -19,6 +19,19 @@ __global__ void k_scatter_state(int ne, int ncell, int ncd, const double *__rest
     }
 }
 
+// state[i] = spatial_values * weights[i]  (solver.py:1281-1283), written straight into the dense layout
+__global__ void k_outer_state(int ne, int ncell, int ncd, const double *__restrict__ weights,
+                              const double *__restrict__ spatial, double *__restrict__ dense,
+                              const int32_t *__restrict__ c2d) {
+    const long long total = (long long)ne * ncell;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(g / ncell);
+        const int q = (int)(g - (long long)i * ncell);
+        dense[(long long)i * ncd + c2d[q]] = spatial[q] * weights[i];
+    }
+}
+
 __global__ void k_gather_state(int ne, int ncell, int ncd, double *__restrict__ compact,
                                const double *__restrict__ dense, const int32_t *__restrict__ c2d) {
     const long long total = (long long)ne * ncell;
@@ -151,6 +164,16 @@ int qpbk_scatter_state(qpb_ctx *c, const double *d_compact) {
     const long long total = (long long)cf.ne * cf.ncell;
     k_scatter_state<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, d_compact, c->d_S,
                                                                           c->d_cell2dense);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int qpbk_outer_state(qpb_ctx *c, const double *d_weights, const double *d_spatial) {
+    const auto &cf = c->cfg;
+    const long long total = (long long)cf.ne * cf.ncell;
+    k_outer_state<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, d_weights, d_spatial,
+                                                                        c->d_S, c->d_cell2dense);
     c->diag.kernel_launches++;
     QPB_CHECK_LAUNCH();
     return QPB_OK;

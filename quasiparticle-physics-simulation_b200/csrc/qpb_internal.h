@@ -187,6 +187,7 @@ int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_a
 int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out);
 int qpbk_integrate(qpb_ctx *c);
 int qpbk_scatter_state(qpb_ctx *c, const double *d_compact);  // [ne][ncell] -> dense
+int qpbk_outer_state(qpb_ctx *c, const double *d_weights, const double *d_spatial);  // dense S[i][cell] = spatial[cell] * weights[i]
 int qpbk_gather_state(qpb_ctx *c, double *d_compact);
 int qpbk_frames(qpb_ctx *c, double *d_out);                   // dense NaN-padded frames [ne][ncd]
 

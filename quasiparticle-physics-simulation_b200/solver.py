@@ -280,8 +280,9 @@ def run_2d_crank_nicolson(
     if has_pre:
         D_array = np.asarray(precomputed["D_array"], dtype=float)
     else:
-        D_bins = diffusion_coefficient * np.sqrt(np.maximum(0.0, 1.0 - (gap / E_bins) ** 2))
-        D_array = D_bins[:, None] * np.ones((1, n))
+        # the reference replicates D(E) over the cells (solver.py:1141-1143) and then only reads column 0
+        # (solver.py:1167); the device takes the NE values
+        D_array = diffusion_coefficient * np.sqrt(np.maximum(0.0, 1.0 - (gap / E_bins) ** 2))
     collisions = bool(enable_recombination or enable_scattering)
 
     omega_bins, idx_diff, idx_sum, diff_sign = physics.phonon_frequency_map(E_bins)
@@ -345,9 +346,9 @@ def run_2d_crank_nicolson(
             rho0 = physics.density_of_states(E_bins, gap, dynes_gamma)
             total = np.sum(rho0) * dE
             weights = rho0 / total if total > 0 else np.ones(ne, dtype=float) / (ne * dE)
-        state = np.empty((ne, n), dtype=float)
-        for i in range(ne):
-            state[i] = spatial * weights[i]
+        # state[i] = spatial * weights[i] (solver.py:1281-1283) is formed on the device from its two factors; the
+        # (NE, N) host array is only materialised when an explicit phonon state has to travel with it
+        state = None
 
     coords = np.argwhere(mask_b)
     policy = _PauliPolicy(E_bins, coords, pauli_warn_threshold, pauli_error_threshold, enforce_pauli)
@@ -387,17 +388,23 @@ def run_2d_crank_nicolson(
         ctx.upload_collision(Kr_tab, Ks_tab, rho_tab, gap_id,
                              idx_diff if collisions else None, idx_sum if collisions else None,
                              diff_sign if collisions else None)
-        if collisions and phonon_state is None:
-            ctx.set_state_uniform_phonons(state, n_ph_eq)
+        if state is None and (phonon_state is None or not collisions):
+            ctx.set_state_separable(weights, spatial, n_ph_eq if collisions else None)
         else:
-            ctx.set_state(state, phonon_state if collisions else None)
+            if state is None:
+                state = spatial[None, :] * weights[:, None]
+            if collisions and phonon_state is None:
+                ctx.set_state_uniform_phonons(state, n_ph_eq)
+            else:
+                ctx.set_state(state, phonon_state if collisions else None)
         policy.check(ctx.pauli(), 0, 0.0)
 
         if want_ph_hist:
             if phonon_state is None:
                 phonon_state = n_ph_eq[:, None] * np.ones((1, n), dtype=float)
             snapshot_phonons(phonon_state)
-        integrated = np.sum(state, axis=0) * dE
+        # sum_i state[i] * dE (solver.py:1356), summed on the device like every later frame
+        integrated = ctx.get_integrated() if state is None else np.sum(state, axis=0) * dE
         times = [0.0]
         frames = [reconstruct_field(mask_b, integrated)]
         energy_frames = [list(ctx.get_frames())] if store_energy_frames else [None]

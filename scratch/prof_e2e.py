@@ -21,7 +21,7 @@ def wrap(name):
     def g(self, *a, **k):
         t0 = time.perf_counter(); r = f(self, *a, **k); acc[name] = acc.get(name, 0.0) + time.perf_counter() - t0; return r
     setattr(capi.Context, name, g)
-for nm in ("__init__", "close", "upload_geometry", "upload_diffusion", "prepare_diffusion", "upload_collision", "set_state", "get_state", "get_frames", "get_integrated", "advance", "pauli"):
+for nm in ("__init__", "close", "upload_geometry", "upload_diffusion", "prepare_diffusion", "upload_collision", "set_state", "set_state_separable", "set_state_uniform_phonons", "get_state", "get_frames", "get_integrated", "advance", "pauli"):
     wrap(nm)
 for rep in range(4):
     acc.clear()

@@ -306,3 +306,48 @@ def test_euler_fixed_bath_forms_match_reference_fixture(tag, no_gemm, monkeypatc
         Q.apply_scattering_step(s, Ks, rho, dE, dt)
         Q.apply_recombination_step(s, Kr, gth, dE, dt)
     helpers.assert_close(s, g[f"{tag}_after_3_pairs"], "three scattering + recombination pairs", rtol=1e-11)
+
+
+def test_separable_state_upload_is_bit_exact():
+    """qpb_set_state_separable forms state[i] = spatial * weights[i] (solver.py:1281-1283) and the bath phonon state on
+    the device: same bits as uploading the host products."""
+    from qpsim_b200 import capi
+
+    rng = np.random.default_rng(5)
+    mask = cases.meander_mask(40, 48, pad=4, pitch=12, gap_len=12)
+    n, ne, nw = int(mask.sum()), 7, 19
+    weights, spatial, bins = rng.random(ne), rng.random(n) * 1e-3, rng.random(nw)
+    out = []
+    for separable in (False, True):
+        with capi.Context(ny=40, nx=48, ne=ne, nw=nw, ncell=n, flags=capi.F_SCATTERING, dx=1.0, dE=2.0) as ctx:
+            ctx.upload_geometry(mask)
+            if separable:
+                ctx.set_state_separable(weights, spatial, bins)
+            else:
+                ctx.set_state(spatial[None, :] * weights[:, None], bins[:, None] * np.ones((1, n)))
+            out.append(ctx.get_state())
+    assert np.array_equal(out[0][0], out[1][0])
+    assert np.array_equal(out[0][1], out[1][1])
+    assert np.array_equal(out[1][0], spatial[None, :] * weights[:, None])
+
+
+@pytest.mark.parametrize("staged", ["0", "1"])
+def test_large_downloads_staged_and_plain_agree(staged, monkeypatch):
+    """qpb_get_frames / qpb_get_state above 16 MiB go through the pinned two-chunk pipeline (uneven last chunk)."""
+    from qpsim_b200 import capi
+
+    monkeypatch.setenv("QPB_STAGED_D2H", staged)
+    rng = np.random.default_rng(6)
+    ny, nx, ne = 250, 272, 33          # 17.1 MiB of frames: two full chunks and a short one
+    mask = np.ones((ny, nx), dtype=bool)
+    mask[:3] = False
+    n = int(mask.sum())
+    state = rng.random((ne, n))
+    with capi.Context(ny=ny, nx=nx, ne=ne, nw=0, ncell=n, flags=0, dx=1.0, dE=1.0) as ctx:
+        ctx.upload_geometry(mask)
+        ctx.set_state(state)
+        frames = ctx.get_frames()
+        back = ctx.get_state(want_phonons=False)[0]
+    assert np.array_equal(back, state)
+    assert np.all(np.isnan(frames[:, ~mask]))
+    assert np.array_equal(frames[:, mask], state)
