@@ -368,11 +368,13 @@ def run_single_gpu(args):
         t0 = time.perf_counter()
         times, frames, mass, _, eframes, _ = Q.run_2d_crank_nicolson(**kw)
         t_e2e = time.perf_counter() - t0
-    h2d = 8 * (ne * n + nw * n) + ncd * (1 + 3 * 8) + 8 * 2 * ne * ne
+    # uploads of one call: mask + three boundary arrays, the two base kernels, and the factors of the default initial
+    # state (energy weights, spatial field, bath phonon occupations: the (NE, N) product is formed on the device)
+    h2d = 8 * (ne + n + nw) + ncd * (1 + 3 * 8) + 8 * 2 * ne * ne
     d2h = 8 * (2 * ne * ncd + n)   # t=0 and final energy frames (dense, NaN padded) + integrated field
     e2e = {"value": n * ne * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
            "seconds": t_e2e, "note": "one run_2d_crank_nicolson call (context creation, geometry compile, uploads, "
-           f"{K} steps, state + frame download), host numpy buffers in and out"}
+           f"{K} steps, download of the t=0 and final energy frames), host numpy buffers in and out"}
     cpu = cpu_baseline(w, tabs)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W,
