@@ -55,17 +55,16 @@ __global__ void k_frames(long long total, int ncd, const double *__restrict__ S,
 }
 
 // state += scale * g   (g: one rate for every bin and cell, or a host-evaluated array [ne][ncell])
+// grid.y = energy bin: no per-element index division, the dense index of a cell is loaded once per thread and bin
 __global__ void k_add_generation(int ne, int ncell, int ncd, double *__restrict__ S,
                                  const int32_t *__restrict__ c2d, double scale, double rate,
                                  const double *__restrict__ arr) {
-    const long long total = (long long)ne * ncell;
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(g / ncell);
-        const int q = (int)(g - (long long)i * ncell);
-        const double v = arr ? arr[g] : rate;
-        S[(long long)i * ncd + c2d[q]] += scale * v;
-    }
+    const int i = blockIdx.y;
+    double *row = S + (long long)i * ncd;
+    const double *g = arr ? arr + (long long)i * ncell : nullptr;
+    const double add = scale * rate;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += gridDim.x * blockDim.x)
+        row[c2d[q]] += g ? scale * g[q] : add;
 }
 
 // integrated[q] = (sum_i n[i][q]) * dE, bins added in order like np.sum(state, axis=0)
@@ -119,27 +118,41 @@ __device__ void pauli_block_reduce(PauliPart &p) {
     }
 }
 
+// grid.y = energy bin, four cells per thread and pass (independent loads); flattened index g = bin*ncell + cell grows
+// along a thread's loop, so ">" keeps the first maximum of the np.argmax order (solver.py:967-996)
 __global__ void k_pauli_stage1(int ne, int ncell, int ncd, const double *__restrict__ S,
                                const int32_t *__restrict__ c2d, const double *__restrict__ rho,
                                const int32_t *__restrict__ gapid, double floor_, PauliPart *__restrict__ part) {
     PauliPart p{-DBL_MAX, LLONG_MAX, LLONG_MAX};
-    const long long total = (long long)ne * ncell;
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const int i = (int)(g / ncell);
-        const int q = (int)(g - (long long)i * ncell);
-        const double n = S[(long long)i * ncd + c2d[q]];
-        const double r = rho[(gapid ? gapid[q] : 0) * ne + i];
-        const bool ok = r > 1e-30;
-        const double f = ok ? n / fmax(r, 1e-30) : 0.0;
-        if (f > p.val) {  // indices grow along the loop, so ">" keeps the first maximum
-            p.val = f;
-            p.idx = g;
+    const int i = blockIdx.y;
+    const double *row = S + (long long)i * ncd;
+    const long long g0 = (long long)i * ncell;
+    const double r0 = rho[i];
+    constexpr int U = 4;
+    const int stride = gridDim.x * blockDim.x;
+    for (int qb = blockIdx.x * blockDim.x + threadIdx.x; qb < ncell; qb += U * stride) {
+        double n[U], r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = qb + u * stride;
+            n[u] = q < ncell ? row[c2d[q]] : 0.0;
+            r[u] = (gapid && q < ncell) ? rho[gapid[q] * ne + i] : r0;
         }
-        if (!ok && n > floor_ && g < p.forb) p.forb = g;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int q = qb + u * stride;
+            if (q >= ncell) break;
+            const bool ok = r[u] > 1e-30;
+            const double f = ok ? n[u] / fmax(r[u], 1e-30) : 0.0;
+            if (f > p.val) {
+                p.val = f;
+                p.idx = g0 + q;
+            }
+            if (!ok && n[u] > floor_ && g0 + q < p.forb) p.forb = g0 + q;
+        }
     }
     pauli_block_reduce(p);
-    if (threadIdx.x == 0) part[blockIdx.x] = p;
+    if (threadIdx.x == 0) part[blockIdx.y * gridDim.x + blockIdx.x] = p;
 }
 
 __global__ void k_pauli_stage2(int nparts, const PauliPart *__restrict__ part, qpb_pauli_rec *__restrict__ out) {
@@ -213,9 +226,9 @@ int qpbk_frames(qpb_ctx *c, double *d_out) {
 
 int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_array) {
     const auto &cf = c->cfg;
-    const long long total = (long long)cf.ne * cf.ncell;
-    k_add_generation<<<grid_for(total, 256, 148 * 16), 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S,
-                                                                           c->d_cell2dense, scale, rate, d_array);
+    const dim3 grid((unsigned)std::max(1, std::min((cf.ncell + 255) / 256, 64)), (unsigned)cf.ne);
+    k_add_generation<<<grid, 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S, c->d_cell2dense, scale, rate,
+                                                  d_array);
     c->diag.kernel_launches++;
     QPB_CHECK_LAUNCH();
     return QPB_OK;
@@ -232,16 +245,18 @@ int qpbk_integrate(qpb_ctx *c) {
 
 int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out) {
     const auto &cf = c->cfg;
-    const long long total = (long long)cf.ne * cf.ncell;
-    const int blocks = grid_for(total, 256, 148 * 8);
+    // grid.x blocks of 256 threads x 4 cells per bin, about 8 CTAs per SM in total
+    const int gx = std::max(1, std::min((cf.ncell + 1023) / 1024, std::max(1, 148 * 8 / cf.ne)));
+    const int blocks = gx * cf.ne;
     if (!c->d_pauli_part || c->pauli_blocks < blocks) {
         if (c->d_pauli_part) qpb_dev_free(c->d_pauli_part);
         c->d_pauli_part = nullptr;
-        c->pauli_blocks = 148 * 8;
+        c->pauli_blocks = blocks;
         QPB_CUDA(qpb_dev_malloc(&c->d_pauli_part, sizeof(PauliPart) * c->pauli_blocks));
     }
-    k_pauli_stage1<<<blocks, 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S, c->d_cell2dense, c->d_rho,
-                                                  c->d_gapid, cf.pauli_floor, (PauliPart *)c->d_pauli_part);
+    k_pauli_stage1<<<dim3((unsigned)gx, (unsigned)cf.ne), 256, 0, c->stream>>>(
+        cf.ne, cf.ncell, c->ncd, c->d_S, c->d_cell2dense, c->d_rho, c->d_gapid, cf.pauli_floor,
+        (PauliPart *)c->d_pauli_part);
     QPB_CHECK_LAUNCH();
     k_pauli_stage2<<<1, 256, 0, c->stream>>>(blocks, (const PauliPart *)c->d_pauli_part, d_out);
     QPB_CHECK_LAUNCH();

@@ -59,18 +59,16 @@ __global__ void k_build_rhs(int ne, int ny, int nx, const double *__restrict__ S
                             const double *__restrict__ ex, const double *__restrict__ ey,
                             const double *__restrict__ gbx, const double *__restrict__ gby) {
     const int ncd = ny * nx;
-    const long long total = (long long)ne * ncd;
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const int bin = (int)(g / ncd);
-        const int c = (int)(g - (long long)bin * ncd);
+    const int bin = blockIdx.y;   // grid.y = energy bin: no per-element index division
+    const long long off = (long long)bin * ncd;
+    const double *u = S + off;
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < ncd; c += gridDim.x * blockDim.x) {
+        const long long g = off + c;
         const unsigned fl = flags[c];
         if (!(fl & QPB_IN)) {
             B[g] = 0.0;
             continue;
         }
-        const double *u = S + (long long)bin * ncd;
-        const long long off = (long long)bin * ncd;
         const double a = VARD ? 0.0 : a_bin[bin];
         Faces f = load_faces<VARD>(c, nx, fl, a, bcx, bcy, VARD ? ex + off : nullptr, VARD ? ey + off : nullptr,
                                    VARD ? gbx + off : nullptr, VARD ? gby + off : nullptr);
@@ -197,9 +195,8 @@ __global__ void k_sweep_generic(int ne, int ny, int nx, int dir, int mode, int i
 int qpbk_build_rhs(qpb_ctx *c, DiffSlot &s) {
     const auto &cf = c->cfg;
     const bool vard = cf.flags & QPB_F_VARIABLE_D;
-    const long long total = (long long)cf.ne * c->ncd;
     const int threads = 256;
-    const int blocks = (int)std::min<long long>(ceil_div64(total, threads), 148 * 32);
+    const dim3 blocks((unsigned)std::max(1, std::min((c->ncd + threads - 1) / threads, 256)), (unsigned)cf.ne);
     if (vard)
         k_build_rhs<true><<<blocks, threads, 0, c->stream>>>(cf.ne, cf.ny, cf.nx, c->d_S, c->d_B, c->d_flags,
                                                              c->d_bcx, c->d_bcy, s.d_a, nullptr, s.d_src, s.d_ex,
