@@ -69,6 +69,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, uint32_t sr
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// Programmatic dependent launch: the next sweep kernel of the stream may start its prologue (barrier init, geometry
+// of its block of lines) on SMs that this grid has already left; it reads nothing a predecessor wrote before the wait.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -230,9 +234,12 @@ __device__ __forceinline__ void load_bin_params(const PipeArgs &A, double *s_a, 
 // S-cell chunk q of tile row g; the chunks of a row sit in QP adjacent lanes.
 // SEG = false: whole lines per tile, separate output tiles (segment count, halo and output mode are compile-time
 // constants: the short-line kernels carry none of the segment arithmetic).
-template <int S, int QP, int NS, int NT, bool SEG>
+// FULL: the tile fits the grid exactly (every lane owns a chunk of the row, every tile row exists): the validity
+// predicates are compile-time true and none of the masking selects are generated.
+template <int S, int QP, int NS, int NT, bool SEG, bool FULL = false>
 __global__ void __launch_bounds__(NT, NT <= 128 ? 2 : 1)
 k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
+    static_assert(!(SEG && FULL), "segmented tiles are never exact fits");
     const PipeArgs &A = Ain;
     const bool inplace = SEG && A.inplace != 0, delta = SEG && A.delta != 0;
     constexpr int R = NT / QP;
@@ -258,9 +265,54 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
     double *s_a = reinterpret_cast<double *>(bars + 8);
     double *s_rho = s_a + A.ne;
     int *s_j = reinterpret_cast<int *>(s_rho + A.ne);
+    const int tpb = A.tiles_per_bin;
+    const int g = tid / QP, q = tid - g * QP;
+    const int nx = A.nx;
+    // geometry of this thread's chunk (constant while the CTA stays on one block of lines)
+    int cur_key = -1;
+    bool qok = false, inter = false;
+    int qc = 0;
+    double cx[S], cy[S];
+    unsigned flw[S / 4];
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i) flw[i] = 0;
+    int cls = 0;
+    bool rowok = false;
+    auto load_geometry = [&](int rem) {
+        const int rblk = rem / nseg, sg = rem - rblk * nseg;
+        const int y = rblk * R + g;
+        if (y * nseg + sg == cur_key) return;
+        cur_key = y * nseg + sg;
+        const int qa = sg * QI - H + q;            // chunk of the row this thread solves
+        qok = FULL || (q < QS && qa >= 0 && qa < Q);
+        inter = FULL || (qok && q >= H && q < H + QI);       // ... and stores / measures
+        qc = FULL ? q : min(max(qa, 0), Q - 1);
+        rowok = FULL || (y < A.ny && qok);
+        const int yc = min(y, A.ny - 1);
+        cls = A.cls[yc];
+        const size_t o = (size_t)yc * nx + qc * S;
+        const unsigned *pf = reinterpret_cast<const unsigned *>(A.flags + o);
+#pragma unroll
+        for (int i = 0; i < S / 4; ++i) flw[i] = (FULL || (rowok && inter)) ? pf[i] : 0u;
+        const double2 *px = reinterpret_cast<const double2 *>(A.cx + o);
+        const double2 *py = reinterpret_cast<const double2 *>(A.cy + o);
+#pragma unroll
+        for (int un = 0; un < UPC; ++un) {
+            const double2 a2 = px[un], b2 = py[un];
+            cx[2 * un] = (FULL || rowok) ? a2.x : 0.0;
+            cx[2 * un + 1] = (FULL || rowok) ? a2.y : 0.0;
+            cy[2 * un] = (FULL || rowok) ? b2.x : 0.0;
+            cy[2 * un + 1] = (FULL || rowok) ? b2.y : 0.0;
+        }
+    };
+    // Static data first (the geometry of the CTA's first tile: with a grid that is a multiple of the tiles per bin it
+    // is the geometry of all its tiles), then wait for the preceding grid of the stream: everything below reads what
+    // it wrote (convergence flags, residuals, the state).
+    pdl_launch_dependents();
+    if ((int)blockIdx.x < A.ntiles) load_geometry((int)blockIdx.x % tpb);
+    pdl_wait();
     load_bin_params<0, NT>(A, s_a, s_rho, s_j);
     __syncthreads();
-    const int tpb = A.tiles_per_bin;
     // producer cursor (thread 0 only): next tile index to load and number of loads issued
     int pt = blockIdx.x, pk = 0;
     auto produce = [&]() {
@@ -287,23 +339,12 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
 #pragma unroll 1
         for (int i = 0; i < NS - 1; ++i) produce();
     }
-    const int g = tid / QP, q = tid - g * QP;
     const int ql = min(q, QS - 1);             // chunk slot inside the tile
     const int reach = A.depth + 1;           // an inclusive scan over offsets < reach covers `depth` earlier chunks
     const int r16 = (ql * S) >> 4;             // 128-byte unit of this chunk within its tile row
     const int ubase = ((ql * S) & 15) >> 1;    // first 16-byte unit of the chunk inside that 128-byte unit
     const int r16o = r16 - ((H * S) >> 4);     // ... within the stored interior
-    const int nx = A.nx;
     int k = 0;
-    int cur_key = -1;
-    bool qok = false, inter = false;
-    int qc = 0;
-    double cx[S], cy[S];
-    unsigned flw[S / 4];
-#pragma unroll
-    for (int i = 0; i < S / 4; ++i) flw[i] = 0;
-    int cls = 0;
-    bool rowok = false;
     for (int t = blockIdx.x; t < A.ntiles; t += gridDim.x) {
         const int bin = t / tpb;
         const int jraw = s_j[bin];
@@ -313,36 +354,13 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
         const int rem = t - bin * tpb;
         const int rblk = rem / nseg, sg = rem - rblk * nseg;
         const int y0 = rblk * R;
-        const int y = y0 + g;
         // separate output tiles: every thread finished reading the stage of tile k-1 before the last named barrier of
         // that iteration, so it is refilled right away
         if (tid == 0 && !inplace) produce();
-        if (y * nseg + sg != cur_key) {   // geometry of this thread's chunk (constant while the CTA stays on one block)
-            cur_key = y * nseg + sg;
-            const int qa = sg * QI - H + q;            // chunk of the row this thread solves
-            qok = q < QS && qa >= 0 && qa < Q;
-            inter = qok && q >= H && q < H + QI;       // ... and stores / measures
-            qc = min(max(qa, 0), Q - 1);
-            rowok = y < A.ny && qok;
-            const int yc = min(y, A.ny - 1);
-            cls = A.cls[yc];
-            const size_t o = (size_t)yc * nx + qc * S;
-            const unsigned *pf = reinterpret_cast<const unsigned *>(A.flags + o);
-#pragma unroll
-            for (int i = 0; i < S / 4; ++i) flw[i] = (rowok && inter) ? pf[i] : 0u;
-            const double2 *px = reinterpret_cast<const double2 *>(A.cx + o);
-            const double2 *py = reinterpret_cast<const double2 *>(A.cy + o);
-#pragma unroll
-            for (int un = 0; un < UPC; ++un) {
-                const double2 a2 = px[un], b2 = py[un];
-                cx[2 * un] = rowok ? a2.x : 0.0;
-                cx[2 * un + 1] = rowok ? a2.y : 0.0;
-                cy[2 * un] = rowok ? b2.x : 0.0;
-                cy[2 * un + 1] = rowok ? b2.y : 0.0;
-            }
-        }
+        load_geometry(rem);   // no-op while the CTA stays on its block of lines
         const double a = s_a[bin];
         const double rho = s_rho[bin];
+        const bool qok_c = FULL ? true : qok, rowok_c = FULL ? true : rowok, inter_c = FULL ? true : inter;
         ChunkSolve<S> ch;
         double2 mR[UPC], gR[UPC];
         {   // LU factors of this chunk (L2 / L1 resident table): issued before the wait on the tile, first touched (masked)
@@ -390,8 +408,8 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
 #pragma unroll
             for (int un = 0; un < UPC; ++un) {
                 const double2 tq = pc[(ubase + un) ^ swc];
-                uc[2 * un] = qok ? tq.x : 0.0;
-                uc[2 * un + 1] = qok ? tq.y : 0.0;
+                uc[2 * un] = qok_c ? tq.x : 0.0;
+                uc[2 * un + 1] = qok_c ? tq.y : 0.0;
             }
             double ul = __shfl_up_sync(0xffffffffu, uc[S - 1], 1, QP);
             double ur = __shfl_down_sync(0xffffffffu, uc[0], 1, QP);
@@ -437,10 +455,10 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
         }
 #pragma unroll
         for (int un = 0; un < UPC; ++un) {
-            ch.m[2 * un] = rowok ? mR[un].x : 0.0;
-            ch.m[2 * un + 1] = rowok ? mR[un].y : 0.0;
-            ch.g[2 * un] = rowok ? gR[un].x : 0.0;
-            ch.g[2 * un + 1] = rowok ? gR[un].y : 0.0;
+            ch.m[2 * un] = rowok_c ? mR[un].x : 0.0;
+            ch.m[2 * un + 1] = rowok_c ? mR[un].y : 0.0;
+            ch.g[2 * un] = rowok_c ? gR[un].x : 0.0;
+            ch.g[2 * un + 1] = rowok_c ? gR[un].y : 0.0;
         }
         double Am, Bm;
         ch.forward(Am, Bm);
@@ -454,7 +472,7 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
                                : reinterpret_cast<double *>(out_base + (size_t)(k & 1) * b_bytes);
         // in place: everybody has formed its right-hand side; else: thread 0 has seen the store of tile k-2 finish reading
         cta_bar<NT>(1);
-        if (inter) {
+        if (inter_c) {
             const int rb = g * QI16 + r16o;
             double2 *dst = reinterpret_cast<double2 *>(so + (size_t)rb * 16);
             const int swb = rb & 7;
@@ -490,9 +508,10 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
 // Tile = (bin, strip of CW columns, all rows), NT = 4096/S threads.  smem stage = u strip + u* strip as
 // [npad rows][CW] (no swizzle: the CW lanes of a row read one contiguous segment).  Thread (q, c): chunk q (S rows) of
 // column c.  
-template <int S, int CW, int NS, int NT, bool SEG>
+template <int S, int CW, int NS, int NT, bool SEG, bool FULL = false>
 __global__ void __launch_bounds__(NT, NT <= 128 ? 2 : 1)
 k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
+    static_assert(!(SEG && FULL), "segmented tiles are never exact fits");
     const PipeArgs &A = Ain;
     const bool inplace = SEG && A.inplace != 0, delta = SEG && A.delta != 0;
     constexpr int NCH = NT / CW;      // chunk slots per column
@@ -518,6 +537,8 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
     double *s_a = reinterpret_cast<double *>(bars + 8);
     double *s_rho = s_a + A.ne;
     int *s_j = reinterpret_cast<int *>(s_rho + A.ne);
+    pdl_launch_dependents();
+    pdl_wait();   // everything below reads what the preceding grid wrote
     load_bin_params<1, NT>(A, s_a, s_rho, s_j);
     __syncthreads();
     const int tpb = A.tiles_per_bin;
@@ -597,7 +618,7 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
         const double rho2 = 2.0 * s_rho[bin];
         ChunkSolve<S> ch;
         load_factors(t);   // issued before the wait on the tile (a register prefetch of the next tile measured slower)
-        const bool qok_t = qok, inter_t = inter;
+        const bool qok_t = FULL ? true : qok, inter_t = FULL ? true : inter;
         if (A.prefetch && tn < A.ntiles) {   // next tile's table lines into L1 (see the x sweep); one line per table
             const size_t basen = factor_base(tn);
             prefetch_l1(A.tabm + basen);
@@ -726,17 +747,35 @@ size_t x_smem(int nt, int QP, int nx16, int ns, bool inplace) {
     return ns * (ub + bb) + (inplace ? 0 : 2 * bb) + 64;
 }
 
-template <int S, int QP, int NS, int NT, bool SEG>
+// Launch with programmatic stream serialization (see pdl_wait): consecutive sweep kernels overlap the tail of one
+// with the prologue of the next.  QPB_PIPE_PDL=0: plain stream order.
+template <class Kern, class Maps>
+int launch_pdl(Kern kern, int grid, int nt, size_t smem, qpb_ctx *c, const PipeArgs &A, const Maps &maps) {
+    const char *e = getenv("QPB_PIPE_PDL");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)nt);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+    QPB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, maps));
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+template <int S, int QP, int NS, int NT, bool SEG, bool FULL = false>
 int launch_x_seg(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
-    auto kern = k_sweep_x_pipe<S, QP, NS, NT, SEG>;
+    auto kern = k_sweep_x_pipe<S, QP, NS, NT, SEG, FULL>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    kern<<<grid, NT, x_smem(NT, QP, A.qs * S / 16, NS, A.inplace != 0) + param_smem(A.ne), c->stream>>>(A, maps);
-    QPB_CHECK_LAUNCH();
-    return QPB_OK;
+    return launch_pdl(kern, grid, NT, x_smem(NT, QP, A.qs * S / 16, NS, A.inplace != 0) + param_smem(A.ne), c, A, maps);
 }
 
 template <int S, int QP, int NS, int NT>
@@ -747,6 +786,9 @@ int launch_x(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
         qpb_set_error("segmented x sweep planned for an unsupported tile shape");
         return QPB_E_INVALID;
     }
+    // exact fit: every lane owns a chunk (QP == chunks per row == chunks per tile) and every tile row exists
+    if (S == 16 && A.qs == QP && A.Q == QP && A.ny % (NT / QP) == 0 && !getenv("QPB_PIPE_NOFULL"))
+        return launch_x_seg<S, QP, NS, NT, false, (S == 16)>(c, A, maps, grid);
     return launch_x_seg<S, QP, NS, NT, false>(c, A, maps, grid);
 }
 
@@ -755,17 +797,15 @@ size_t y_smem(int nt, int cw, int trows, int ns, bool inplace) {
     return ns * 2 * sb + (inplace ? 0 : 2 * sb) + sizeof(double) * 2 * nt + 64;
 }
 
-template <int S, int CW, int NS, int NT, bool SEG>
+template <int S, int CW, int NS, int NT, bool SEG, bool FULL = false>
 int launch_y_seg(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
-    auto kern = k_sweep_y_pipe<S, CW, NS, NT, SEG>;
+    auto kern = k_sweep_y_pipe<S, CW, NS, NT, SEG, FULL>;
     static bool configured = false;
     if (!configured) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    kern<<<grid, NT, y_smem(NT, CW, A.qs * S, NS, A.inplace != 0) + param_smem(A.ne), c->stream>>>(A, maps);
-    QPB_CHECK_LAUNCH();
-    return QPB_OK;
+    return launch_pdl(kern, grid, NT, y_smem(NT, CW, A.qs * S, NS, A.inplace != 0) + param_smem(A.ne), c, A, maps);
 }
 
 template <int S, int CW, int NS, int NT>
@@ -776,6 +816,9 @@ int launch_y(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
         qpb_set_error("segmented y sweep planned for an unsupported tile shape");
         return QPB_E_INVALID;
     }
+    // exact fit: the chunk slots of the CTA are the chunks of a column and the strips tile the grid
+    if (S == 16 && A.qs == NT / CW && A.Q == NT / CW && A.nx % CW == 0 && !getenv("QPB_PIPE_NOFULL"))
+        return launch_y_seg<S, CW, NS, NT, false, (S == 16)>(c, A, maps, grid);
     return launch_y_seg<S, CW, NS, NT, false>(c, A, maps, grid);
 }
 
