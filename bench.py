@@ -343,6 +343,13 @@ def run_single_gpu(args):
                   "kernel": "k_sweep (x+y tridiagonal sweeps)", "launches": int(nxl + nyl),
                   "ms_per_launch": sweep_ms / max(1, nxl + nyl), "peak_source": peak_src}
     roof_sweep["frac"] = roof_sweep["achieved"] / roof_sweep["peak"]
+    # what the kernels actually move: 24 B per DENSE grid cell, bin and sweep (x: u and b in, u* out; y: u* and u in, u
+    # out; cells outside the mask are part of the dense lines) -- the distance between this figure and `achieved` is
+    # the mask fill (cells / dense cells) times 16/24, not idle memory pipes
+    roof_sweep["implementation"] = {
+        "bytes_per_dense_cell_bin_sweep": 24, "dense_cells": int(ncd),
+        "achieved": 24.0 * ncd * bin_sweeps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0, "unit": "GB/s"}
+    roof_sweep["implementation"]["frac"] = roof_sweep["implementation"]["achieved"] / roof_sweep["peak"]
     roof_coll = {"bound": "fp64", "achieved": coll_flops / (tc * 1e-3) / 1e12 if tc > 0 else 0.0, "peak": fp64_peak,
                  "unit": "TFLOP/s", "traffic": prof.get("collide"), "kernel": "k_collide_struct", "launches": int(ncl),
                  "ms_per_launch": tc / max(1, ncl),
