@@ -176,3 +176,43 @@ def test_c4a_frozen_uniform_tensor_core_gemm_sampled():
     O.collide(so, po, t["Kr"], t["Ks"], t["rho"], t["idd"], t["ids"], t["sg"], t["dE"], 0.05, recomb=True, scat=True,
               update_phonons=False, chunk=8)
     helpers.assert_close(outs[0][:, pick].T, so.T, "tensor-core GEMM vs oracle on sampled cells")
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (128, 1024)], ids=["whole_lines_exact_fit", "segmented_rows"])
+def test_sweep_scheduling_switches_do_not_change_the_result(shape, monkeypatch):
+    """The L1 prefetch of the factor tables, programmatic dependent launch, the reversed bin walk of the y sweep and
+    the exact-fit tile variants only reorder loads and launches: a masked Crank-Nicolson solve must come out bit for
+    bit the same with each of them switched off (the switches are read at launch time)."""
+    ny, nx = shape
+    ne = 12
+    mask = cases.meander_mask(ny, nx, pad=8, slot=4, pitch=16, gap_len=32)
+    edges = Q.extract_edge_segments(mask)
+    bcs = cases.make_bcs(edges, "short_absorbing", Q.BoundaryCondition)
+    bcx, bcy, src = Q.compile_boundaries(mask, edges, bcs, 1.0)
+    n = int(mask.sum())
+    t = _tables(ne, 5.0)
+    u0 = np.stack([cases.gaussian_field(mask, cx=0.3 + 0.03 * k, cy=0.5, sigma=0.07)[mask] for k in range(ne)])
+
+    def solve():
+        with capi.Context(ny=ny, nx=nx, ne=ne, nw=0, ncell=n, flags=capi.F_DIFFUSION, dx=1.0, dE=t["dE"]) as ctx:
+            ctx.upload_geometry(mask, bcx, bcy, src)
+            ctx.upload_diffusion(t["D"])
+            ctx.prepare_diffusion(0, 0.5)
+            ctx.set_state(u0)
+            ctx.advance(3, 0.5)
+            out, _ = ctx.get_state(want_phonons=False)
+            info = ctx.diag()
+        assert info["sweep_path"] in (2, 3), info
+        return out, info["sweeps"]
+
+    want, sweeps = solve()
+    assert np.all(np.isfinite(want)) and sweeps > 6
+    for switch in ("QPB_PIPE_PREFETCH", "QPB_PIPE_PDL", "QPB_PIPE_REV"):
+        monkeypatch.setenv(switch, "0")
+        got, sw = solve()
+        monkeypatch.delenv(switch)
+        assert sw == sweeps, switch
+        assert np.array_equal(got, want), switch
+    monkeypatch.setenv("QPB_PIPE_NOFULL", "1")
+    got, sw = solve()
+    assert sw == sweeps and np.array_equal(got, want)
