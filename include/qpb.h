@@ -145,6 +145,12 @@ int qpb_get_integrated(qpb_ctx *ctx, double *out);
 /* the NE stored energy frames of one snapshot, dense [NE][ny][nx] with NaN outside the mask: what the reference
  * builds with NE calls of reconstruct_field (solver.py:215-218, 1484-1486), assembled on the device */
 int qpb_get_frames(qpb_ctx *ctx, double *frames);
+/* the same frames without stalling the run (the storage branch of the loop, solver.py:1479-1494, off the critical
+ * path): qpb_frames_snapshot assembles them into a device buffer of their own, stream ordered and non-blocking;
+ * qpb_frames_download waits for that snapshot only and copies it out on a second stream.  It may be called from
+ * another host thread while this context keeps stepping; one snapshot is outstanding at a time. */
+int qpb_frames_snapshot(qpb_ctx *ctx);
+int qpb_frames_download(qpb_ctx *ctx, double *frames);
 
 /* external generation (solver.py:878-964, 1459-1464) */
 #define QPB_GEN_NONE     0

@@ -80,6 +80,7 @@ EXPORTED = [
     "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
     "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons", "qpb_pauli_record", "qpb_pauli_fetch", "qpb_set_exchange", "qpb_collide_exchange",
     "qpb_ipc_export", "qpb_ipc_open", "qpb_ipc_close", "qpb_euler_step", "qpb_set_state_separable",
+    "qpb_frames_snapshot", "qpb_frames_download",
 ]
 
 
@@ -171,6 +172,8 @@ def load_library():
     lib.qpb_set_state_separable.argtypes = [vp, vp, vp, vp]
     lib.qpb_get_integrated.argtypes = [vp, vp]
     lib.qpb_get_frames.argtypes = [vp, vp]
+    lib.qpb_frames_snapshot.argtypes = [vp]
+    lib.qpb_frames_download.argtypes = [vp, vp]
     lib.qpb_trim_cache.argtypes = []
     lib.qpb_advance.argtypes = [vp, i32, dbl, i32, dbl, C.POINTER(Generation), vp]
     lib.qpb_collide.argtypes = [vp, dbl]
@@ -314,6 +317,19 @@ class Context:
         """The NE stored energy frames of one snapshot, (NE, ny, nx) with NaN outside the mask."""
         out = np.empty((self.ne, self.ny, self.nx))
         self._check(self.lib.qpb_get_frames(self.handle, _ptr(out)))
+        return out
+
+    def frames_snapshot(self):
+        """Assemble the NE frames of the current state into a device buffer of their own (stream ordered, returns at
+        once).  :meth:`frames_download` fetches them; one snapshot is outstanding at a time."""
+        self._check(self.lib.qpb_frames_snapshot(self.handle))
+
+    def frames_download(self, out=None):
+        """Copy the last snapshot to the host, (NE, ny, nx) with NaN outside the mask.  Safe to call from another
+        thread while this context keeps stepping (ctypes releases the GIL)."""
+        if out is None:
+            out = np.empty((self.ne, self.ny, self.nx))
+        self._check(self.lib.qpb_frames_download(self.handle, _ptr(out)))
         return out
 
     # ---- stepping ------------------------------------------------------------------------------------

@@ -164,6 +164,11 @@ struct qpb_ctx {
     bool timers_on = false;
     Timer timer[3];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // asynchronous snapshots (qpb_frames_snapshot / qpb_frames_download): device copy of the NaN-padded frames, the
+    // event that marks it complete and the stream its download runs on while the context keeps stepping
+    double *d_snap = nullptr;
+    cudaEvent_t ev_snap = nullptr;
+    cudaStream_t copy_stream = nullptr;
 };
 
 // ---- launch wrappers implemented in the .cu files (all enqueue on ctx->stream) ----

@@ -8,6 +8,8 @@ C ABI of ``include/qpb.h``.  Nothing in this module computes a time step on the 
 """
 from __future__ import annotations
 
+import threading
+
 import warnings
 from typing import Any, Callable
 
@@ -407,44 +409,83 @@ def run_2d_crank_nicolson(
         integrated = ctx.get_integrated() if state is None else np.sum(state, axis=0) * dE
         times = [0.0]
         frames = [reconstruct_field(mask_b, integrated)]
-        energy_frames = [list(ctx.get_frames())] if store_energy_frames else [None]
-        mass = [float(np.sum(integrated) * dx * dx)]
-        _callback(progress_callback, 0.0, frames[0])
+        # The NE frames of a stored step are snapshotted on the device and downloaded by a helper thread while the
+        # next steps run; the list entry is filled in when the download is joined (before the next snapshot / return).
+        energy_frames = []
+        pending = []   # [(thread, result holder, index into energy_frames)]
 
-        current_time = 0.0
-        step = 0
-        per_step_gen = (external_generation is not None
-                        and external_generation.mode.strip().lower() == "custom")
-        has_gen = external_generation is not None and external_generation.mode != "none"
-        while step < total_steps:
-            nxt = min(((step // store_every) + 1) * store_every, total_steps)
-            if nxt > full_steps and step < full_steps:
-                nxt = full_steps
-            if per_step_gen:
-                nxt = step + 1
-            is_final = step >= full_steps
-            h = remainder_dt if is_final else dt
-            count = nxt - step
-            gen_kwargs, _ = (_generation_args(external_generation, E_bins, n, current_time, mask_b)
-                             if has_gen else (dict(gen_mode=capi.GEN_NONE), True))
-            recs = ctx.advance(count, h, slot=1 if is_final else 0, t_start=current_time, want_pauli=True,
-                               **gen_kwargs)
-            for k in range(count):
-                policy.check(recs[k], step + k + 1, current_time + h)
-                current_time += h
-            step = nxt
-            if step % store_every == 0 or step == total_steps:
-                integrated = ctx.get_integrated()
-                times.append(float(current_time))
-                frame = reconstruct_field(mask_b, integrated)
-                frames.append(frame)
-                # NE NaN-padded frames assembled on the device (one dense download instead of NE host scatters)
-                energy_frames.append(list(ctx.get_frames()) if store_energy_frames else None)
-                if want_ph_hist:
-                    ph = ctx.get_state(want_qp=False, want_phonons=True)[1] if collisions else None
-                    snapshot_phonons(ph if ph is not None else phonon_state)
-                mass.append(float(np.sum(integrated) * dx * dx))
-                _callback(progress_callback, float(current_time), frame)
+        def join_pending():
+            while pending:
+                th, box, idx = pending.pop()
+                th.join()
+                if "error" in box:
+                    raise box["error"]
+                energy_frames[idx] = list(box["frames"])
+
+        def store_frames():
+            if not store_energy_frames:
+                energy_frames.append(None)
+                return
+            join_pending()                 # one snapshot buffer: the previous download has to be through
+            ctx.frames_snapshot()
+            box = {}
+
+            def work():
+                try:
+                    box["frames"] = ctx.frames_download()
+                except BaseException as exc:   # re-raised in the calling thread by join_pending
+                    box["error"] = exc
+
+            th = threading.Thread(target=work, daemon=True)
+            energy_frames.append(None)
+            pending.append((th, box, len(energy_frames) - 1))
+            th.start()
+
+        try:
+            store_frames()
+            mass = [float(np.sum(integrated) * dx * dx)]
+            _callback(progress_callback, 0.0, frames[0])
+
+            current_time = 0.0
+            step = 0
+            per_step_gen = (external_generation is not None
+                            and external_generation.mode.strip().lower() == "custom")
+            has_gen = external_generation is not None and external_generation.mode != "none"
+            while step < total_steps:
+                nxt = min(((step // store_every) + 1) * store_every, total_steps)
+                if nxt > full_steps and step < full_steps:
+                    nxt = full_steps
+                if per_step_gen:
+                    nxt = step + 1
+                is_final = step >= full_steps
+                h = remainder_dt if is_final else dt
+                count = nxt - step
+                gen_kwargs, _ = (_generation_args(external_generation, E_bins, n, current_time, mask_b)
+                                 if has_gen else (dict(gen_mode=capi.GEN_NONE), True))
+                recs = ctx.advance(count, h, slot=1 if is_final else 0, t_start=current_time, want_pauli=True,
+                                   **gen_kwargs)
+                for k in range(count):
+                    policy.check(recs[k], step + k + 1, current_time + h)
+                    current_time += h
+                step = nxt
+                if step % store_every == 0 or step == total_steps:
+                    integrated = ctx.get_integrated()
+                    times.append(float(current_time))
+                    frame = reconstruct_field(mask_b, integrated)
+                    frames.append(frame)
+                    # NE NaN-padded frames assembled on the device (one dense download instead of NE host scatters)
+                    store_frames()
+                    if want_ph_hist:
+                        ph = ctx.get_state(want_qp=False, want_phonons=True)[1] if collisions else None
+                        snapshot_phonons(ph if ph is not None else phonon_state)
+                    mass.append(float(np.sum(integrated) * dx * dx))
+                    _callback(progress_callback, float(current_time), frame)
+            join_pending()
+        finally:
+            # an exception on the way (Pauli violation, callback, device error) must not leave a download running into a
+            # context that is being destroyed
+            for th, _, _ in pending:
+                th.join()
         info.update(ctx.diag())
 
     limits = _color_limits(frames)

@@ -351,3 +351,41 @@ def test_large_downloads_staged_and_plain_agree(staged, monkeypatch):
     assert np.array_equal(back, state)
     assert np.all(np.isnan(frames[:, ~mask]))
     assert np.array_equal(frames[:, mask], state)
+
+
+def test_snapshot_download_overlaps_stepping_and_matches_get_frames():
+    """qpb_frames_snapshot / qpb_frames_download: the frames of the snapshot instant, also when the context keeps
+    stepping (and overwriting the state and its work arrays) while a helper thread downloads them."""
+    import threading
+
+    from qpsim_b200 import capi
+
+    case = cases.meander_c2(ny=96, nx=96, ne=40, steps=2)       # 2.9 MiB of frames, plain copy path
+    big = cases.meander_c2(ny=256, nx=272, ne=40, steps=2)      # 22 MiB: pinned two-chunk pipeline
+    for c_ in (case, big):
+        mask = c_["mask"]
+        ny, nx = mask.shape
+        n, ne = int(mask.sum()), c_["num_energy_bins"]
+        edges = Q.extract_edge_segments(mask)
+        bcs = cases.make_bcs(edges, c_["bc"], Q.BoundaryCondition)
+        bcx, bcy, src = Q.compile_boundaries(mask, edges, bcs, 1.0)
+        E, dE = Q.build_energy_grid(cases.GAP, 1.0, 5.0, ne)
+        D = cases.D0 * np.sqrt(np.maximum(0.0, 1.0 - (cases.GAP / E) ** 2))
+        rng = np.random.default_rng(11)
+        state = rng.random((ne, n)) * 1e-4
+        with capi.Context(ny=ny, nx=nx, ne=ne, nw=0, ncell=n, flags=capi.F_DIFFUSION, dx=1.0, dE=dE) as ctx:
+            ctx.upload_geometry(mask, bcx, bcy, src)
+            ctx.upload_diffusion(D)
+            ctx.prepare_diffusion(0, 0.5)
+            ctx.set_state(state)
+            want = ctx.get_frames()
+            ctx.frames_snapshot()
+            box = {}
+            th = threading.Thread(target=lambda: box.update(frames=ctx.frames_download()))
+            th.start()
+            ctx.advance(3, 0.5)                      # overwrites the state while the download runs
+            th.join()
+            after = ctx.get_frames()
+        assert np.array_equal(box["frames"], want, equal_nan=True)
+        assert not np.array_equal(after, want, equal_nan=True)
+        assert np.array_equal(want[:, mask], state) and np.all(np.isnan(want[:, ~mask]))
