@@ -30,13 +30,25 @@ with torch.cuda.stream(stages.stream):
         t0 = time.perf_counter(); e0.record(stages.stream); fn(); e1.record(stages.stream); torch.cuda.synchronize()
         a = acc.setdefault(name, [0.0, 0.0]); a[0] += e0.elapsed_time(e1); a[1] += (time.perf_counter() - t0) * 1e3
     K = 10
+    fused = stages.enable_fused_exchange(prob)
+    st = ShardedStepper(plan, stages, diffusion=True, collisions=True)
+    for _ in range(2):
+        st.step(dt, 0, w["pulse_rate"])
     for _ in range(K):
         timed("generation", lambda: stages.add_generation(dt, w["pulse_rate"]))
-        timed("collide", lambda: stages.collide(0.5 * dt))
-        timed("to_bins", st.to_bins)
-        timed("diffuse", lambda: stages.diffuse(0))
-        timed("to_cells", st.to_cells)
-        timed("collide", lambda: stages.collide(0.5 * dt))
+        if fused:
+            timed("collide_x1", lambda: stages.collide_exchange(0.5 * dt, 1))
+            timed("barrier", st._rank_barrier)
+            timed("diffuse", lambda: stages.diffuse(0))
+            timed("barrier", st._rank_barrier)
+            timed("collide_x2", lambda: stages.collide_exchange(0.5 * dt, 2))
+            timed("barrier", st._rank_barrier)
+        else:
+            timed("collide", lambda: stages.collide(0.5 * dt))
+            timed("to_bins", st.to_bins)
+            timed("diffuse", lambda: stages.diffuse(0))
+            timed("to_cells", st.to_cells)
+            timed("collide", lambda: stages.collide(0.5 * dt))
         timed("pauli_record", lambda: stages.pauli_record(0))
     torch.cuda.synchronize(); dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
