@@ -81,6 +81,32 @@ def extract_edge_segments(mask: np.ndarray) -> list[EdgeSegment]:
     return out
 
 
+def _face_arrays(edge):
+    """[(direction, rows, cols)] of an edge's faces as index arrays.  The per-face attribute walk is the expensive part
+    of compiling a geometry (7 000 faces at 256 x 256), so the result is kept on the edge object and reused as long as
+    its face list is the same list with the same end faces (a GUI reruns one geometry many times)."""
+    faces = edge.faces
+    key = (id(faces), len(faces), id(faces[0]), id(faces[-1]))
+    cached = getattr(edge, "_qpb_face_arrays", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    rows = np.fromiter((f.row for f in faces), dtype=np.int64, count=len(faces))
+    cols = np.fromiter((f.col for f in faces), dtype=np.int64, count=len(faces))
+    dirs = {f.direction for f in faces}
+    if len(dirs) == 1:
+        out = [(next(iter(dirs)), rows, cols)]
+    else:
+        out = []
+        for d in dirs:
+            sel = np.fromiter((f.direction == d for f in faces), dtype=bool, count=len(faces))
+            out.append((d, rows[sel], cols[sel]))
+    try:
+        edge._qpb_face_arrays = (key, out)
+    except Exception:   # objects that refuse new attributes (slots, frozen): just do not cache
+        pass
+    return out
+
+
 def compile_boundaries(mask: np.ndarray, edges, edge_conditions, dx: float):
     """Return dense (bcx, bcy, source) arrays, each [ny,nx] float64.
 
@@ -134,15 +160,7 @@ def compile_boundaries(mask: np.ndarray, edges, edge_conditions, dx: float):
             raise BoundaryAssignmentError(f"Unsupported boundary kind: {bc.kind}")
         if not edge.faces:
             continue
-        rows = np.fromiter((f.row for f in edge.faces), dtype=np.int64, count=len(edge.faces))
-        cols = np.fromiter((f.col for f in edge.faces), dtype=np.int64, count=len(edge.faces))
-        dirs = {f.direction for f in edge.faces}
-        for d in dirs:
-            if len(dirs) == 1:
-                r, c = rows, cols
-            else:
-                sel = np.fromiter((f.direction == d for f in edge.faces), dtype=bool, count=len(edge.faces))
-                r, c = rows[sel], cols[sel]
+        for d, r, c in _face_arrays(edge):
             ok = (r >= 0) & (r < ny) & (c >= 0) & (c < nx)
             r, c = r[ok], c[ok]
             covered[d][r, c] = True
