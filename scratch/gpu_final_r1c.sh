@@ -8,7 +8,8 @@ cat $O/bench.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/launches_bench.csv python bench.py --steps 2 --warmup 3 > $O/ncu_launch.log 2>&1; echo "launch list rc=$?"
 python scratch/prof_step.py 4 > $O/step_plain.log 2>&1 || exit 1
 for k in k_collide_struct k_sweep_x_pipe k_sweep_y_pipe; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 40 -c 1 -f -o $O/full_$k python scratch/prof_step.py 4 > $O/ncu_$k.log 2>&1; echo "$k rc=$?"
+  skip=40; [ $k = k_collide_struct ] && skip=2   # 8 collision launches in the 4 profiled steps, 144 sweeps
+  ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c 1 -f -o $O/full_$k python scratch/prof_step.py 4 > $O/ncu_$k.log 2>&1; echo "$k rc=$?"
   ncu -i $O/full_$k.ncu-rep --page raw --csv > $O/full_${k}_raw.csv 2>/dev/null
 done
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
