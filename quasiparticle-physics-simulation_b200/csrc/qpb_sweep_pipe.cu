@@ -374,6 +374,15 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
                 mR[un] = pm[un * Q + qc];
                 gR[un] = pg[un * Q + qc];
             }
+            if (SEG) {   // segmented tiles: masked at once (measured: the late touch costs 3 % there)
+#pragma unroll
+                for (int un = 0; un < UPC; ++un) {
+                    ch.m[2 * un] = rowok_c ? mR[un].x : 0.0;
+                    ch.m[2 * un + 1] = rowok_c ? mR[un].y : 0.0;
+                    ch.g[2 * un] = rowok_c ? gR[un].x : 0.0;
+                    ch.g[2 * un + 1] = rowok_c ? gR[un].y : 0.0;
+                }
+            }
         }
         if (A.prefetch) {
             // The tables are L2 resident, but an L2 round trip per tile sat exposed in front of the solve (ncu: the first
@@ -454,12 +463,14 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
             bulk_wait_read<0>();
             produce();
         }
+        if (!SEG) {
 #pragma unroll
-        for (int un = 0; un < UPC; ++un) {
-            ch.m[2 * un] = rowok_c ? mR[un].x : 0.0;
-            ch.m[2 * un + 1] = rowok_c ? mR[un].y : 0.0;
-            ch.g[2 * un] = rowok_c ? gR[un].x : 0.0;
-            ch.g[2 * un + 1] = rowok_c ? gR[un].y : 0.0;
+            for (int un = 0; un < UPC; ++un) {
+                ch.m[2 * un] = rowok_c ? mR[un].x : 0.0;
+                ch.m[2 * un + 1] = rowok_c ? mR[un].y : 0.0;
+                ch.g[2 * un] = rowok_c ? gR[un].x : 0.0;
+                ch.g[2 * un + 1] = rowok_c ? gR[un].y : 0.0;
+            }
         }
         double Am, Bm;
         ch.forward(Am, Bm);
@@ -627,6 +638,15 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
         ChunkSolve<S> ch;
         load_factors(t);   // issued before the wait on the tile (a register prefetch of the next tile measured slower)
         const bool qok_t = FULL ? true : qok, inter_t = FULL ? true : inter;
+        if (SEG) {   // segmented tiles: masked at once (see the x sweep)
+#pragma unroll
+            for (int un = 0; un < S / 2; ++un) {
+                ch.m[2 * un] = qok_t ? mR[un].x : 0.0;
+                ch.m[2 * un + 1] = qok_t ? mR[un].y : 0.0;
+                ch.g[2 * un] = qok_t ? gR[un].x : 0.0;
+                ch.g[2 * un + 1] = qok_t ? gR[un].y : 0.0;
+            }
+        }
         if (A.prefetch && tn < A.ntiles) {   // next tile's table lines into L1 (see the x sweep); one line per table
             const size_t basen = factor_base(tn);
             prefetch_l1(A.tabm + basen);
@@ -643,12 +663,14 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
             ch.v[tt] = delta ? sw[tt * CW] : sw[tt * CW] - uold[tt];
         }
         // the factors are first touched here, behind the wait and the tile reads: their L2 latency is off the critical path
+        if (!SEG) {
 #pragma unroll
-        for (int un = 0; un < S / 2; ++un) {
-            ch.m[2 * un] = qok_t ? mR[un].x : 0.0;
-            ch.m[2 * un + 1] = qok_t ? mR[un].y : 0.0;
-            ch.g[2 * un] = qok_t ? gR[un].x : 0.0;
-            ch.g[2 * un + 1] = qok_t ? gR[un].y : 0.0;
+            for (int un = 0; un < S / 2; ++un) {
+                ch.m[2 * un] = qok_t ? mR[un].x : 0.0;
+                ch.m[2 * un + 1] = qok_t ? mR[un].y : 0.0;
+                ch.g[2 * un] = qok_t ? gR[un].x : 0.0;
+                ch.g[2 * un + 1] = qok_t ? gR[un].y : 0.0;
+            }
         }
         // refill the stage of tile k-1 with tile k+NS-1 (its store, issued an iteration ago, has read the shared memory)
         if (tid == 0 && inplace) {
@@ -658,13 +680,16 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
         double Am, Bm;
         ch.forward(Am, Bm);
         double *cA = carry + (size_t)(k & 1) * 3 * NCH * CW, *cB = cA + NCH * CW, *cR = cB + NCH * CW;
+        if (SEG) cta_bar<NT>(1);   // segmented tiles keep the five-barrier schedule (measured faster there)
         cA[q * CW + c] = Am;
         cB[q * CW + c] = Bm;
         cta_bar<NT>(2);
         double cin = 0.0;
         for (int kk = max(0, q - A.depth); kk < q; ++kk) cin = fma(cA[kk * CW + c], cin, cB[kk * CW + c]);
         ch.forward_fix(cin);
-        cR[q * CW + c] = ch.backward();
+        Bm = ch.backward();
+        if (SEG) cta_bar<NT>(3);
+        cR[q * CW + c] = Bm;
         cta_bar<NT>(4);
         cin = 0.0;
         for (int kk = min(NCH - 1, q + A.depth); kk > q; --kk) cin = fma(cA[kk * CW + c], cin, cR[kk * CW + c]);
@@ -1008,6 +1033,10 @@ int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check) {
         A.tiles_per_bin = p.x_tpb;
         A.ntiles = p.x_tpb * cf.ne;
         const int grid = pick_grid(A.ntiles, p.x_tpb, p.nsm);
+        // the prefetch addresses assume that a CTA's next tile differs from this one only in the bin (whole lines, grid a
+        // multiple of the tiles per bin); on segmented or wandering tilings it fetched the wrong rows and cost 4 % at
+        // 2048^2
+        if (A.nseg > 1 || grid % p.x_tpb != 0) A.prefetch = 0;
         const XMaps &maps = *reinterpret_cast<const XMaps *>(p.xmaps.data());
         if (fd.S == 8) return dispatch_x<8, 512>(c, A, maps, grid, p.x_qp, p.x_ns);
         return dispatch_x<16, 256>(c, A, maps, grid, p.x_qp, p.x_ns);
@@ -1015,6 +1044,7 @@ int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check) {
     A.tiles_per_bin = p.y_tpb;
     A.ntiles = p.y_tpb * cf.ne;
     const int grid = pick_grid(A.ntiles, p.y_tpb, p.nsm);
+    if (A.nseg > 1 || grid % p.y_tpb != 0) A.prefetch = 0;   // see above: the class lookup of a new strip would sit in the tile's path
     const YMaps &maps = *reinterpret_cast<const YMaps *>(p.ymaps.data());
     if (fd.S == 8) return dispatch_y<8, 512>(c, A, maps, grid, p.y_cw, p.y_ns);
     return dispatch_y<16, 256>(c, A, maps, grid, p.y_cw, p.y_ns);

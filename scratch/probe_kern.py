@@ -8,21 +8,7 @@ import bench, cases
 import qpsim_b200 as Q
 from qpsim_b200 import capi
 variants = [v for v in sys.argv[1:]] or [""]
-if os.environ.get("QPB_LIB"):   # A/B against an older build of the library (missing entry points become dummies)
-    import ctypes
-    capi.LIB_PATH = os.path.abspath(os.environ["QPB_LIB"])
-    class _Dummy:
-        pass
-    class _Tol(ctypes.CDLL):
-        def __getattr__(self, name):
-            try:
-                return super().__getattr__(name)
-            except AttributeError:
-                if name.startswith("qpb_"):
-                    return _Dummy()
-                raise
-    capi.C.CDLL = _Tol
-    print("library:", capi.LIB_PATH)
+import _libswitch  # noqa: F401  (QPB_LIB=... selects another build of the library)
 w = bench.c2_workload(); tabs = bench.build_tables(w, Q)
 mask = w["mask"]; ny, nx = mask.shape; n, ne, nw = tabs["n"], w["num_energy_bins"], tabs["omega"].size
 edges = Q.extract_edge_segments(mask); bcs = cases.make_bcs(edges, w["bc"], Q.BoundaryCondition)

@@ -6,6 +6,7 @@ import numpy as np
 import qpsim_b200 as Q
 from qpsim_b200 import capi
 import cases
+import _libswitch  # noqa: F401  (QPB_LIB=... selects another build of the library)
 
 def diffusion_probe(ny, nx, ne, dt=0.2, fmax=3.0, steps=3):
     mask = np.ones((ny, nx), bool)
