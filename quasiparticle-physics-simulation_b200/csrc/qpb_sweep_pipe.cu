@@ -309,9 +309,11 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
     // Static data first (the geometry of the CTA's first tile: with a grid that is a multiple of the tiles per bin it
     // is the geometry of all its tiles), then wait for the preceding grid of the stream: everything below reads what
     // it wrote (convergence flags, residuals, the state).
-    pdl_launch_dependents();
-    if ((int)blockIdx.x < A.ntiles) load_geometry((int)blockIdx.x % tpb);
-    pdl_wait();
+    if (!SEG) {   // segmented instances are launched in plain stream order (launch_pdl): they measured slower with it
+        pdl_launch_dependents();
+        if ((int)blockIdx.x < A.ntiles) load_geometry((int)blockIdx.x % tpb);
+        pdl_wait();
+    }
     load_bin_params<0, NT>(A, s_a, s_rho, s_j);
     __syncthreads();
     // producer cursor (thread 0 only): next tile index to load and number of loads issued
@@ -551,8 +553,10 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
     double *s_a = reinterpret_cast<double *>(bars + 8);
     double *s_rho = s_a + A.ne;
     int *s_j = reinterpret_cast<int *>(s_rho + A.ne);
-    pdl_launch_dependents();
-    pdl_wait();   // everything below reads what the preceding grid wrote
+    if (!SEG) {
+        pdl_launch_dependents();
+        pdl_wait();   // everything below reads what the preceding grid wrote
+    }
     load_bin_params<1, NT>(A, s_a, s_rho, s_j);
     __syncthreads();
     const int tpb = A.tiles_per_bin;
@@ -562,7 +566,7 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
     const int nbox_o = (orows + 255) / 256;
     const int box_rows_o = orows / nbox_o;
     // tile of a position in the walking order (rev: from the last bin down, what the preceding sweep wrote last)
-    auto tile_of = [&](int pos) { return A.rev ? A.ntiles - 1 - pos : pos; };
+    auto tile_of = [&](int pos) { return (!SEG && A.rev) ? A.ntiles - 1 - pos : pos; };
     int pt = blockIdx.x, pk = 0;
     auto produce = [&]() {
         while (pt < A.ntiles) {
@@ -608,7 +612,7 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
         const int qa = sg * QI - H + q;               // chunk of the column this thread solves
         qok = q < QS && qa >= 0 && qa < Q;
         inter = qok && q >= H && q < H + QI;
-        if (strip != cur_strip) {   // the CTA normally stays on one strip: the class lookup is not on the tile's path
+        if (SEG || strip != cur_strip) {   // the CTA normally stays on one strip: the class lookup is not on the tile's path
             cur_strip = strip;
             cls = A.cls[min(strip * CW + c, A.nx - 1)];
         }
@@ -679,7 +683,7 @@ k_sweep_y_pipe(PipeArgs Ain, const __grid_constant__ YMaps maps) {
         }
         double Am, Bm;
         ch.forward(Am, Bm);
-        double *cA = carry + (size_t)(k & 1) * 3 * NCH * CW, *cB = cA + NCH * CW, *cR = cB + NCH * CW;
+        double *cA = carry + (size_t)(SEG ? 0 : (k & 1)) * 3 * NCH * CW, *cB = cA + NCH * CW, *cR = cB + NCH * CW;
         if (SEG) cta_bar<NT>(1);   // segmented tiles keep the five-barrier schedule (measured faster there)
         cA[q * CW + c] = Am;
         cB[q * CW + c] = Bm;
@@ -780,7 +784,7 @@ size_t x_smem(int nt, int QP, int nx16, int ns, bool inplace) {
 // Launch with programmatic stream serialization (see pdl_wait): consecutive sweep kernels overlap the tail of one
 // with the prologue of the next.  QPB_PIPE_PDL=0: plain stream order.
 template <class Kern, class Maps>
-int launch_pdl(Kern kern, int grid, int nt, size_t smem, qpb_ctx *c, const PipeArgs &A, const Maps &maps) {
+int launch_pdl(Kern kern, int grid, int nt, size_t smem, qpb_ctx *c, const PipeArgs &A, const Maps &maps, bool pdl) {
     const char *e = getenv("QPB_PIPE_PDL");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid);
@@ -791,7 +795,7 @@ int launch_pdl(Kern kern, int grid, int nt, size_t smem, qpb_ctx *c, const PipeA
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = (e && e[0] == '0') ? 0 : 1;
+    cfg.numAttrs = (!pdl || (e && e[0] == '0')) ? 0 : 1;
     QPB_CUDA(cudaLaunchKernelEx(&cfg, kern, A, maps));
     QPB_CHECK_LAUNCH();
     return QPB_OK;
@@ -805,7 +809,7 @@ int launch_x_seg(qpb_ctx *c, const PipeArgs &A, const XMaps &maps, int grid) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    return launch_pdl(kern, grid, NT, x_smem(NT, QP, A.qs * S / 16, NS, A.inplace != 0) + param_smem(A.ne), c, A, maps);
+    return launch_pdl(kern, grid, NT, x_smem(NT, QP, A.qs * S / 16, NS, A.inplace != 0) + param_smem(A.ne), c, A, maps, !SEG);
 }
 
 template <int S, int QP, int NS, int NT>
@@ -835,7 +839,7 @@ int launch_y_seg(qpb_ctx *c, const PipeArgs &A, const YMaps &maps, int grid) {
         QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_CAP));
         configured = true;
     }
-    return launch_pdl(kern, grid, NT, y_smem(NT, CW, A.qs * S, NS, A.inplace != 0) + param_smem(A.ne), c, A, maps);
+    return launch_pdl(kern, grid, NT, y_smem(NT, CW, A.qs * S, NS, A.inplace != 0) + param_smem(A.ne), c, A, maps, !SEG);
 }
 
 template <int S, int CW, int NS, int NT>
