@@ -82,6 +82,22 @@ def c2_workload(tile_y: int = 1, tile_x: int = 1, ny: int = 256, nx: int = 256, 
     )
 
 
+def c2_case(steps: int = 2):
+    """c2_workload() in the vocabulary of tests/cases.py (what the reference / oracle / drop-in runners take): the
+    full-size parity fixture tests/golden/c2_full_256x256x128.npz is this case run by the unmodified reference."""
+    w = c2_workload()
+    return dict(
+        name="c2_full_256x256x128", mask=w["mask"], bc=w["bc"], initial_field=w["initial_field"],
+        diffusion_coefficient=w["diffusion_coefficient"], dt=w["dt"], total_time=w["dt"] * steps, dx=w["dx"],
+        store_every=steps, energy_gap=w["energy_gap"], energy_min_factor=w["energy_min_factor"],
+        energy_max_factor=w["energy_max_factor"], num_energy_bins=w["num_energy_bins"], weights=None,
+        enable_diffusion=True, enable_recombination=True, enable_scattering=True, dynes_gamma=w["dynes_gamma"],
+        tau_0=w["tau_0"], T_c=w["T_c"], bath_temperature=w["bath_temperature"],
+        generation=dict(mode="pulse", pulse_rate=w["pulse_rate"], pulse_start=w["pulse_start"],
+                        pulse_duration=w["pulse_duration"]),
+    )
+
+
 def c3_workload():
     """BASELINE configs[2]: 2048 x 2048 full mask, reflective walls, 256 bins on [gap, 3 gap],
     dt = 0.2 ns, seeded lognormal field x thermal weights, dynamic phonons.  Strong scaling: the grid is fixed and cut

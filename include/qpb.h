@@ -156,7 +156,10 @@ int qpb_frames_download(qpb_ctx *ctx, double *frames);
 #define QPB_GEN_NONE     0
 #define QPB_GEN_CONSTANT 1   /* rate                                  */
 #define QPB_GEN_PULSE    2   /* rate while t0 <= t < t0 + duration    */
-#define QPB_GEN_ARRAY    3   /* host-evaluated g[ne][N], nsteps must be 1 */
+#define QPB_GEN_ARRAY    3   /* host-evaluated g[ne][N] (custom bodies, solver.py:918-962): uploaded by this call and
+                              * applied in every step of the batch; it stays resident on the device afterwards */
+#define QPB_GEN_RESIDENT 4   /* the array the last QPB_GEN_ARRAY call left on the device: a time-independent custom body
+                              * is evaluated and uploaded once per run */
 
 typedef struct qpb_generation {
     int32_t mode;

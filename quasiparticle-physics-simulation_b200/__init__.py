@@ -11,6 +11,7 @@ from .models import (  # noqa: F401
     BoundaryFace,
     EdgeSegment,
     ExternalGenerationSpec,
+    InitialConditionSpec,
 )
 from .geometry import compile_boundaries, extract_edge_segments  # noqa: F401
 from .physics import (  # noqa: F401
@@ -33,7 +34,7 @@ from .solver import (  # noqa: F401
     reconstruct_field,
     run_2d_crank_nicolson,
 )
-from . import capi  # noqa: F401
+from . import capi, userexpr  # noqa: F401
 from .ensemble import parameter_grid, run_ensemble  # noqa: F401
 
 __all__ = [
@@ -41,6 +42,6 @@ __all__ = [
     "apply_collision_step_fischer_catelani_uniform",
     "apply_collision_step_fischer_catelani_nonuniform",
     "apply_scattering_step", "apply_recombination_step",
-    "BoundaryCondition", "BoundaryFace", "EdgeSegment", "ExternalGenerationSpec", "BoundaryAssignmentError",
+    "BoundaryCondition", "BoundaryFace", "EdgeSegment", "ExternalGenerationSpec", "InitialConditionSpec", "BoundaryAssignmentError",
     "extract_edge_segments", "compile_boundaries", "build_energy_grid", "capi", "run_ensemble", "parameter_grid",
 ]

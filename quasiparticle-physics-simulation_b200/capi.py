@@ -29,7 +29,7 @@ F_VARIABLE_D = 1 << 4
 F_PAULI = 1 << 5
 F_SCALAR = 1 << 6
 
-GEN_NONE, GEN_CONSTANT, GEN_PULSE, GEN_ARRAY = 0, 1, 2, 3
+GEN_NONE, GEN_CONSTANT, GEN_PULSE, GEN_ARRAY, GEN_RESIDENT = 0, 1, 2, 3, 4
 
 E_NOCONV = -5
 

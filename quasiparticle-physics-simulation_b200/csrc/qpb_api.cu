@@ -182,6 +182,7 @@ void qpbk_free_slot(DiffSlot &s) {
     dev_free(s.d_a);
     dev_free(s.d_shift);
     dev_free(s.d_jlen);
+    dev_free(s.d_tol);
     dev_free(s.d_known);
     dev_free(s.d_ex);
     dev_free(s.d_ey);
@@ -392,7 +393,7 @@ extern "C" int qpb_upload_geometry(qpb_ctx *c, const uint8_t *mask, const double
         QPB_CUDA(cudaMemcpyAsync(c->d_bcy, bcy, sizeof(double) * ncd, cudaMemcpyHostToDevice, c->stream));
         QPB_CUDA(cudaMemcpyAsync(c->d_srcgeom, source, sizeof(double) * ncd, cudaMemcpyHostToDevice, c->stream));
         // Gershgorin bounds and a commutator probe of Gx, Gy (unit coefficient)
-        double gx = 0.0, gy = 0.0;
+        double gx = 0.0, gy = 0.0, gmin = 0.0;
         for (int p = 0; p < ncd; ++p) {
             const unsigned f = c->h_flags[p];
             if (!(f & QPB_IN)) continue;
@@ -400,7 +401,9 @@ extern "C" int qpb_upload_geometry(qpb_ctx *c, const uint8_t *mask, const double
             const int dyl = ((f & QPB_LK_U) ? 1 : 0) + ((f & QPB_LK_D) ? 1 : 0);
             gx = std::max(gx, 2.0 * dxl + std::fabs(bcx[p]));
             gy = std::max(gy, 2.0 * dyl + std::fabs(bcy[p]));
+            gmin = std::min(gmin, std::min(bcx[p], bcy[p]));
         }
+        c->gmin = gmin;
         c->gmax_x = gx;
         c->gmax_y = gy;
         std::mt19937_64 rng(12345);
@@ -613,11 +616,21 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
     int jmax = 1;
     const double target = std::min(1e-2, std::max(cf.diff_tol * 0.1, 1e-15));
     for (int i = 0; i < ne; ++i) {
-        const double lo = 0.5, hi = std::max(hi_bin[i], 0.5);
+        // spectrum of H, V = I/2 + alpha*G inside [lo, hi]; G is positive semi-definite unless a Robin face has a negative
+        // beta, which lowers the bound by alpha*|beta| (vard: the dense coefficient fields carry the same sign)
+        const double amax = vard ? (hi_bin[i] - 0.5) / std::max(1.0, std::max(c->gmax_x, c->gmax_y)) : s.a_bin[i];
+        const double lo = 0.5 + amax * c->gmin, hi = std::max(hi_bin[i], 0.5);
+        if (s.mode == 0 && !(lo > 0.05)) {
+            qpb_set_error("qpb_prepare_diffusion: a boundary face with a negative Robin coefficient makes the split "
+                          "operators indefinite at this step length (bin %d: lower spectral bound %.3g); the sweep "
+                          "iteration does not cover that case", i, lo);
+            return QPB_E_INVALID;
+        }
         if (s.mode != 0) sh[i] = {0.0};
         else if (s.commuting) sh[i] = plan_shifts(lo, hi, target, 48);
         else {
-            const int J = 4;  // cyclic geometric set (box D)
+            // cyclic geometric set (box D); one shift per octave of hi/lo, at least 4
+            const int J = std::max(4, std::min(16, (int)std::ceil(std::log2(hi / lo))));
             sh[i].resize(J);
             for (int k = 1; k <= J; ++k) sh[i][k - 1] = hi * std::pow(lo / hi, (2.0 * k - 1.0) / (2.0 * J));
         }
@@ -631,6 +644,13 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
     QPB_ALLOC(s.d_a, ne);
     QPB_ALLOC(s.d_shift, (size_t)ne * jmax);
     QPB_ALLOC(s.d_jlen, ne);
+    // The stop test is ||b - Au|| <= tol ||u||.  The residual itself is evaluated in fp64 with entries of size
+    // (1 + 2 * max row sum of alpha*G) |u|: below a few ulps of that it is rounding noise and the test could never pass
+    // (fine meshes / long steps: alpha in the thousands), so the tolerance of a bin is floored there.
+    std::vector<double> tolb(ne);
+    for (int i = 0; i < ne; ++i) tolb[i] = std::max(cf.diff_tol, 1e-15 * (1.0 + 2.0 * (hi_bin[i] - 0.5)));
+    QPB_ALLOC(s.d_tol, ne);
+    QPB_CUDA(cudaMemcpyAsync(s.d_tol, tolb.data(), sizeof(double) * ne, cudaMemcpyHostToDevice, c->stream));
     QPB_ALLOC(s.d_known, ne);
     QPB_CUDA(cudaMemsetAsync(s.d_known, 0, sizeof(int) * ne, c->stream));
     s.known_iters = 0;
@@ -787,7 +807,16 @@ extern "C" int qpb_upload_collision(qpb_ctx *c, const double *K_r0, const double
         }
     }
     c->have_coll = true;
-    const int rcs = qpbk_collision_setup(c);
+    int rcs = qpbk_collision_setup(c);
+    // packed effective kernels (frozen cell-independent phonons) were built from the PREVIOUS tables: re-pack them from
+    // the occupations they were made of, so that a table upload on a live context cannot leave stale products behind
+    const bool was_uniform = c->uniform_ph;
+    c->uniform_ph = false;
+    c->gemm_ready = false;
+    if (rcs == QPB_OK && was_uniform && (int)c->h_ph_bins.size() == cf.nw) {
+        const std::vector<double> bins = c->h_ph_bins;
+        rcs = qpbk_uniform_setup(c, bins.data(), true);
+    }
     // the setup code uses blocking copies on the legacy stream, which the context's non-blocking stream is not
     // ordered against: everything has landed before the caller can enqueue a step
     QPB_CUDA(cudaDeviceSynchronize());
@@ -843,7 +872,8 @@ static cudaError_t d2h_staged(void *dst, const void *dsrc, size_t bytes, cudaStr
         for (int b = 0; b < 2; ++b) {
             cudaError_t e = cudaHostAlloc(&g_stage_pin[b], kStageChunk, cudaHostAllocPortable);
             if (e != cudaSuccess) {
-                g_stage_pin[0] = nullptr;
+                if (b == 1) cudaFreeHost(g_stage_pin[0]);
+                g_stage_pin[0] = g_stage_pin[1] = nullptr;
                 return e;
             }
         }
@@ -851,7 +881,10 @@ static cudaError_t d2h_staged(void *dst, const void *dsrc, size_t bytes, cudaStr
     cudaEvent_t ev[2];   // events belong to the current device: made per call, the pinned chunks are portable
     for (int b = 0; b < 2; ++b) {
         cudaError_t e = cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming);
-        if (e != cudaSuccess) return e;
+        if (e != cudaSuccess) {
+            if (b == 1) cudaEventDestroy(ev[0]);
+            return e;
+        }
     }
     cudaError_t rc = cudaSuccess;
     const size_t nchunk = (bytes + kStageChunk - 1) / kStageChunk;
@@ -1206,13 +1239,23 @@ extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, 
     }
     const int gmode = gen ? gen->mode : QPB_GEN_NONE;
     if (gmode == QPB_GEN_ARRAY) {
-        if (nsteps > 1 || !gen->array) {
-            qpb_set_error("qpb_advance: array generation needs nsteps == 1 and a non-null array");
+        if (!gen->array) {
+            qpb_set_error("qpb_advance: array generation needs a non-null array");
             return QPB_E_INVALID;
         }
         const size_t n = (size_t)cf.ne * cf.ncell;
         if (!c->d_gen) QPB_ALLOC(c->d_gen, n);
+        c->gen_resident = false;
         QPB_CUDA(cudaMemcpyAsync(c->d_gen, gen->array, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        c->gen_resident = true;
+    } else if (gmode == QPB_GEN_RESIDENT) {
+        if (!c->d_gen || !c->gen_resident) {
+            qpb_set_error("qpb_advance: no generation array is resident (run a QPB_GEN_ARRAY batch first)");
+            return QPB_E_INVALID;
+        }
+    } else if (gmode < QPB_GEN_NONE || gmode > QPB_GEN_RESIDENT) {
+        qpb_set_error("qpb_advance: unknown generation mode %d", gmode);
+        return QPB_E_INVALID;
     }
     if (pauli && nsteps > c->pauli_cap) {
         dev_free(c->d_pauli);
@@ -1235,7 +1278,7 @@ extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, 
         } else if (gmode == QPB_GEN_PULSE) {
             if (gen->pulse_start <= t && t < gen->pulse_start + gen->pulse_duration)  // solver.py:914
                 if ((rc = qpbk_add_generation(c, dt, gen->rate, nullptr)) != QPB_OK) return rc;
-        } else if (gmode == QPB_GEN_ARRAY) {
+        } else if (gmode == QPB_GEN_ARRAY || gmode == QPB_GEN_RESIDENT) {
             if ((rc = qpbk_add_generation(c, dt, 0.0, c->d_gen)) != QPB_OK) return rc;
         }
         if (coll && diff) {  // solver.py:1469-1472

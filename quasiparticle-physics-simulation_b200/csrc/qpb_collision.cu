@@ -357,6 +357,7 @@ int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin) {
     const auto &cf = c->cfg;
     const bool scat = cf.flags & QPB_F_SCATTERING, rec = cf.flags & QPB_F_RECOMBINATION;
     c->uniform_ph = false;
+    c->gemm_ready = false;
     if (!(cf.flags & QPB_F_FREEZE_PHONONS) || !(scat || rec) || cf.ngap != 1 || !n_ph || !c->have_coll) return QPB_OK;
     if (getenv("QPB_NO_UNIFORM") && getenv("QPB_NO_UNIFORM")[0] == '1') return QPB_OK;
     const int ne = cf.ne, nw = cf.nw;
@@ -407,6 +408,7 @@ int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin) {
     QPB_CUDA(cudaMemcpy(c->d_K4, K4.data(), sizeof(double) * K4.size(), cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMemcpy(c->d_K4 + K4.size(), rhop.data(), sizeof(double) * nep, cudaMemcpyHostToDevice));
     c->uniform_ph = true;
+    c->h_ph_bins = ph;
     // ---- tensor-core form (qpb_collide_gemm.cuh) where the bin count makes the products a real GEMM ----
     if (c->d_Mg) qpb_dev_free(c->d_Mg);
     if (c->d_Xn) qpb_dev_free(c->d_Xn);

@@ -86,7 +86,7 @@ __global__ void k_build_rhs(int ne, int ny, int nx, const double *__restrict__ S
 
 // One thread per (bin, line).  mode 0: PR sweep along x, 1: PR sweep along y, 2: direct solve along `dir`.
 template <bool VARD>
-__global__ void k_sweep_generic(int ne, int ny, int nx, int dir, int mode, int iter, double tol,
+__global__ void k_sweep_generic(int ne, int ny, int nx, int dir, int mode, int iter, const double *__restrict__ tol,
                                 double *__restrict__ S, const double *__restrict__ B, double *__restrict__ T1,
                                 double *__restrict__ T2, const uint8_t *__restrict__ flags,
                                 const double *__restrict__ bcx, const double *__restrict__ bcy,
@@ -112,7 +112,7 @@ __global__ void k_sweep_generic(int ne, int ny, int nx, int dir, int mode, int i
         if (mode == 1) {
             const double r = __longlong_as_double((long long)res[(long long)iter * ne + bin]);
             const double un = __longlong_as_double((long long)unorm[(long long)iter * ne + bin]);
-            if (r <= tol * un) {  // the input of this iteration already satisfies the system
+            if (r <= tol[bin] * un) {  // the input of this iteration already satisfies the system
                 if (line == 0) {
                     done[bin] = 1;
                     iters_out[bin] = iter;
@@ -217,7 +217,7 @@ int qpbk_sweep_generic(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode) {
     const long long total = (long long)cf.ne * nlines;
     const int threads = 128;
     const int blocks = (int)ceil_div64(total, threads);
-    const double tol = cf.diff_tol;
+    const double *tol = s.d_tol;
     ScopedTimer tm(c, dir == 0 ? 0 : 1);
     if (vard)
         k_sweep_generic<true><<<blocks, threads, 0, c->stream>>>(

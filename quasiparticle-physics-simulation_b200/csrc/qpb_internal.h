@@ -64,6 +64,7 @@ struct DiffSlot {
     double *d_a = nullptr;     // [ne]
     double *d_shift = nullptr; // [ne][jmax]
     int *d_jlen = nullptr;     // [ne]
+    double *d_tol = nullptr;   // [ne] residual tolerance per bin: the requested one, floored at what fp64 can resolve
     int *d_known = nullptr;    // [ne] iterations the previous solve needed per bin (0: unknown)
     // variable-D coefficient fields (dense, per bin): links to the left / up neighbour, boundary diagonals
     double *d_ex = nullptr, *d_ey = nullptr, *d_gbx = nullptr, *d_gby = nullptr;
@@ -105,6 +106,7 @@ struct qpb_ctx {
     bool thin_x = false, thin_y = false;  // no links along y / along x anywhere
     bool commuting = false;
     double gmax_x = 0.0, gmax_y = 0.0;    // Gershgorin bounds of -Lx, -Ly (grid units)
+    double gmin = 0.0;                    // lower Gershgorin bound of both (negative only with a negative Robin beta)
     // diffusion
     bool have_D = false;
     std::vector<double> h_D;          // [ne] or [ne][ncell]
@@ -131,6 +133,7 @@ struct qpb_ctx {
     double *d_P = nullptr;            // phonon state [nw][ncell]
     bool uniform_ph = false;          // frozen phonons, identical in every cell: packed effective kernels in d_K4
     double *d_K4 = nullptr;           // [nep][nep][4] + rho[nep]
+    std::vector<double> h_ph_bins;    // the per-bin occupations d_K4 / d_Mg were packed from (re-packed on a table upload)
     // tensor-core form of the same products (qpb_collide_gemm.cuh): 4 padded row-major matrices + rho, packed operands
     bool gemm_ready = false;
     double *d_Mg = nullptr, *d_Xn = nullptr, *d_Xp = nullptr;
@@ -153,6 +156,7 @@ struct qpb_ctx {
     size_t euler_bytes = 0;
     // generation array
     double *d_gen = nullptr;          // [ne][ncell]
+    bool gen_resident = false;        // d_gen holds the array of the last QPB_GEN_ARRAY batch
     // reductions
     double *d_integrated = nullptr;   // [ncell]
     qpb_pauli_rec *d_pauli = nullptr; // [capacity]

@@ -99,7 +99,7 @@ __device__ __forceinline__ double warp_carry(double A, double B, int q) {
 
 struct SweepArgs {
     int ne, ny, nx, iter, jmax;
-    double tol;
+    const double *tol;   // [ne]
     double *S;          // state u (dense)
     const double *B;    // rhs b
     double *T1;         // u*
@@ -175,7 +175,7 @@ __device__ __forceinline__ bool bin_active(const SweepArgs &A, int bin, int mode
     if (mode == 1) {
         const double r = __longlong_as_double((long long)A.res[(long long)A.iter * A.ne + bin]);
         const double un = __longlong_as_double((long long)A.unorm[(long long)A.iter * A.ne + bin]);
-        if (r <= A.tol * un) {
+        if (r <= A.tol[bin] * un) {
             if (leader) {
                 A.done[bin] = 1;
                 A.iters_out[bin] = A.iter;
@@ -869,7 +869,7 @@ int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode, bool c
     const DiffSlot::FastDir &fd = dir == 0 ? s.fx : s.fy;
     const int nlines = dir == 0 ? cf.ny : cf.nx;
     SweepArgs A;
-    A.ne = cf.ne; A.ny = cf.ny; A.nx = cf.nx; A.iter = iter; A.jmax = s.jmax; A.tol = cf.diff_tol;
+    A.ne = cf.ne; A.ny = cf.ny; A.nx = cf.nx; A.iter = iter; A.jmax = s.jmax; A.tol = s.d_tol;
     A.S = c->d_S; A.B = c->d_B; A.T1 = c->d_T1; A.flags = c->d_flags; A.bcx = c->d_bcx; A.bcy = c->d_bcy;
     A.a_bin = s.d_a; A.shift = s.d_shift; A.jlen = s.d_jlen;
     A.cls = fd.d_cls;

@@ -98,7 +98,7 @@ __device__ __forceinline__ double warp_carry(double A, double B, int q, int reac
 
 struct PipeArgs {
     int ne, ny, nx, iter, jmax;
-    double tol;
+    const double *tol;   // [ne]
     const double *cx, *cy;       // dense geometry doubles
     const uint8_t *flags;        // dense flag bytes (QPB_IN = 16)
     const double *a_bin, *shift;
@@ -151,7 +151,7 @@ __device__ __forceinline__ bool tile_active(const PipeArgs &A, int bin, bool lea
     if (MODE == 1 && bin_checks(A, bin)) {
         const double r = __longlong_as_double((long long)A.res[(long long)A.iter * A.ne + bin]);
         const double un = __longlong_as_double((long long)A.unorm[(long long)A.iter * A.ne + bin]);
-        if (r <= A.tol * un) {
+        if (r <= A.tol[bin] * un) {
             if (leader) {
                 A.iters_out[bin] = A.iter;
                 __threadfence();
@@ -1006,7 +1006,7 @@ int qpbp_sweep(qpb_ctx *c, DiffSlot &s, int dir, int iter, bool check) {
     const PipePlan &p = s.pipe;
     const DiffSlot::FastDir &fd = dir == 0 ? s.fx : s.fy;
     PipeArgs A;
-    A.ne = cf.ne; A.ny = cf.ny; A.nx = cf.nx; A.iter = iter; A.jmax = s.jmax; A.tol = cf.diff_tol;
+    A.ne = cf.ne; A.ny = cf.ny; A.nx = cf.nx; A.iter = iter; A.jmax = s.jmax; A.tol = s.d_tol;
     A.cx = c->d_cx; A.cy = c->d_cy; A.flags = c->d_flags;
     A.a_bin = s.d_a; A.shift = s.d_shift; A.jlen = s.d_jlen;
     A.cls = fd.d_cls;

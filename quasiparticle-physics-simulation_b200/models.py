@@ -89,3 +89,35 @@ class ExternalGenerationSpec:
             raise ValueError("External generation pulse rate must be non-negative.")
         if self.pulse_duration < 0:
             raise ValueError("External generation pulse_duration must be non-negative.")
+
+
+_FULL_BODY = "return np.exp(-((x-0.5)**2 + (y-0.5)**2) / 0.02) * np.exp(-E / 500.0)"
+
+
+@dataclass
+class InitialConditionSpec:
+    """Field names of qpsim/models.py:82-108 (the drop-in reads them by attribute, so the reference's own object works
+    as well): split spatial / energy profiles of the quasiparticles and the phonons, plus optional non-separable
+    bodies F(x, y, E, params)."""
+    spatial_kind: str = ""
+    spatial_params: dict[str, Any] = field(default_factory=dict)
+    spatial_custom_body: str = "return np.exp(-((x-0.5)**2 + (y-0.5)**2) / 0.02)"
+    spatial_custom_params: dict[str, Any] = field(default_factory=dict)
+    energy_kind: str = ""
+    energy_params: dict[str, Any] = field(default_factory=dict)
+    energy_custom_body: str = "return np.ones_like(E)"
+    energy_custom_params: dict[str, Any] = field(default_factory=dict)
+    qp_full_custom_enabled: bool = False
+    qp_full_custom_body: str = _FULL_BODY
+    qp_full_custom_params: dict[str, Any] = field(default_factory=dict)
+    phonon_spatial_kind: str = ""
+    phonon_spatial_params: dict[str, Any] = field(default_factory=dict)
+    phonon_spatial_custom_body: str = "return 1.0"
+    phonon_spatial_custom_params: dict[str, Any] = field(default_factory=dict)
+    phonon_energy_kind: str = ""
+    phonon_energy_params: dict[str, Any] = field(default_factory=dict)
+    phonon_energy_custom_body: str = "return np.ones_like(E)"
+    phonon_energy_custom_params: dict[str, Any] = field(default_factory=dict)
+    phonon_full_custom_enabled: bool = False
+    phonon_full_custom_body: str = _FULL_BODY
+    phonon_full_custom_params: dict[str, Any] = field(default_factory=dict)

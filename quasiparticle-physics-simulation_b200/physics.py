@@ -132,21 +132,22 @@ def phonon_frequency_map(E: np.ndarray):
 
 
 def integration_widths_from_centers(centers: np.ndarray, *, fallback_width: float = 1.0) -> np.ndarray:
-    """solver.py:87-109 (used for the phonon history integrals)."""
-    bins = np.asarray(centers, dtype=float).reshape(-1)
-    if bins.size == 0:
+    """Quadrature weight of every bin of a strictly increasing grid of bin centres: the distance between the midpoints
+    to its two neighbours, the outermost bins extended symmetrically about their centre (role of solver.py:87-109 for
+    the phonon history integrals; a single bin gets ``fallback_width``)."""
+    c = np.asarray(centers, dtype=float).ravel()
+    if c.size == 0:
         raise ValueError("centers must be non-empty.")
-    if bins.size == 1:
-        return np.array([float(fallback_width)], dtype=float)
-    if np.any(~np.isfinite(bins)):
+    if c.size == 1:
+        return np.full(1, float(fallback_width))
+    if not np.all(np.isfinite(c)):
         raise ValueError("centers must contain finite values.")
-    if np.any(np.diff(bins) <= 0):
+    gaps = np.diff(c)
+    if not np.all(gaps > 0):
         raise ValueError("centers must be strictly increasing.")
-    edges = np.empty(bins.size + 1, dtype=float)
-    edges[1:-1] = 0.5 * (bins[:-1] + bins[1:])
-    edges[0] = bins[0] - 0.5 * (bins[1] - bins[0])
-    edges[-1] = bins[-1] + 0.5 * (bins[-1] - bins[-2])
-    widths = np.diff(edges)
-    if np.any(widths <= 0):
+    mid = c[:-1] + 0.5 * gaps
+    walls = np.concatenate(([c[0] - 0.5 * gaps[0]], mid, [c[-1] + 0.5 * gaps[-1]]))
+    widths = walls[1:] - walls[:-1]
+    if not np.all(widths > 0):
         raise ValueError("Derived non-positive integration width from centers.")
     return widths

@@ -15,24 +15,9 @@ from typing import Any, Callable
 
 import numpy as np
 
-from . import capi, physics
+from . import capi, physics, userexpr
 from .geometry import compile_boundaries
 from .models import ExternalGenerationSpec, check_collision_solver
-
-
-def _reference_module(name: str):
-    """Host-only helpers the reference evaluates from user expressions (initial-condition specs, gap
-    expressions, custom generation bodies) are reused from the reference package when it is importable;
-    they are one-off Python evaluations outside the accelerated path."""
-    import importlib
-
-    try:
-        return importlib.import_module(f"qpsim.{name}")
-    except Exception as exc:  # pragma: no cover - depends on deployment
-        raise RuntimeError(
-            f"this option needs the reference's host-side module qpsim.{name} on sys.path "
-            f"(user-expression evaluation is not part of the accelerated path): {exc}"
-        ) from exc
 
 
 def reconstruct_field(mask: np.ndarray, values: np.ndarray) -> np.ndarray:
@@ -50,29 +35,43 @@ def _step_plan(dt: float, total_time: float):
     return full, rem, full + (1 if rem > 0.0 else 0)
 
 
-def _generation_args(spec, E_bins, n_cells, t, mask):
-    """Map an ExternalGenerationSpec to qpb_advance arguments for a run of steps starting at time t."""
-    if spec is None:
-        return dict(gen_mode=capi.GEN_NONE), True
-    mode = spec.mode.strip().lower()
-    if mode == "constant":
-        rate = float(spec.rate)
-        if not np.isfinite(rate):
+class _Generation:
+    """External generation (solver.py:878-964) as qpb_advance arguments.  ``constant`` / ``pulse`` are evaluated on the
+    device.  ``custom`` bodies are evaluated on the host by :mod:`userexpr`; a body that never names ``t`` is
+    evaluated once, uploaded with the first batch and stays resident (later batches: QPB_GEN_RESIDENT, any number of
+    steps); a time-dependent body is re-evaluated and uploaded for every step, as the reference does."""
+
+    def __init__(self, spec, E_bins, mask):
+        self.mode = "none" if spec is None else spec.mode.strip().lower()
+        self.spec = spec
+        self.custom = None
+        self.uploaded = False
+        self.uploads = 0
+        if self.mode == "constant" and not np.isfinite(float(spec.rate)):
             raise ValueError("External generation mode 'constant' produced non-finite values.")
-        return dict(gen_mode=capi.GEN_CONSTANT, rate=rate), True
-    if mode == "pulse":
-        rate = float(spec.pulse_rate)
-        if not np.isfinite(rate):
+        if self.mode == "pulse" and not np.isfinite(float(spec.pulse_rate)):
             raise ValueError("External generation mode 'pulse' produced non-finite values.")
-        return dict(gen_mode=capi.GEN_PULSE, rate=rate, pulse_start=float(spec.pulse_start),
-                    pulse_duration=float(spec.pulse_duration)), True
-    if mode == "custom":
-        ref = _reference_module("solver")
-        g = ref.evaluate_external_generation(spec, E_bins, n_cells, t, mask)
-        if g is None:
-            return dict(gen_mode=capi.GEN_NONE), False
-        return dict(gen_mode=capi.GEN_ARRAY, gen_array=g), False
-    return dict(gen_mode=capi.GEN_NONE), True
+        if self.mode == "custom":
+            self.custom = userexpr.CustomGeneration(spec, E_bins, mask)
+
+    @property
+    def one_step_batches(self) -> bool:
+        return self.custom is not None and self.custom.time_dependent
+
+    def advance_args(self, t: float) -> dict:
+        sp = self.spec
+        if self.mode == "constant":
+            return dict(gen_mode=capi.GEN_CONSTANT, rate=float(sp.rate))
+        if self.mode == "pulse":
+            return dict(gen_mode=capi.GEN_PULSE, rate=float(sp.pulse_rate), pulse_start=float(sp.pulse_start),
+                        pulse_duration=float(sp.pulse_duration))
+        if self.mode == "custom":
+            if self.uploaded and not self.custom.time_dependent:
+                return dict(gen_mode=capi.GEN_RESIDENT)
+            self.uploaded = True
+            self.uploads += 1
+            return dict(gen_mode=capi.GEN_ARRAY, gen_array=self.custom(t))
+        return dict(gen_mode=capi.GEN_NONE)
 
 
 class _PauliPolicy:
@@ -264,18 +263,11 @@ def run_2d_crank_nicolson(
     ne = int(num_energy_bins)
     custom_qp_state = None
     if initial_condition_spec is not None:
-        ic = _reference_module("initial_conditions")
-        custom_qp_state = ic.build_initial_qp_energy_state(mask=mask_b, E_bins=E_bins, spec=initial_condition_spec)
+        custom_qp_state = userexpr.initial_qp_state(mask_b, E_bins, initial_condition_spec)
     if precomputed is None and gap_expression.strip():
-        pre = _reference_module("precompute")
-        models = _reference_module("models")
-        params = models.SimulationParameters(
-            diffusion_coefficient=diffusion_coefficient, dt=dt, total_time=total_time, mesh_size=dx,
-            energy_gap=energy_gap, energy_min_factor=energy_min_factor, energy_max_factor=energy_max_factor,
-            num_energy_bins=num_energy_bins, dynes_gamma=dynes_gamma, gap_expression=gap_expression,
-            tau_0=tau_0, tau_s=tau_s_eff, tau_r=tau_r_eff, T_c=T_c, bath_temperature=bath_temperature,
-        )
-        precomputed = pre.precompute_arrays(mask_b, edges, edge_conditions, params, include_collision_kernels=False)
+        # what precompute_arrays(..., include_collision_kernels=False) hands the solver (solver.py:1105-1124)
+        precomputed = userexpr.precompute_from_gap_expression(gap_expression, mask_b, E_bins, energy_gap,
+                                                              diffusion_coefficient)
     has_pre = precomputed is not None
     nonuniform_gap = has_pre and not bool(precomputed.get("is_uniform", True))
     check_collision_solver(collision_solver)
@@ -293,10 +285,7 @@ def run_2d_crank_nicolson(
     # only materialised when somebody needs it; the device broadcasts the Nw values itself.
     phonon_state = None
     if initial_condition_spec is not None:
-        ic = _reference_module("initial_conditions")
-        phonon_state = ic.build_initial_phonon_energy_state(
-            mask=mask_b, omega_bins=omega_bins, spec=initial_condition_spec, bath_temperature=bath_temperature,
-        )
+        phonon_state, _ = userexpr.initial_phonon_state(mask_b, omega_bins, initial_condition_spec, bath_temperature)
     nw = int(omega_bins.size)
 
     # density of states and base kernels: one table per distinct gap value (solver.py:1203-1238 builds the same
@@ -448,20 +437,17 @@ def run_2d_crank_nicolson(
 
             current_time = 0.0
             step = 0
-            per_step_gen = (external_generation is not None
-                            and external_generation.mode.strip().lower() == "custom")
-            has_gen = external_generation is not None and external_generation.mode != "none"
+            generation = _Generation(external_generation, E_bins, mask_b)
             while step < total_steps:
                 nxt = min(((step // store_every) + 1) * store_every, total_steps)
                 if nxt > full_steps and step < full_steps:
                     nxt = full_steps
-                if per_step_gen:
+                if generation.one_step_batches:
                     nxt = step + 1
                 is_final = step >= full_steps
                 h = remainder_dt if is_final else dt
                 count = nxt - step
-                gen_kwargs, _ = (_generation_args(external_generation, E_bins, n, current_time, mask_b)
-                                 if has_gen else (dict(gen_mode=capi.GEN_NONE), True))
+                gen_kwargs = generation.advance_args(current_time)
                 recs = ctx.advance(count, h, slot=1 if is_final else 0, t_start=current_time, want_pauli=True,
                                    **gen_kwargs)
                 for k in range(count):
@@ -487,6 +473,7 @@ def run_2d_crank_nicolson(
             for th, _, _ in pending:
                 th.join()
         info.update(ctx.diag())
+        info["generation_uploads"] = generation.uploads
 
     limits = _color_limits(frames)
     if phonon_history_out is not None:

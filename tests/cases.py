@@ -168,6 +168,44 @@ def nonuniform_gap_case(ny=10, nx=14, ne=8, steps=3):
     return case
 
 
+def custom_mode_cases():
+    """User-expression options of the drop-in boundary (custom generation bodies, initial-condition specs, gap
+    expressions; reference call sites solver.py:918-962, 1094-1124, 1186-1196).  Recorded from the unmodified
+    reference by tests/golden/make_golden_custom.py into tests/golden/custom_modes.npz."""
+    mask = np.ones((12, 16), dtype=bool)
+    mask[4:7, 5:9] = False
+    mask[0, :2] = False
+    base = dict(
+        mask=mask, bc="mixed", initial_field=gaussian_field(mask, sigma=0.2), diffusion_coefficient=D0, dt=0.25,
+        total_time=1.35, dx=1.0, store_every=2, energy_gap=GAP, energy_min_factor=1.0, energy_max_factor=4.0,
+        num_energy_bins=10, weights=None, enable_diffusion=True, enable_recombination=True, enable_scattering=True,
+        dynes_gamma=GAMMA, tau_0=TAU, T_c=TC, bath_temperature=TBATH, generation=None,
+    )
+    out = []
+    out.append(dict(base, name="custom_gen_static", generation=dict(
+        mode="custom", custom_body="return params.get('a', 1e-8) * (1.0 + x) * np.exp(-(E - 180.0) / 200.0) * (y < 0.8)",
+        custom_params={"a": 3e-8})))
+    out.append(dict(base, name="custom_gen_timedep", store_every=3, generation=dict(
+        mode="custom", custom_body="params['a'] * np.exp(-t / 0.5) * np.where(E < 400.0, 1.0, 0.25) * (0.5 + y * x)",
+        custom_params={"a": 5e-8})))
+    out.append(dict(base, name="custom_gen_scalar_body", enable_diffusion=False, generation=dict(
+        mode="custom", custom_body="return 2e-8 if E < 300 else 0.0", custom_params={})))
+    out.append(dict(base, name="ic_full_custom", ic_spec=dict(
+        qp_full_custom_enabled=True,
+        qp_full_custom_body="return 1e-4 * (1 + np.exp(-((x-0.3)**2 + (y-0.6)**2) / 0.05)) * np.exp(-(E-180.0) / 90.0)",
+        phonon_spatial_kind="gaussian", phonon_spatial_params={"amplitude": 1.5, "x0": 0.6, "y0": 0.4, "sigma": 0.3},
+        phonon_energy_kind="custom", phonon_energy_custom_body="return params.get('s', 1.0) * np.exp(-E / 60.0)",
+        phonon_energy_custom_params={"s": 0.02})))
+    out.append(dict(base, name="ic_phonon_full_custom", enable_diffusion=False, ic_spec=dict(
+        phonon_full_custom_enabled=True,
+        phonon_full_custom_body="return 1e-3 * np.exp(-E / 100.0) * (1.0 + 0.5 * np.sin(3.0 * x) * y)",
+        phonon_energy_kind="bose_einstein", phonon_energy_params={"temperature": 0.3})))
+    for c in out:
+        c["bc"] = "reflective"      # no boundary sources: the generation bodies / initial states carry the run
+    out.append(dict(base, name="gap_expression_step", gap_expression="np.where(x > 0.5, 162.0, 180.0) + 3.0 * (y > 0.7)"))
+    return out
+
+
 def golden_cases():
     """The cases stored under tests/golden (small enough for the reference's Python loops)."""
     return [
@@ -209,7 +247,7 @@ def precomputed_for(case, physics_mod):
     return {"D_array": D, "gap_values": gv, "is_uniform": np.array(len(np.unique(gv)) == 1), "E_bins": E}
 
 
-def solver_kwargs(case, edges, bcs, gen_spec, physics_mod):
+def solver_kwargs(case, edges, bcs, gen_spec, physics_mod, ic_spec_cls=None):
     """Keyword arguments for run_2d_crank_nicolson (reference or drop-in)."""
     kw = dict(
         mask=case["mask"], edges=edges, edge_conditions=bcs, initial_field=case["initial_field"],
@@ -227,4 +265,8 @@ def solver_kwargs(case, edges, bcs, gen_spec, physics_mod):
     pre = precomputed_for(case, physics_mod)
     if pre is not None:
         kw["precomputed"] = pre
+    if case.get("ic_spec") is not None:
+        kw["initial_condition_spec"] = ic_spec_cls(**case["ic_spec"])
+    if case.get("gap_expression"):
+        kw["gap_expression"] = case["gap_expression"]
     return kw

@@ -209,3 +209,35 @@ def test_ensemble_runs_members_through_the_single_gpu_path():
         assert times == t2 and mass == m2
         np.testing.assert_array_equal(last, np.array(ef[-1]))
     assert len({tuple(r[1]) for r in res}) == 4   # the parameters matter
+
+
+# ---- robustness of the sweep iteration where the reference's direct solve has no such concept ------------------
+@pytest.mark.parametrize("alpha", [40.0, 2500.0])
+def test_stiff_steps_on_a_slotted_mask_converge_like_the_direct_solve(alpha):
+    """dt D / dx^2 in the tens to thousands (fine mesh, long step) on a non-commuting geometry: the residual test is
+    floored at what fp64 resolves and the cyclic shift set grows with log(hi/lo), so the iteration ends where the
+    reference's SuperLU solve simply returns."""
+    case = cases.meander_c2(ny=48, nx=48, ne=4, steps=2)
+    case.update(enable_recombination=False, enable_scattering=False, generation=None, dynes_gamma=0.0,
+                dt=2.0 * alpha / cases.D0, total_time=4.0 * alpha / cases.D0, store_every=1)
+    import helpers
+
+    got = helpers.run_dropin(case)
+    want = helpers.run_oracle(case)
+    assert helpers.norm_err(got["state"], want["state"]) <= 1e-9
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=1e-9)
+
+
+def test_negative_robin_coefficient_is_solved_or_refused_loudly():
+    mask, edges, _ = _geom(6, 9)
+    for beta, ok in ((-0.05, True), (-5.0, False)):
+        bcs = {e.edge_id: Q.BoundaryCondition(kind="robin", value=beta, aux_value=0.1) for e in edges}
+        field = cases.gaussian_field(mask, sigma=0.3)
+        args = (mask, edges, bcs, field, 1.0, 0.4, 0.8, 1.0)
+        if not ok:
+            with pytest.raises(Q.capi.QpbError, match="negative Robin"):
+                Q.run_2d_crank_nicolson(*args)
+            continue
+        _, frames, mass, *_ = Q.run_2d_crank_nicolson(*args)
+        res = O.run(mask, edges, bcs, field, 1.0, 0.4, 0.8, 1.0)
+        np.testing.assert_allclose(frames[-1][mask], res.state_frames[-1][0], rtol=1e-9)

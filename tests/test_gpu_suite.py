@@ -1,0 +1,103 @@
+"""CUDA drop-in against recordings of the UNMODIFIED reference at the sizes and on the inputs the reference itself
+tests (north_star: "a bit-for-tolerance match to qpsim.solver on all data/test_cases"):
+
+* all 28 runs of ``generate_test_suite()`` (qpsim/test_cases.py:1133-1178): 10 strip, 9 rectangle, 4 polygon donut,
+  3 recombination, 2 scattering cases (tests/golden/suite_cases.npz);
+* BASELINE configs[1] at full size, 256 x 256 meander x 128 bins, two steps (tests/golden/c2_full_256x256x128.npz);
+* BASELINE configs[0], 128 cells x 64 bins, 20 steps; the input of the reference's tests/test_mkid_crosscheck.py.
+
+Bar: element-wise 1e-9 (helpers.rel_err) on n(x,y,E) and 1e-9 on the total number.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import cases
+import helpers
+
+pytestmark = pytest.mark.gpu
+
+SUITE_IDS = helpers.suite_case_ids()
+
+
+@pytest.mark.parametrize("k", range(len(SUITE_IDS)), ids=SUITE_IDS)
+def test_dropin_matches_reference_validation_suite(k):
+    kw, want = helpers.load_suite_case(k)
+    got = helpers.run_suite_case_dropin(kw, want["keep"])
+    np.testing.assert_allclose(got["times"], want["times"], rtol=0, atol=1e-9)
+    helpers.assert_close(got["state"], want["state"], "field")
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL, atol=1e-300)
+
+
+def test_c2_full_size_two_steps_match_reference():
+    """256 x 256 x 128 exactly as bench.py runs it; the reference's answer after two full steps."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+
+    want = helpers.load_golden("c2_full_256x256x128")
+    case = bench.c2_case(steps=2)
+    got = helpers.run_dropin(case)
+    np.testing.assert_allclose(got["times"], want["times"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
+    bins, cells, ph_cells = want["bins"], want["cells"], want["ph_cells"]
+    helpers.assert_close(got["state"][:, bins, :], want["state_bins"], "n(E,cell), all cells of 4 bins")
+    helpers.assert_close(got["state"][:, :, cells], want["state_cells"], "n(E,cell), all bins of 2048 cells")
+    dE = (case["energy_max_factor"] - case["energy_min_factor"]) * case["energy_gap"] / case["num_energy_bins"]
+    helpers.assert_close((got["state"].sum(axis=1) * dE)[:, None, :], want["integrated"][:, None, :], "integrated field")
+    helpers.assert_close(got["phonons"][:, :, ph_cells], want["phonons_cells"], "n_ph", rtol=helpers.RTOL_PHONON)
+
+
+@pytest.mark.parametrize("name", ["c1_strip_128x64_20steps", "mkid_crosscheck_48x12"])
+def test_strip_runs_match_reference(name):
+    if name.startswith("c1"):
+        case = cases.strip_c1(steps=20, nx=128, ne=64)
+    else:
+        case = cases.strip_c1(steps=12, nx=48, ne=12)
+        case.update(tau_0=400.0, store_every=1)
+    want = helpers.load_golden(name)
+    got = helpers.run_dropin(case)
+    np.testing.assert_allclose(got["times"], want["times"], rtol=0, atol=1e-12)
+    helpers.assert_close(got["state"], want["state"], "n(E,cell)")
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
+    helpers.assert_close(got["phonons"], want["phonons"], "n_ph", rtol=helpers.RTOL_PHONON)
+
+
+CUSTOM = cases.custom_mode_cases()
+
+
+@pytest.mark.parametrize("case", CUSTOM, ids=[c["name"] for c in CUSTOM])
+def test_user_expression_options_match_reference(case):
+    """Custom generation bodies (resident when time independent, per-step uploads otherwise), initial-condition specs
+    and gap expressions through the drop-in, against the unmodified reference (solver.py:918-962, 1094-1124,
+    1186-1196; reference tests: tests/test_initial_condition_split.py:144-173, tests/test_regressions.py:435-499)."""
+    import qpsim_b200 as Q
+
+    gold = helpers.load_golden("custom_modes")
+    p = case["name"] + "/"
+    got = helpers.run_dropin(case)
+    np.testing.assert_allclose(got["times"], gold[p + "times"], rtol=0, atol=1e-12)
+    helpers.assert_close(got["state"], gold[p + "state"], "n(E,cell)")
+    np.testing.assert_allclose(got["mass"], gold[p + "mass"], rtol=helpers.RTOL)
+    helpers.assert_close(got["phonons"], gold[p + "phonons"], "n_ph", rtol=helpers.RTOL_PHONON)
+    info = Q.solver.last_run_info
+    if case["name"] == "custom_gen_static":
+        assert info["generation_uploads"] == 1          # evaluated and uploaded once, resident afterwards
+    if case["name"] == "custom_gen_timedep":
+        assert info["generation_uploads"] == info["steps_done"] == 6
+
+
+def test_unsafe_custom_generation_is_rejected():
+    """tests/test_regressions.py:501-525 of the reference."""
+    import qpsim_b200 as Q
+
+    mask = np.ones((1, 2), dtype=bool)
+    edges = Q.extract_edge_segments(mask)
+    bcs = {e.edge_id: Q.BoundaryCondition(kind="reflective") for e in edges}
+    gen = Q.ExternalGenerationSpec(mode="custom", custom_body="__import__('os').system('echo unsafe')")
+    with pytest.raises(ValueError):
+        Q.run_2d_crank_nicolson(mask=mask, edges=edges, edge_conditions=bcs, initial_field=np.zeros((1, 2)),
+                                diffusion_coefficient=6.0, dt=0.1, total_time=0.1, dx=1.0, energy_gap=180.0,
+                                energy_min_factor=1.0, energy_max_factor=3.0, num_energy_bins=8,
+                                enable_diffusion=False, external_generation=gen)

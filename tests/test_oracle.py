@@ -99,3 +99,17 @@ def test_oracle_euler_forms_match_reference_fixture(tag):
         O.euler_scattering_step(s, g[f"{tag}_Ks"], g[f"{tag}_rho"], dE, dt)
         O.euler_recombination_step(s, g[f"{tag}_Kr"], g[f"{tag}_G_therm"], dE, dt)
     np.testing.assert_allclose(s, g[f"{tag}_after_3_pairs"], rtol=1e-12, atol=0)
+
+
+SUITE_IDS = helpers.suite_case_ids()
+
+
+@pytest.mark.parametrize("k", range(len(SUITE_IDS)), ids=SUITE_IDS)
+def test_oracle_matches_reference_validation_suite(k):
+    """All 28 runs of the reference's generate_test_suite() (qpsim/test_cases.py:1133-1178), recorded from the
+    unmodified reference by tests/golden/make_golden_suite.py."""
+    kw, want = helpers.load_suite_case(k)
+    got = helpers.run_suite_case_oracle(kw, want["keep"])
+    np.testing.assert_allclose(got["times"], want["times"], rtol=0, atol=1e-9)
+    helpers.assert_close(got["state"], want["state"], "field", rtol=1e-11)
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=1e-11, atol=1e-300)
