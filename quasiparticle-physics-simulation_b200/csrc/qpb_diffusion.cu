@@ -14,41 +14,13 @@
 // This file holds the generic kernels (any mask, any boundary kinds, uniform or per-cell D): one thread per
 // line, pivots by division.  qpb_sweep_fast.cu holds the chunked, table-driven kernels used for uniform D.
 #include "qpb_internal.h"
+#include "qpb_faces.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 
 namespace {
-
-struct Faces {
-    double eL, eR, eU, eD;  // face couplings (already multiplied by dt/2/dx^2 and D)
-    double gbx, gby;        // boundary diagonal terms in x / y
-};
-
-template <bool VARD>
-__device__ __forceinline__ Faces load_faces(int c, int nx, unsigned fl, double a, const double *__restrict__ bcx,
-                                            const double *__restrict__ bcy, const double *__restrict__ ex,
-                                            const double *__restrict__ ey, const double *__restrict__ gbx,
-                                            const double *__restrict__ gby) {
-    Faces f;
-    if (VARD) {
-        f.eL = (fl & QPB_LK_L) ? ex[c] : 0.0;
-        f.eR = (fl & QPB_LK_R) ? ex[c + 1] : 0.0;
-        f.eU = (fl & QPB_LK_U) ? ey[c] : 0.0;
-        f.eD = (fl & QPB_LK_D) ? ey[c + nx] : 0.0;
-        f.gbx = gbx[c];
-        f.gby = gby[c];
-    } else {
-        f.eL = (fl & QPB_LK_L) ? a : 0.0;
-        f.eR = (fl & QPB_LK_R) ? a : 0.0;
-        f.eU = (fl & QPB_LK_U) ? a : 0.0;
-        f.eD = (fl & QPB_LK_D) ? a : 0.0;
-        f.gbx = a * bcx[c];
-        f.gby = a * bcy[c];
-    }
-    return f;
-}
 
 // b = (I + a L) u + dt*D*s       (solver.py:1440, 1451)
 template <bool VARD>
@@ -112,7 +84,8 @@ __global__ void k_sweep_generic(int ne, int ny, int nx, int dir, int mode, int i
         if (mode == 1) {
             const double r = __longlong_as_double((long long)res[(long long)iter * ne + bin]);
             const double un = __longlong_as_double((long long)unorm[(long long)iter * ne + bin]);
-            if (r <= tol[bin] * un) {  // the input of this iteration already satisfies the system
+            (void)un;
+            if (r <= 0.0) {  // the input of this iteration satisfies the system in every cell (componentwise bound)
                 if (line == 0) {
                     done[bin] = 1;
                     iters_out[bin] = iter;
@@ -150,16 +123,18 @@ __global__ void k_sweep_generic(int ne, int ny, int nx, int dir, int mode, int i
             const double uc = u[c];
             if (mode == 0) {
                 // cross operator on u, and the along-line operator for the residual
-                double cross = gc * uc;
-                if (eCm != 0.0) cross += eCm * (uc - u[c - sc]);
-                if (eCp != 0.0) cross += eCp * (uc - u[c + sc]);
+                const double au = fabs(uc);
+                double cross = gc * uc, wsum = (fabs(gc) + fabs(gl)) * au;
+                if (eCm != 0.0) { cross += eCm * (uc - u[c - sc]); wsum += eCm * (au + fabs(u[c - sc])); }
+                if (eCp != 0.0) { cross += eCp * (uc - u[c + sc]); wsum += eCp * (au + fabs(u[c + sc])); }
                 double along = gl * uc;
-                if (eM != 0.0) along += eM * (uc - u[c - sk]);
-                if (eP != 0.0) along += eP * (uc - u[c + sk]);
+                if (eM != 0.0) { along += eM * (uc - u[c - sk]); wsum += eM * (au + fabs(u[c - sk])); }
+                if (eP != 0.0) { along += eP * (uc - u[c + sk]); wsum += eP * (au + fabs(u[c + sk])); }
                 const double bc_ = b[c];
                 d = bc_ + (rho - 0.5) * uc - cross;
-                rmax = fmax(rmax, fabs(bc_ - uc - cross - along));
-                umax = fmax(umax, fabs(uc));
+                // componentwise stop test: excess of |b - A u| over tol (|A||u| + |b|) in this cell
+                rmax = fmax(rmax, fabs(bc_ - uc - cross - along) - tol[bin] * (fabs(bc_) + au + wsum));
+                umax = fmax(umax, au);
             } else if (mode == 1) {
                 d = t1[c] - uc;
             } else {
@@ -248,6 +223,7 @@ int qpbk_diffuse(qpb_ctx *c, DiffSlot &s) {
         c->diag.bin_sweeps += ne;
         return QPB_OK;
     }
+    if (s.krylov) return qpbk_diffuse_krylov(c, s);
     QPB_CUDA(cudaMemsetAsync(c->d_res, 0, sizeof(unsigned long long) * (size_t)c->maxit * ne, c->stream));
     QPB_CUDA(cudaMemsetAsync(c->d_unorm, 0, sizeof(unsigned long long) * (size_t)c->maxit * ne, c->stream));
     QPB_CUDA(cudaMemsetAsync(c->d_done, 0, sizeof(int) * 2 * (size_t)ne, c->stream));
@@ -278,9 +254,19 @@ int qpbk_diffuse(qpb_ctx *c, DiffSlot &s) {
         batch = 1;
     }
     if (!all) {
-        qpb_set_error("Crank-Nicolson sweep iteration did not reach tolerance %.3g in %d iterations", cf.diff_tol,
-                      c->maxit);
-        return QPB_E_NOCONV;
+        // The sweep iteration stalled (it has no convergence guarantee on non-commuting geometries): solve this and
+        // every later step of the slot with the preconditioned Krylov method, from b as the initial guess (the
+        // iterate may have grown without bound).
+        if (getenv("QPB_NO_KRYLOV") && getenv("QPB_NO_KRYLOV")[0] == '1') {
+            qpb_set_error("Crank-Nicolson sweep iteration did not reach tolerance %.3g in %d iterations", cf.diff_tol,
+                          c->maxit);
+            return QPB_E_NOCONV;
+        }
+        QPB_CUDA(cudaMemcpyAsync(c->d_S, c->d_B, sizeof(double) * (size_t)ne * c->ncd, cudaMemcpyDeviceToDevice,
+                                 c->stream));
+        s.krylov = true;
+        c->diag.sweeps += 2 * it;
+        return qpbk_diffuse_krylov(c, s);
     }
     if (const char *dbg = getenv("QPB_DEBUG_RES")) {   // residual history of the first and last bin (diagnostics)
         if (dbg[0] == '1') {

@@ -64,8 +64,11 @@ struct DiffSlot {
     double *d_a = nullptr;     // [ne]
     double *d_shift = nullptr; // [ne][jmax]
     int *d_jlen = nullptr;     // [ne]
-    double *d_tol = nullptr;   // [ne] residual tolerance per bin: the requested one, floored at what fp64 can resolve
+    double *d_tol = nullptr;   // [ne] componentwise residual tolerance per bin of the sweep iteration
+    double *d_tolk = nullptr;  // [ne] max-norm tolerance of the Krylov path, floored at what fp64 can resolve
     int *d_known = nullptr;    // [ne] iterations the previous solve needed per bin (0: unknown)
+    bool krylov = false;       // stiff non-commuting solve: preconditioned BiCGStab instead of the sweep iteration (qpb_krylov.cu)
+    double *d_kshift = nullptr; // [ne] shift sqrt(lo hi) of the line-solve preconditioner
     // variable-D coefficient fields (dense, per bin): links to the left / up neighbour, boundary diagonals
     double *d_ex = nullptr, *d_ey = nullptr, *d_gbx = nullptr, *d_gby = nullptr;
     // source term dt*D*s, dense [ncd] (uniform: multiplied by D_i on the fly) or [ne][ncd] (variable)
@@ -118,6 +121,8 @@ struct qpb_ctx {
     unsigned long long *d_unorm = nullptr; // [maxit][ne]
     int *d_done = nullptr;                 // [ne]
     int maxit = 0;
+    double *d_kry[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // BiCGStab vectors, dense [ne][ncd], allocated on first use
+    double *d_kry_small = nullptr;         // block partials + per-bin scalars of the same
     // collision
     bool have_coll = false;
     bool structured = false;          // Toeplitz/Hankel index maps, symmetric kernels
@@ -179,6 +184,8 @@ struct qpb_ctx {
 int qpbk_build_rhs(qpb_ctx *c, DiffSlot &s);
 int qpbk_sweep_generic(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
 int qpbk_diffuse(qpb_ctx *c, DiffSlot &s);
+int qpbk_diffuse_krylov(qpb_ctx *c, DiffSlot &s);   // A u = b, b in d_B, guess/result in d_S
+void qpbk_free_krylov(qpb_ctx *c);
 int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s);
 int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode, bool check = true);
 int qpbp_chunk(int n, int dir);

@@ -175,7 +175,8 @@ __device__ __forceinline__ bool bin_active(const SweepArgs &A, int bin, int mode
     if (mode == 1) {
         const double r = __longlong_as_double((long long)A.res[(long long)A.iter * A.ne + bin]);
         const double un = __longlong_as_double((long long)A.unorm[(long long)A.iter * A.ne + bin]);
-        if (r <= A.tol[bin] * un) {
+        (void)un;
+        if (r <= 0.0) {   // no cell exceeded its componentwise bound (recorded by the x sweep)
             if (leader) {
                 A.done[bin] = 1;
                 A.iters_out[bin] = A.iter;
@@ -219,15 +220,18 @@ __global__ void __launch_bounds__(256) k_sweep_x(SweepArgs A) {
                 const double bc_ = b[c];
                 if (MODE == 0) {
                     const double uc = u[c];
+                    const double au = fabs(uc);
                     double cross = (fl & QPB_BCYNZ) ? A.bcy[c] * uc : 0.0;
-                    if (fl & QPB_LK_U) cross += uc - u[c - nx];
-                    if (fl & QPB_LK_D) cross += uc - u[c + nx];
+                    double wsum = ((fl & QPB_BCYNZ) ? fabs(A.bcy[c]) * au : 0.0) + ((fl & QPB_BCXNZ) ? fabs(A.bcx[c]) * au : 0.0);
+                    if (fl & QPB_LK_U) { cross += uc - u[c - nx]; wsum += au + fabs(u[c - nx]); }
+                    if (fl & QPB_LK_D) { cross += uc - u[c + nx]; wsum += au + fabs(u[c + nx]); }
                     double along = (fl & QPB_BCXNZ) ? A.bcx[c] * uc : 0.0;
-                    if (fl & QPB_LK_L) along += uc - u[c - 1];
-                    if (fl & QPB_LK_R) along += uc - u[c + 1];
+                    if (fl & QPB_LK_L) { along += uc - u[c - 1]; wsum += au + fabs(u[c - 1]); }
+                    if (fl & QPB_LK_R) { along += uc - u[c + 1]; wsum += au + fabs(u[c + 1]); }
                     d = fma(rho - 0.5, uc, bc_) - a * cross;
-                    rmax = fmax(rmax, fabs(bc_ - uc - a * (cross + along)));
-                    umax = fmax(umax, fabs(uc));
+                    // componentwise stop test: excess of |b - A u| over tol (|A||u| + |b|) in this cell
+                    rmax = fmax(rmax, fabs(bc_ - uc - a * (cross + along)) - A.tol[bin] * (fabs(bc_) + au + a * wsum));
+                    umax = fmax(umax, au);
                 } else {
                     d = bc_;
                 }
@@ -397,6 +401,7 @@ k_sweep_x_tma(SweepArgs A, const __grid_constant__ TmaMaps maps) {
     Chunk<S> ch;
     ch.a = a;
     double rmax = 0.0, umax = 0.0;
+    const double tolb = A.tol[bin];
     {
         // chunk linear index inside a tile decides the swizzle phase: unit' = unit ^ ((row*Q + q) & 7)
         const int rb = g * Q + qc;            // b tile / output tile
@@ -428,22 +433,23 @@ k_sweep_x_tma(SweepArgs A, const __grid_constant__ TmaMaps maps) {
                     const double u0 = uc[t];
                     const double uu = h == 0 ? tu.x : tu.y, ud = h == 0 ? td.x : td.y, bv = h == 0 ? tb.x : tb.y;
                     const double left = t == 0 ? ul : uc[t - 1], right = t == S - 1 ? ur : uc[t + 1];
-                    double cross = 0.0, along = 0.0;
-                    if (fl & QPB_LK_U) cross += u0 - uu;
-                    if (fl & QPB_LK_D) cross += u0 - ud;
-                    if (fl & QPB_LK_L) along += u0 - left;
-                    if (fl & QPB_LK_R) along += u0 - right;
+                    const double au = fabs(u0);
+                    double cross = 0.0, along = 0.0, wsum = 0.0;
+                    if (fl & QPB_LK_U) { cross += u0 - uu; wsum += au + fabs(uu); }
+                    if (fl & QPB_LK_D) { cross += u0 - ud; wsum += au + fabs(ud); }
+                    if (fl & QPB_LK_L) { along += u0 - left; wsum += au + fabs(left); }
+                    if (fl & QPB_LK_R) { along += u0 - right; wsum += au + fabs(right); }
                     if (fl & (QPB_BCXNZ | QPB_BCYNZ)) {
                         const size_t c = (size_t)yc * nx + qc * S + t;
-                        if (fl & QPB_BCYNZ) cross = fma(A.bcy[c], u0, cross);
-                        if (fl & QPB_BCXNZ) along = fma(A.bcx[c], u0, along);
+                        if (fl & QPB_BCYNZ) { cross = fma(A.bcy[c], u0, cross); wsum = fma(fabs(A.bcy[c]), au, wsum); }
+                        if (fl & QPB_BCXNZ) { along = fma(A.bcx[c], u0, along); wsum = fma(fabs(A.bcx[c]), au, wsum); }
                     }
                     const bool in = (fl & QPB_IN) && rowok;
                     const double d = fma(rho - 0.5, u0, bv) - a * cross;
                     ch.v[t] = in ? d : 0.0;
-                    if (in) {
-                        rmax = fmax(rmax, fabs(bv - u0 - a * (cross + along)));
-                        umax = fmax(umax, fabs(u0));
+                    if (in) {   // componentwise stop test: excess of |b - A u| over tol (|A||u| + |b|) in this cell
+                        rmax = fmax(rmax, fabs(bv - u0 - a * (cross + along)) - tolb * (fabs(bv) + au + a * wsum));
+                        umax = fmax(umax, au);
                     }
                 }
             }

@@ -151,7 +151,8 @@ __device__ __forceinline__ bool tile_active(const PipeArgs &A, int bin, bool lea
     if (MODE == 1 && bin_checks(A, bin)) {
         const double r = __longlong_as_double((long long)A.res[(long long)A.iter * A.ne + bin]);
         const double un = __longlong_as_double((long long)A.unorm[(long long)A.iter * A.ne + bin]);
-        if (r <= A.tol[bin] * un) {
+        (void)un;
+        if (r <= 0.0) {   // no cell exceeded its componentwise bound (recorded by the x sweep)
             if (leader) {
                 A.iters_out[bin] = A.iter;
                 __threadfence();
@@ -428,6 +429,7 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
             if (q == 0) ul = 0.0;
             if (q == QP - 1) ur = 0.0;
             const double rm = rho - 0.5, rp = rho + 0.5;
+            const double tolb = chk ? A.tol[bin] : 0.0;
 #pragma unroll
             for (int un = 0; un < UPC; ++un) {
                 const double2 tu = pu[(ubase + un) ^ swu], td = pd[(ubase + un) ^ swd], tb = pb[(ubase + un) ^ swb];
@@ -442,8 +444,13 @@ k_sweep_x_pipe(PipeArgs Ain, const __grid_constant__ XMaps maps) {
                     const double d = fma(-a, cross, fma(rm, u0, bv));      // b - (V - rho) u
                     ch.v[tt] = d;
                     if (chk) {
+                        // componentwise stop test (Oettli-Prager): |b - A u|_i <= tol (|A||u| + |b|)_i in every cell; what
+                        // is recorded is the largest excess over that bound, 0 when the bin has converged
                         const double rres = fma(-a, along, fma(-rp, u0, d));   // b - A u
-                        const int rh = __double2hiint(rres) & 0x7fffffff;
+                        const double nb = (fabs(left) + fabs(right)) + (fabs(uu) + fabs(ud));
+                        const double wgt = fabs(bv) + fma(a, nb, fma(a, cx[tt] + cy[tt], 1.0) * fabs(u0));
+                        const double ex = fma(-tolb, wgt, fabs(rres));
+                        const int rh = ex > 0.0 ? __double2hiint(ex) : 0;
                         if (flw[tt >> 2] & (16u << (8 * (tt & 3)))) rhi = max(rhi, rh);
                         uhi = max(uhi, __double2hiint(u0) & 0x7fffffff);
                     }

@@ -241,3 +241,17 @@ def test_negative_robin_coefficient_is_solved_or_refused_loudly():
         _, frames, mass, *_ = Q.run_2d_crank_nicolson(*args)
         res = O.run(mask, edges, bcs, field, 1.0, 0.4, 0.8, 1.0)
         np.testing.assert_allclose(frames[-1][mask], res.state_frames[-1][0], rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["c2_meander_40x40x12", "nonuniform_10x14x8", "annulus_32x5_mixed"])
+def test_krylov_solve_reproduces_the_reference_fixtures(name, monkeypatch):
+    """The preconditioned BiCGStab path (stiff steps) forced on at ordinary step lengths: same fixtures, same bar -
+    uniform D on a slotted mask, per-cell D (non-uniform gap), all five boundary kinds with a remainder step."""
+    import helpers
+
+    monkeypatch.setenv("QPB_KRYLOV_RATIO", "0")
+    case = next(c for c in cases.golden_cases() if c["name"] == name)
+    want = helpers.load_golden(name)
+    got = helpers.run_dropin(case)
+    helpers.assert_close(got["state"], want["state"], "n(E,cell)")
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=1e-9)

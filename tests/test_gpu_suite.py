@@ -28,7 +28,12 @@ def test_dropin_matches_reference_validation_suite(k):
     got = helpers.run_suite_case_dropin(kw, want["keep"])
     np.testing.assert_allclose(got["times"], want["times"], rtol=0, atol=1e-9)
     helpers.assert_close(got["state"], want["state"], "field")
-    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL, atol=1e-300)
+    # total number to 1e-9 of the number of quasiparticles present (the antisymmetric eigenmodes of the suite sum to
+    # zero up to rounding: a tolerance relative to that sum itself would compare noise)
+    ne = want["state"].shape[1]
+    dE = 1.0 if ne == 1 or kw["energy_gap"] <= 0 else (kw["energy_max_factor"] - kw["energy_min_factor"]) * kw["energy_gap"] / ne
+    present = float(np.max(np.sum(np.abs(want["state"]), axis=(1, 2)))) * dE * kw["dx"] ** 2
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL, atol=helpers.RTOL * present)
 
 
 def test_c2_full_size_two_steps_match_reference():
