@@ -443,6 +443,213 @@ def init_process_group(backend: str | None = None):
 
 
 # ------------------------------------------------------------------------------------------------------------
+# run_2d_crank_nicolson(..., devices=[...]): the sharded loop behind the drop-in
+# ------------------------------------------------------------------------------------------------------------
+def _gather_rows(local, plan: ShardPlan, dst: int = 0, group=None):
+    """[rows, N_g] device tensors of all ranks -> host [rows, N] on rank `dst` (None elsewhere).  One block travels at
+    a time, so the receiver never holds more than one rank's slice on the device."""
+    import torch
+    import torch.distributed as dist
+
+    if plan.world == 1:
+        return local.cpu().numpy().copy()
+    rows = local.shape[0]
+    if plan.rank != dst:
+        dist.send(local.contiguous(), dst=dst, group=group)
+        return None
+    out = np.empty((rows, plan.ncell))
+    for g in range(plan.world):
+        c0, c1 = plan.cells(g)
+        if g == dst:
+            out[:, c0:c1] = local.cpu().numpy()
+        else:
+            buf = torch.empty((rows, c1 - c0), dtype=local.dtype, device=local.device)
+            dist.recv(buf, src=g, group=group)
+            out[:, c0:c1] = buf.cpu().numpy()
+    return out
+
+
+def _run_spmd(su: dict, progress_callback=None) -> dict:
+    """The loop of solver.run_2d_crank_nicolson (energy-resolved mode) on the ranks of the current process group.
+    Called by every rank with identical arguments; rank r drives su["devices"][r]."""
+    import torch
+    import torch.distributed as dist
+
+    from .solver import reconstruct_field, _callback
+    from . import physics
+
+    rank, world = dist.get_rank(), dist.get_world_size()
+    device = int(su["devices"][rank])
+    mask, ne, n, nw = su["mask"], su["ne"], su["n"], su["nw"]
+    gen = su["generation"]
+    gmode = "none" if gen is None else gen.mode.strip().lower()
+    if gmode == "custom":
+        raise ValueError("external_generation mode 'custom' is not available with devices=[...]; run it on one device")
+    plan = ShardPlan(ne, n, world, rank, interleave=True)
+    c0, c1 = plan.cells()
+    coll = su["scattering"] or su["recombination"]
+    state_local = (su["state"][:, c0:c1] if su["state"] is not None
+                   else su["weights"][:, None] * su["spatial"][None, c0:c1])
+    prob = ShardedProblem(
+        mask=mask, bcx=su["bcx"], bcy=su["bcy"], src=su["src"], dx=su["dx"], dE=su["dE"], D=np.asarray(su["D"]),
+        variable_D=su["variable_D"], rho=su["rho"], Kr=su["Kr"], Ks=su["Ks"], gap_id=su["gap_id"],
+        idx_diff=su["idx_diff"], idx_sum=su["idx_sum"], sign=su["sign"], nw=nw, state=None,
+        phonons=su["phonon_state"], diffusion=su["diffusion"], scattering=su["scattering"],
+        recombination=su["recombination"], freeze_phonons=su["freeze_phonons"], pauli_floor=su["pauli_floor"],
+        diff_tol=su["diff_tol"], state_local=np.ascontiguousarray(state_local),
+        phonon_bins=su["phonon_bins"] if su["phonon_state"] is None else None)
+    dt, rem = su["dt"], su["remainder_dt"]
+    stages = DeviceStages(plan, prob, device, dt, rem)
+    policy = su["policy"]
+    try:
+        fused = stages.enable_fused_exchange(prob)
+        with torch.cuda.stream(stages.stream):
+            stepper = ShardedStepper(plan, stages, diffusion=su["diffusion"], collisions=coll)
+            dev = stages.coll_state.device
+            dE, dx = su["dE"], su["dx"]
+            ph_view = None
+            if coll and nw > 0:
+                pptr, _ = stages.ctx_c.device_ptr(1)
+                ph_view = torch.as_tensor(_DevArray(pptr, (nw, plan.ncells())), device=dev)
+            widths = (physics.integration_widths_from_centers(su["omega_bins"], fallback_width=dE)
+                      if su["want_phonon_history"] else None)
+
+            def integrated_all():
+                mine = torch.as_tensor(stages.ctx_c.get_integrated(), device=dev)
+                if world == 1:
+                    return mine.cpu().numpy()
+                nmax = max(plan.ncells(g) for g in range(world))
+                pad = torch.zeros(nmax, dtype=mine.dtype, device=dev)
+                pad[:mine.numel()] = mine
+                parts = [torch.empty_like(pad) for _ in range(world)]
+                dist.all_gather(parts, pad)
+                return np.concatenate([parts[g][:plan.ncells(g)].cpu().numpy() for g in range(world)])
+
+            times, frames, mass, eframes = [0.0], [], [], []
+            ph_frames, ph_eframes = [], []
+
+            def store(t):
+                integ = integrated_all()
+                frame = reconstruct_field(mask, integ)
+                frames.append(frame)
+                mass.append(float(np.sum(integ) * dx * dx))
+                if su["store_energy_frames"]:
+                    full = _gather_rows(stages.coll_state, plan)
+                    eframes.append(None if full is None else [reconstruct_field(mask, full[i]) for i in range(ne)])
+                else:
+                    eframes.append(None)
+                if su["want_phonon_history"]:
+                    if ph_view is not None:
+                        ph = _gather_rows(ph_view, plan)
+                    elif rank == 0:   # collisions off: the phonons stay what they were initialised to
+                        ph = (np.asarray(su["phonon_state"], dtype=float) if su["phonon_state"] is not None
+                              else su["phonon_bins"][:, None] * np.ones((1, n)))
+                    else:
+                        ph = None
+                    if ph is not None:
+                        ph_eframes.append([reconstruct_field(mask, ph[i]) for i in range(ph.shape[0])])
+                        ph_frames.append(reconstruct_field(mask, np.sum(ph * widths[:, None], axis=0)))
+                _callback(progress_callback, float(t), frame)
+
+            rec0 = stepper.merge_pauli([stages.pauli()])[0]
+            policy.check(rec0, 0, 0.0)
+            store(0.0)
+            full_steps, total_steps, store_every = su["full_steps"], su["total_steps"], su["store_every"]
+            t, step = 0.0, 0
+            while step < total_steps:
+                nxt = min(((step // store_every) + 1) * store_every, total_steps)
+                if nxt > full_steps and step < full_steps:
+                    nxt = full_steps
+                is_final = step >= full_steps
+                h = rem if is_final else dt
+                count = nxt - step
+                tt = t
+                for k in range(count):
+                    rate = None
+                    if gmode == "constant":
+                        rate = float(gen.rate)
+                    elif gmode == "pulse" and gen.pulse_start <= tt < gen.pulse_start + gen.pulse_duration:
+                        rate = float(gen.pulse_rate)
+                    stepper.step(h, 1 if is_final else 0, rate, pauli_slot=k)
+                    tt += h
+                merged = stepper.merge_pauli(stages.pauli_fetch(count))
+                for k in range(count):
+                    policy.check(merged[k], step + k + 1, t + h)
+                    t += h
+                step = nxt
+                if step % store_every == 0 or step == total_steps:
+                    times.append(float(t))
+                    store(t)
+            info = dict(stages.ctx_c.diag())
+            info.update(world=world, fused_exchange=bool(fused), exchanges=stepper.exchanges,
+                        exchange_bytes_per_gpu=plan.exchange_bytes())
+            if stages.ctx_d is not None:
+                d = stages.ctx_d.diag()
+                info.update({k: d[k] for k in ("sweeps", "bin_sweeps", "pr_iterations", "sweep_path", "commuting")})
+                info["kernel_launches"] += d["kernel_launches"]
+            torch.cuda.synchronize()
+    finally:
+        stages.close()
+    hist = None
+    if su["want_phonon_history"] and rank == 0:
+        hist = {"phonon_frames": ph_frames, "phonon_energy_frames": ph_eframes,
+                "phonon_energy_bins": np.asarray(su["omega_bins"], dtype=float).copy(),
+                "phonon_metadata": {"mode": "dynamic_local_coupled", "field_units": "integrated_occupation",
+                                    "energy_frame_units": "occupation"}}
+    return {"times": times, "frames": frames, "mass": mass,
+            "energy_frames": eframes if (rank == 0 and su["store_energy_frames"]) else [None] * len(times),
+            "phonon_history": hist, "info": info}
+
+
+def _spawn_worker(rank: int, world: int, setup: dict, port: int, outpath: str):
+    import pickle
+
+    import torch
+    import torch.distributed as dist
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    dev = int(setup["devices"][rank])
+    torch.cuda.set_device(dev)
+    dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{dev}"))
+    try:
+        out = _run_spmd(setup, None)
+        if rank == 0:
+            with open(outpath, "wb") as f:
+                pickle.dump(out, f, protocol=5)
+    finally:
+        dist.destroy_process_group()
+
+
+def run_dropin(setup: dict, progress_callback=None) -> dict:
+    """Entry point of run_2d_crank_nicolson(devices=[...]).  Inside an initialised process group (torchrun) the call
+    is collective: every rank runs its share.  From a plain process one worker per device is spawned for the duration
+    of the call (rendezvous on 127.0.0.1) and rank 0's result is handed back; progress callbacks are not forwarded
+    across that boundary."""
+    import torch.distributed as dist
+
+    world = len(setup["devices"])
+    if dist.is_available() and dist.is_initialized():
+        if dist.get_world_size() != world:
+            raise ValueError(f"devices lists {world} GPUs but the process group has {dist.get_world_size()} ranks")
+        return _run_spmd(setup, progress_callback)
+    import pickle
+    import socket
+    import tempfile
+
+    import torch.multiprocessing as mp
+
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    with tempfile.TemporaryDirectory() as tmp:
+        outpath = os.path.join(tmp, "result.pkl")
+        mp.spawn(_spawn_worker, args=(world, setup, port, outpath), nprocs=world, join=True)
+        with open(outpath, "rb") as f:
+            return pickle.load(f)
+
+
+# ------------------------------------------------------------------------------------------------------------
 # bench.py --gpus N
 # ------------------------------------------------------------------------------------------------------------
 def weak_tiling(world: int) -> tuple[int, int]:

@@ -176,17 +176,26 @@ def run_2d_crank_nicolson(
     progress_callback: Callable[[float, np.ndarray], None] | None = None,
     *,
     device: int = 0,
+    devices: list[int] | None = None,
     diffusion_tolerance: float = 0.0,
     store_energy_frames: bool = True,
 ):
-    """Same contract as the reference function; the three keyword-only extras select the GPU, the residual
-    tolerance of the Crank-Nicolson solve and (for benchmarks) allow skipping the NE full-frame copies."""
+    """Same contract as the reference function; the keyword-only extras select the GPU(s), the residual tolerance of
+    the Crank-Nicolson solve and (for benchmarks) allow skipping the NE full-frame copies.
+
+    ``devices=[g0, g1, ...]`` (energy-resolved mode) runs the loop sharded over several GPUs of one box: diffusion by
+    energy bin, collisions by cell (:mod:`multigpu`).  Under ``torchrun`` every rank makes the
+    same call and rank r drives ``devices[r]``; from a plain process the ranks are spawned for the duration of the
+    call.  Rank 0 (the caller, when spawned) gets the full result; the other ranks get the same ``times``, ``frames``,
+    ``mass`` and ``None`` in place of the per-energy frames."""
     if dt <= 0 or total_time <= 0:
         raise ValueError("dt and total_time must be positive.")
     if enable_diffusion and diffusion_coefficient <= 0:
         raise ValueError("Diffusion coefficient must be positive.")
     if store_every <= 0:
         store_every = 1
+    if devices is not None and len(devices) == 1:
+        device = int(devices[0])
     mask = np.asarray(mask)
     if initial_field.shape != mask.shape:
         raise ValueError("Initial field shape must match mask shape.")
@@ -357,6 +366,30 @@ def run_2d_crank_nicolson(
         flags |= capi.F_FREEZE_PHONONS
 
     want_ph_hist = phonon_history_out is not None
+    if devices is not None and len(devices) > 1:
+        from . import multigpu
+
+        setup = dict(
+            mask=mask_b, bcx=bcx, bcy=bcy, src=src, dx=dx, dE=dE, ne=ne, nw=nw, n=n, E_bins=E_bins,
+            omega_bins=omega_bins, D=D_array if nonuniform_gap else (D_array[:, 0] if D_array.ndim == 2 else D_array),
+            variable_D=bool(nonuniform_gap and enable_diffusion), rho=rho_tab, Kr=Kr_tab, Ks=Ks_tab, gap_id=gap_id,
+            idx_diff=idx_diff, idx_sum=idx_sum, sign=diff_sign, state=state,
+            weights=None if state is not None else weights, spatial=None if state is not None else spatial,
+            phonon_state=phonon_state, phonon_bins=n_ph_eq, diffusion=bool(enable_diffusion),
+            scattering=bool(enable_scattering), recombination=bool(enable_recombination),
+            freeze_phonons=bool(freeze_phonon_dynamics), pauli_floor=pauli_density_floor,
+            diff_tol=diffusion_tolerance, dt=dt, full_steps=full_steps, remainder_dt=remainder_dt,
+            total_steps=total_steps, store_every=store_every, generation=external_generation,
+            store_energy_frames=store_energy_frames, want_phonon_history=want_ph_hist, devices=list(devices),
+            policy=policy,
+        )
+        out = multigpu.run_dropin(setup, progress_callback)
+        info.update(out.pop("info", {}))
+        if phonon_history_out is not None and out.get("phonon_history") is not None:
+            phonon_history_out.clear()
+            phonon_history_out.update(out["phonon_history"])
+        frames = out["frames"]
+        return out["times"], frames, out["mass"], _color_limits(frames), out["energy_frames"], E_bins
     ph_frames: list = []
     ph_energy_frames: list = []
     ph_widths = physics.integration_widths_from_centers(omega_bins, fallback_width=dE) if want_ph_hist else None
