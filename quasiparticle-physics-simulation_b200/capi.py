@@ -210,6 +210,22 @@ def load_library():
     return lib
 
 
+# bytes that crossed PCIe through this binding, counted at the copy calls (bench.py reports them per step)
+transfer_stats = {"h2d": 0, "d2h": 0}
+
+
+def _up(*arrays):
+    for a in arrays:
+        if a is not None:
+            transfer_stats["h2d"] += int(a.nbytes)
+
+
+def _down(*arrays):
+    for a in arrays:
+        if a is not None:
+            transfer_stats["d2h"] += int(a.nbytes)
+
+
 def _ptr(arr):
     return None if arr is None else arr.ctypes.data_as(C.c_void_p)
 
@@ -261,11 +277,13 @@ class Context:
         if m.shape != (self.ny, self.nx):
             raise ValueError("mask shape does not match the context")
         arrs = [None if a is None else _f64(a, (self.ny, self.nx)) for a in (bcx, bcy, source)]
+        _up(m, *arrs)
         self._check(self.lib.qpb_upload_geometry(self.handle, _ptr(m), *[_ptr(a) for a in arrs]))
 
     def upload_diffusion(self, D):
         shape = (self.ne, self.ncell) if self.flags & F_VARIABLE_D else (self.ne,)
         d = _f64(D, shape)
+        _up(d)
         self._check(self.lib.qpb_upload_diffusion(self.handle, _ptr(d)))
 
     def prepare_diffusion(self, slot: int, dt: float):
@@ -280,6 +298,7 @@ class Context:
         idd = None if idx_diff is None else np.ascontiguousarray(idx_diff, dtype=np.int32).reshape(ne, ne)
         ids = None if idx_sum is None else np.ascontiguousarray(idx_sum, dtype=np.int32).reshape(ne, ne)
         sg = None if sign is None else np.ascontiguousarray(sign, dtype=np.int8).reshape(ne, ne)
+        _up(kr, ks, rh, gid, idd, ids, sg)
         self._check(self.lib.qpb_upload_collision(self.handle, _ptr(kr), _ptr(ks), _ptr(rh), _ptr(gid), _ptr(idd),
                                                   _ptr(ids), _ptr(sg)))
 
@@ -287,12 +306,14 @@ class Context:
     def set_state(self, n, n_ph=None):
         a = _f64(n, (self.ne, self.ncell))
         p = None if (n_ph is None or self.nw == 0) else _f64(n_ph, (self.nw, self.ncell))
+        _up(a, p)
         self._check(self.lib.qpb_set_state(self.handle, _ptr(a), _ptr(p)))
 
     def set_state_uniform_phonons(self, n, n_ph_bins):
         """State upload when every cell starts from the same phonon occupations (one value per phonon bin)."""
         a = _f64(n, (self.ne, self.ncell))
         p = None if self.nw == 0 else _f64(n_ph_bins, (self.nw,))
+        _up(a, p)
         self._check(self.lib.qpb_set_state_uniform_phonons(self.handle, _ptr(a), _ptr(p)))
 
     def set_state_separable(self, weights, spatial, n_ph_bins=None):
@@ -301,23 +322,27 @@ class Context:
         w = _f64(weights, (self.ne,))
         sp = _f64(spatial, (self.ncell,))
         p = None if self.nw == 0 else _f64(n_ph_bins, (self.nw,))
+        _up(w, sp, p)
         self._check(self.lib.qpb_set_state_separable(self.handle, _ptr(w), _ptr(sp), _ptr(p)))
 
     def get_state(self, want_phonons=True, want_qp=True):
         n = np.empty((self.ne, self.ncell)) if want_qp else None
         p = np.empty((self.nw, self.ncell)) if (want_phonons and self.nw > 0) else None
         self._check(self.lib.qpb_get_state(self.handle, _ptr(n), _ptr(p)))
+        _down(n, p)
         return n, p
 
     def get_integrated(self):
         out = np.empty(self.ncell)
         self._check(self.lib.qpb_get_integrated(self.handle, _ptr(out)))
+        _down(out)
         return out
 
     def get_frames(self):
         """The NE stored energy frames of one snapshot, (NE, ny, nx) with NaN outside the mask."""
         out = np.empty((self.ne, self.ny, self.nx))
         self._check(self.lib.qpb_get_frames(self.handle, _ptr(out)))
+        _down(out)
         return out
 
     def frames_snapshot(self):
@@ -331,6 +356,7 @@ class Context:
         if out is None:
             out = np.empty((self.ne, self.ny, self.nx))
         self._check(self.lib.qpb_frames_download(self.handle, _ptr(out)))
+        _down(out)
         return out
 
     # ---- stepping ------------------------------------------------------------------------------------
@@ -340,6 +366,7 @@ class Context:
         keep = None
         if gen_mode == GEN_ARRAY:
             keep = _f64(gen_array, (self.ne, self.ncell))
+            _up(keep)
             g.array = keep.ctypes.data
         recs = (PauliRec * max(1, int(nsteps)))() if want_pauli else None
         rc = self.lib.qpb_advance(self.handle, int(nsteps), float(dt), int(slot), float(t_start), C.byref(g),
@@ -347,6 +374,7 @@ class Context:
         self._check(rc)
         if recs is None:
             return None
+        transfer_stats["d2h"] += 24 * int(nsteps)
         return [(recs[k].max_occ, recs[k].max_index, recs[k].forbidden) for k in range(int(nsteps))]
 
     def collide(self, dt):

@@ -650,7 +650,7 @@ def run_dropin(setup: dict, progress_callback=None) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------------------
-# bench.py --gpus N
+# tilings of the weak-scaling workload (bench.py --workload c2 --gpus N)
 # ------------------------------------------------------------------------------------------------------------
 def weak_tiling(world: int) -> tuple[int, int]:
     """(tiles along y, tiles along x) of the per-GPU 256 x 256 mask: 1x1, 1x2, 2x2, 4x2.  Rows stay at most 512 cells
@@ -663,124 +663,3 @@ def weak_tiling(world: int) -> tuple[int, int]:
     while tx * 2 <= 2 and world % (tx * 2) == 0:
         tx *= 2
     return world // tx, tx
-
-
-def bench_main(args, make_workload, build_tables, ClockSampler, METRIC, UNIT, emit=None):
-    import json
-    import sys
-
-    import torch
-    import torch.distributed as dist
-
-    from . import compile_boundaries, extract_edge_segments, BoundaryCondition
-
-    sys.path.insert(0, os.path.join(capi.REPO_DIR, "tests"))
-    import cases
-
-    rank, world, local = init_process_group("nccl")
-    strong = getattr(args, "workload", "c2") != "c2"
-    if strong:   # a fixed large grid cut across the ranks (BASELINE configs[2]); ranks hold only their own cells
-        w = make_workload()
-    else:
-        ty, tx = weak_tiling(world)
-        w = make_workload(tile_y=ty, tile_x=tx)
-    mask = w["mask"]
-    n, ne = int(mask.sum()), w["num_energy_bins"]
-    plan = ShardPlan(ne, n, world, rank, interleave=True)
-    c0, c1 = plan.cells()
-    tabs = build_tables(w, cells=(c0, c1) if strong else None)
-    nw = int(tabs["omega"].size)
-    edges = extract_edge_segments(mask)
-    bcs = cases.make_bcs(edges, w["bc"], BoundaryCondition)
-    bcx, bcy, src = compile_boundaries(mask, edges, bcs, w["dx"])
-    prob = ShardedProblem(mask=mask, bcx=bcx, bcy=bcy, src=src, dx=w["dx"], dE=tabs["dE"], D=tabs["D"],
-                          variable_D=False, rho=tabs["rho"][None], Kr=tabs["Kr"][None], Ks=tabs["Ks"][None],
-                          gap_id=None, idx_diff=tabs["idx_diff"], idx_sum=tabs["idx_sum"], sign=tabs["sign"], nw=nw,
-                          state=None if strong else tabs["state"], phonons=None if strong else tabs["phonons"],
-                          state_local=tabs["state"] if strong else None,
-                          phonon_bins=tabs["phonon_bins"] if strong else None)
-    K, W = args.steps, args.warmup
-    dt = w["dt"]
-    stages = DeviceStages(plan, prob, local, dt)
-    fused = stages.enable_fused_exchange(prob)
-    gen_on = w.get("pulse_rate") is not None
-    with torch.cuda.stream(stages.stream):
-        stepper = ShardedStepper(plan, stages, diffusion=True, collisions=True)
-
-        def rate_at(t):
-            if not gen_on:
-                return None
-            return w["pulse_rate"] if w["pulse_start"] <= t < w["pulse_start"] + w["pulse_duration"] else None
-
-        t = 0.0
-        for _ in range(W):
-            stepper.step(dt, 0, rate_at(t), want_pauli=True)
-            t += dt
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        l0 = stages.launches()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stages.stream)
-        for k in range(K):
-            stepper.step(dt, 0, rate_at(t), pauli_slot=k)   # occupancy record per step on the device
-            t += dt
-        e1.record(stages.stream)
-        torch.cuda.synchronize()
-        dist.barrier()
-        torch.cuda.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        clocks = sampler.stop() if rank == 0 else None
-        launches = stages.launches() - l0
-        recs = stages.pauli_fetch(K)
-        merged = stepper.merge_pauli(recs)
-        sweeps = stages.ctx_d.diag()["sweeps"] / max(1, K + W)
-        # ---- end to end: host state in, K steps, host integrated field out (rank-local slices) ----
-        import time
-
-        dist.barrier()
-        t0 = time.perf_counter()
-        stages.load_state(prob)
-        t = 0.0
-        for k in range(K):
-            stepper.step(dt, 0, rate_at(t), pauli_slot=k)
-            t += dt
-        stages.pauli_fetch(K)
-        integ = stages.ctx_c.get_integrated()
-        dist.barrier()
-        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        assert np.all(np.isfinite(integ))
-    ms_total = float(ms.item())
-    if rank == 0:
-        nloc = plan.ncells()
-        ph_bytes = 8 * nw if strong else 8 * nw * nloc
-        line = {
-            "metric": METRIC, "value": n * ne * K / (ms_total * 1e-3), "unit": UNIT, "n_gpus": world, "steps": K,
-            "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
-            "scaling": "strong" if strong else "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "cells": n, "energy_bins": ne, "phonon_bins": nw, "dt_ns": dt,
-                       "parallelism": (f"bins/{world} (diffusion) <-> cells/{world} (collisions), "
-                                       + ("exchange fused into the collision kernel over NVLink peer memory, "
-                                          "3 stream-ordered barriers per step" if fused
-                                          else "NCCL all-to-all x2 per step")),
-                       "exchange_bytes_per_gpu": plan.exchange_bytes(),
-                       "sweeps_per_step": sweeps,
-                       "l2": "per-GPU state + phonons + work arrays exceed the 126 MB L2"},
-            "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": n * ne * K / float(t_e2e.item()), "unit": UNIT,
-                    "h2d_bytes_per_step": (8 * ne * nloc + ph_bytes) / K, "d2h_bytes_per_step": 8 * nloc / K,
-                    "note": "per rank: host state+phonons upload, K sharded steps, integrated field download"},
-            "max_occupation": max(r[0] for r in merged),
-        }
-        if emit is not None:
-            emit(line)
-        else:
-            print(json.dumps(line))
-    stages.close()
-    dist.destroy_process_group()
