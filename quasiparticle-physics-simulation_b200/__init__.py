@@ -34,7 +34,8 @@ from .solver import (  # noqa: F401
     reconstruct_field,
     run_2d_crank_nicolson,
 )
-from . import capi, userexpr  # noqa: F401
+from . import capi, output, userexpr  # noqa: F401
+from .output import frame_to_jsonable, frames_to_jsonable, load_result, save_result  # noqa: F401
 from .ensemble import parameter_grid, run_ensemble  # noqa: F401
 
 __all__ = [
@@ -44,4 +45,5 @@ __all__ = [
     "apply_scattering_step", "apply_recombination_step",
     "BoundaryCondition", "BoundaryFace", "EdgeSegment", "ExternalGenerationSpec", "InitialConditionSpec", "BoundaryAssignmentError",
     "extract_edge_segments", "compile_boundaries", "build_energy_grid", "capi", "run_ensemble", "parameter_grid",
+    "frame_to_jsonable", "frames_to_jsonable", "save_result", "load_result",
 ]
