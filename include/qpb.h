@@ -77,7 +77,9 @@ typedef struct qpb_diag {
                                 library's stream, first launch to last kernel)                          */
     int32_t sweep_path;      /* kernels of the prepared CN solve: 0 generic (one thread per line), 1 chunked table
                                 kernels, 2 persistent TMA-pipelined kernels (x and y), 3 the same with lines cut
-                                into overlapping segments (lines longer than 512 cells)                  */
+                                into overlapping segments (lines longer than 512 cells), 4 direct spectral
+                                solve (cosine transform along x + one tridiagonal solve along y per mode: full
+                                rectangles with reflective left / right walls)                          */
     int32_t reserved;
 } qpb_diag;
 

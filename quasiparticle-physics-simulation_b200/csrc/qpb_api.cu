@@ -185,6 +185,11 @@ void qpbk_free_slot(DiffSlot &s) {
     dev_free(s.d_tol);
     dev_free(s.d_tolk);
     dev_free(s.d_kshift);
+    dev_free(s.d_sp_tw);
+    dev_free(s.d_sp_tw2);
+    dev_free(s.d_sp_lam);
+    dev_free(s.d_sp_bcy);
+    s.spectral = false;
     dev_free(s.d_known);
     dev_free(s.d_ex);
     dev_free(s.d_ey);
@@ -252,7 +257,7 @@ extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
     lap("set device");
     qpb_ctx *c = new qpb_ctx();
     c->cfg = *cfg;
-    if (!(c->cfg.diff_tol > 0.0)) c->cfg.diff_tol = 2e-13;   // componentwise: see qpb_prepare_diffusion
+    if (!(c->cfg.diff_tol > 0.0)) c->cfg.diff_tol = 5e-14;   // componentwise: see qpb_prepare_diffusion
     c->ncd = cfg->ny * cfg->nx;
     c->maxit = 512;
     auto fail = [&](int rc) {
@@ -669,8 +674,8 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
     // cell.  A max-norm test ||b - Au|| <= tol ||u|| leaves cells far below the bin's peak unconstrained (boundary
     // sources next to a cold interior, lognormal fields): measured on such a case the element-wise error still fell
     // from 1e-7 to 1e-12 while the max-norm residual sat at its rounding floor.  The componentwise residual tracks the
-    // element-wise relative error of the solution (within 10x on masks, 1000x on the first step from a rough field),
-    // so tol = 2e-13 keeps every cell within the 1e-9 bar.  Its rounding floor is a few ulps whatever alpha is.
+    // element-wise relative error of the solution (within 10x on masks, up to a few 1000x on the first steps from a
+    // rough field), so tol = 5e-14 keeps every cell within the 1e-9 bar.  Its rounding floor is a few ulps whatever alpha is.
     // d_tolk is the max-norm tolerance of the Krylov path (qpb_krylov.cu), floored at the fp64 resolution of a
     // residual whose terms are (1 + 2 max row sum of alpha*G) |u| large.
     std::vector<double> tolb(ne), tolk(ne);
@@ -696,11 +701,12 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
     if (!vard) {
         int rc = qpbk_prepare_fast(c, s);
         if (rc != QPB_OK) return rc;
+        if ((rc = qpbk_prepare_spectral(c, s)) != QPB_OK) return rc;
     }
     QPB_CUDA(cudaDeviceSynchronize());   // blocking legacy-stream copies of the table setup (see qpb_upload_collision)
     c->diag.direct_mode = s.mode != 0;
     c->diag.commuting = s.commuting;
-    c->diag.sweep_path = !s.fast ? 0
+    c->diag.sweep_path = s.spectral ? 4 : !s.fast ? 0
                          : !(s.pipe.x_ok && s.pipe.y_ok) ? 1
                          : (s.pipe.x_nseg > 1 || s.pipe.y_nseg > 1) ? 3 : 2;
     return QPB_OK;

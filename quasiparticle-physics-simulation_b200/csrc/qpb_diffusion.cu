@@ -223,6 +223,7 @@ int qpbk_diffuse(qpb_ctx *c, DiffSlot &s) {
         c->diag.bin_sweeps += ne;
         return QPB_OK;
     }
+    if (s.spectral) return qpbk_diffuse_spectral(c, s);
     if (s.krylov) return qpbk_diffuse_krylov(c, s);
     QPB_CUDA(cudaMemsetAsync(c->d_res, 0, sizeof(unsigned long long) * (size_t)c->maxit * ne, c->stream));
     QPB_CUDA(cudaMemsetAsync(c->d_unorm, 0, sizeof(unsigned long long) * (size_t)c->maxit * ne, c->stream));

@@ -67,6 +67,11 @@ struct DiffSlot {
     double *d_tol = nullptr;   // [ne] componentwise residual tolerance per bin of the sweep iteration
     double *d_tolk = nullptr;  // [ne] max-norm tolerance of the Krylov path, floored at what fp64 can resolve
     int *d_known = nullptr;    // [ne] iterations the previous solve needed per bin (0: unknown)
+    // direct spectral solve on full rectangles with reflective left / right walls (qpb_spectral.cu)
+    bool spectral = false;
+    int sp_logn = 0;
+    double2 *d_sp_tw = nullptr, *d_sp_tw2 = nullptr;   // exp(-2 pi i k / nx), exp(-i pi k / (2 nx))
+    double *d_sp_lam = nullptr, *d_sp_bcy = nullptr;   // eigenvalues of Gx [nx], wall diagonal of every row [ny]
     bool krylov = false;       // stiff non-commuting solve: preconditioned BiCGStab instead of the sweep iteration (qpb_krylov.cu)
     double *d_kshift = nullptr; // [ne] shift sqrt(lo hi) of the line-solve preconditioner
     // variable-D coefficient fields (dense, per bin): links to the left / up neighbour, boundary diagonals
@@ -184,6 +189,8 @@ struct qpb_ctx {
 int qpbk_build_rhs(qpb_ctx *c, DiffSlot &s);
 int qpbk_sweep_generic(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode);
 int qpbk_diffuse(qpb_ctx *c, DiffSlot &s);
+int qpbk_prepare_spectral(qpb_ctx *c, DiffSlot &s);
+int qpbk_diffuse_spectral(qpb_ctx *c, DiffSlot &s);  // A u = b directly, b in d_B, result in d_S
 int qpbk_diffuse_krylov(qpb_ctx *c, DiffSlot &s);   // A u = b, b in d_B, guess/result in d_S
 void qpbk_free_krylov(qpb_ctx *c);
 int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s);

@@ -88,13 +88,15 @@ def _cn_residual(u_old, u_new, a):
     return np.max(np.abs((u_new - a * lap(u_new)) - (u_old + a * lap(u_old))), axis=(1, 2))
 
 
+@pytest.mark.parametrize("solver", ["spectral", "sweeps"])
 @pytest.mark.parametrize("shape", [(2048, 2048, 256, 3.0, 0.2), (1024, 1024, 512, 10.0, 0.05)],
                          ids=["C3_2048x2048", "C4_1024x1024"])
-def test_large_grid_diffusion_solves_the_cn_system(shape):
+def test_large_grid_diffusion_solves_the_cn_system(shape, solver, monkeypatch):
     """BASELINE configs[2] and [3]: the full grids, the four bins of the named energy grid with the largest and
     smallest diffusion coefficients (bins are independent solves).  The result must satisfy the reference's unsplit
-    Crank-Nicolson equations to the solver tolerance, conserve the number exactly (reflective walls) and take the
-    segmented pipelined kernels."""
+    Crank-Nicolson equations to the solver tolerance and conserve the number exactly (reflective walls) - on the
+    direct spectral solve these grids take by default and on the segmented pipelined sweeps (QPB_NO_SPECTRAL=1)."""
+    monkeypatch.setenv("QPB_NO_SPECTRAL", "0" if solver == "spectral" else "1")
     ny, nx, ne_full, fmax, dt = shape
     t = _tables(ne_full, fmax)
     bins = [1, 2, ne_full - 2, ne_full - 1]
@@ -116,7 +118,7 @@ def test_large_grid_diffusion_solves_the_cn_system(shape):
     scale = np.max(np.abs(u1), axis=1)
     assert np.all(res <= 4e-12 * scale), (res / scale)
     np.testing.assert_allclose(u1.sum(axis=1), u0.sum(axis=1), rtol=1e-12)
-    assert info["sweep_path"] == 3, info
+    assert info["sweep_path"] == (4 if solver == "spectral" else 3), info
 
 
 @pytest.mark.parametrize("cfg", [(256, 3.0, 8192, 192), (512, 10.0, 2048, 64)], ids=["C3_NE256", "C4b_NE512"])

@@ -389,3 +389,71 @@ def test_snapshot_download_overlaps_stepping_and_matches_get_frames():
         assert np.array_equal(box["frames"], want, equal_nan=True)
         assert not np.array_equal(after, want, equal_nan=True)
         assert np.array_equal(want[:, mask], state) and np.all(np.isnan(want[:, ~mask]))
+
+
+def _walls_by_normal(edges, kinds):
+    out = {}
+    for e in edges:
+        kind, val, aux = kinds[e.normal]
+        out[e.edge_id] = Q.BoundaryCondition(kind=kind, value=val, aux_value=aux)
+    return out
+
+
+@pytest.mark.parametrize("shape", [(48, 64), (33, 128), (70, 256), (20, 1024)])
+@pytest.mark.parametrize("walls", ["reflective", "mixed_y"])
+def test_spectral_direct_solve_matches_oracle(shape, walls, monkeypatch):
+    """Full rectangles whose left / right walls are reflective (or carry a flux) take the direct solve: cosine
+    transform along x, one tridiagonal system along y per mode (qpb_spectral.cu).  Any wall kind on top / bottom,
+    odd row counts, sources.  Same run with the sweep iteration (QPB_NO_SPECTRAL=1): both within the bar."""
+    ny, nx = shape
+    mask = np.ones((ny, nx), dtype=bool)
+    edges = Q.extract_edge_segments(mask)
+    if walls == "reflective":
+        kinds = {k: ("reflective", None, None) for k in ("up", "down", "left", "right")}
+    else:
+        kinds = {"up": ("absorbing", None, None), "down": ("robin", 0.7, 0.2), "left": ("reflective", None, None),
+                 "right": ("neumann", 0.05, None)}
+    bcs = _walls_by_normal(edges, kinds)
+    field = cases.lognormal_field(mask, seed=3, scale=1e-4)
+    kw = dict(mask=mask, edges=edges, edge_conditions=bcs, initial_field=field, diffusion_coefficient=cases.D0, dt=0.4,
+              total_time=1.0, dx=1.0, store_every=1, energy_gap=cases.GAP, energy_min_factor=1.0,
+              energy_max_factor=3.0, num_energy_bins=5, enable_diffusion=True, dynes_gamma=cases.GAMMA,
+              enforce_pauli=False)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, _, mass, _, ef, _ = Q.run_2d_crank_nicolson(**kw)
+        info = dict(Q.solver.last_run_info)
+        monkeypatch.setenv("QPB_NO_SPECTRAL", "1")
+        _, _, mass_pr, _, ef_pr, _ = Q.run_2d_crank_nicolson(**kw)
+        info_pr = dict(Q.solver.last_run_info)
+    assert info["sweep_path"] == 4 and info_pr["sweep_path"] != 4
+    res = O.run(mask, edges, bcs, field, cases.D0, 0.4, 1.0, 1.0, store_every=1, gap=cases.GAP, fmin=1.0, fmax=3.0,
+                ne=5, gamma=cases.GAMMA)
+    want = np.array(res.state_frames)
+    got = np.array([[f[mask] for f in t] for t in ef])
+    got_pr = np.array([[f[mask] for f in t] for t in ef_pr])
+    helpers.assert_close(got, want, "spectral n(E,cell)")
+    helpers.assert_close(got_pr, want, "sweep-iteration n(E,cell)")
+    np.testing.assert_allclose(mass, res.mass, rtol=helpers.RTOL)
+
+
+def test_spectral_path_is_not_taken_where_it_does_not_apply():
+    """A wall term on the left, a wall kind that changes along the top wall, a hole, a row length that is not a power of
+    two: all stay with the sweep iteration (and still match, see the other tests)."""
+    def path(mask, kinds=None, custom=None):
+        edges = Q.extract_edge_segments(mask)
+        bcs = custom(edges) if custom else _walls_by_normal(edges, kinds)
+        Q.run_2d_crank_nicolson(mask=mask, edges=edges, edge_conditions=bcs, initial_field=np.where(mask, 1e-4, 0.0),
+                                diffusion_coefficient=6.0, dt=0.5, total_time=0.5, dx=1.0, energy_gap=180.0,
+                                energy_max_factor=3.0, num_energy_bins=3)
+        return Q.solver.last_run_info["sweep_path"]
+
+    refl = {k: ("reflective", None, None) for k in ("up", "down", "left", "right")}
+    full = np.ones((32, 64), dtype=bool)
+    assert path(full, refl) == 4
+    assert path(full, dict(refl, left=("absorbing", None, None))) != 4
+    assert path(np.ones((32, 80), dtype=bool), refl) != 4
+    holed = full.copy()
+    holed[10:12, 20:30] = False
+    assert path(holed, custom=lambda edges: {e.edge_id: Q.BoundaryCondition(kind="reflective") for e in edges}) != 4
