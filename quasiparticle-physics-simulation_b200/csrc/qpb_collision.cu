@@ -212,7 +212,7 @@ static int struct_cells_per_cta(int nep) {
                (size_t)(nt / 32) * (32 / cc) * NSTAGE * (TI * TJ * 16);
     };
     if (need(32, 512) <= cap) return 32;
-    if (need(16, 256) <= cap) return 16;
+    if (need(16, 512) <= cap) return 16;
     if (need(8, 256) <= cap) return 8;
     if (need(4, 128) <= cap) return 4;
     return 0;
@@ -309,7 +309,10 @@ int qpbk_collision_setup(qpb_ctx *c) {
 
 template <int CC>
 struct StructCfg {
-    static constexpr int NT = CC >= 32 ? 512 : (CC >= 8 ? 256 : 128);
+    // 16 cells per CTA (256 / 384 bins) run with 16 warps as well: two warp slots per row block keep every slot busy in
+    // one round of each pass and give each scheduler four warps to hide the FP64 latency with (ncu at 256 bins with
+    // 8 warps: 12.5 % warps active, top stall "wait")
+    static constexpr int NT = CC >= 16 ? 512 : (CC >= 8 ? 256 : 128);
     static size_t smem(int nep) {
         return sizeof(double) * (size_t)CC * (2 * (nep + PADF + PADB) + 3 * nep) +
                (size_t)(NT / 32) * (32 / CC) * NSTAGE * (TI * TJ * 16);
