@@ -408,18 +408,23 @@ def load_profile_traffic(tag):
 
 
 def rooflines(n_sweep_cells, ncd, ne, n_coll_cells, tx, ty, nsweep_launches, bin_sweeps, tc, ncoll, peaks, peak_src,
-              fp64_peak, traffic):
+              fp64_peak, traffic, sweep_path=2):
     """HBM roofline of the sweeps (algorithmic 16 B per mask cell, bin and directional sweep) and FP64 roofline of the
     collision kernel (21 NE^2 flop per cell and call with dynamic phonons), from per-kernel event times."""
     sweep_ms = tx + ty
     rs = {"bound": "hbm", "achieved": 16.0 * n_sweep_cells * bin_sweeps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0,
           "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": traffic.get("sweep"),
           "traffic_source": "committed ncu capture (profiles/), not this run" if traffic.get("sweep") else None,
-          "kernel": "k_sweep_x_pipe + k_sweep_y_pipe (tridiagonal line sweeps)", "launches": int(nsweep_launches),
+          "kernel": ("k_dct_forward + k_thomas_frozen + k_dct_inverse (direct spectral solve: three passes per bin)"
+                     if sweep_path == 4 else "k_sweep_x_pipe + k_sweep_y_pipe (tridiagonal line sweeps)"),
+          "launches": int(nsweep_launches),
           "ms_per_launch": sweep_ms / max(1, nsweep_launches), "peak_source": peak_src}
     rs["frac"] = rs["achieved"] / rs["peak"]
-    rs["implementation"] = {"bytes_per_dense_cell_bin_sweep": 24, "dense_cells": int(ncd),
-                            "achieved": 24.0 * ncd * bin_sweeps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0,
+    # what the kernels move per dense cell, bin and pass: sweeps 24 B (x: u, b in, u* out; y: u*, u in, u out); the
+    # spectral passes 16 B each (read and write the bin once)
+    impl = 16 if sweep_path == 4 else 24
+    rs["implementation"] = {"bytes_per_dense_cell_bin_sweep": impl, "dense_cells": int(ncd),
+                            "achieved": impl * ncd * bin_sweeps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0,
                             "unit": "GB/s"}
     rs["implementation"]["frac"] = rs["implementation"]["achieved"] / rs["peak"]
     flops = 21.0 * ne * ne * n_coll_cells * ncoll
@@ -693,7 +698,8 @@ def run_sharded(args, strong: bool):
     if rank == 0:
         coll_ms, sweep_ms, ser_step = (float(v) for v in parts.tolist())
         roof_sweep, roof_coll = rooflines(n, ny * nx, ne, nloc, tx, ty, nxl + nyl, bin_sweeps, tc, ncl, peaks,
-                                          peak_src, fp64_peak, load_profile_traffic("c3" if strong else "c2"))
+                                          peak_src, fp64_peak, load_profile_traffic("c3" if strong else "c2"),
+                                          sweep_path=dd1["sweep_path"])
         roof_coll["scope"] = f"rank 0: {nloc} of {n} cells, all bins"
         roof_sweep["scope"] = f"rank 0: {plan.nbins()} of {ne} bins, all cells"
         dominant = roof_coll if coll_ms >= sweep_ms else roof_sweep

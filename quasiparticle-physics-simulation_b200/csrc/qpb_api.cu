@@ -189,6 +189,8 @@ void qpbk_free_slot(DiffSlot &s) {
     dev_free(s.d_sp_tw2);
     dev_free(s.d_sp_lam);
     dev_free(s.d_sp_bcy);
+    dev_free(s.d_sp_piv);
+    s.sp_T = 0;
     s.spectral = false;
     dev_free(s.d_known);
     dev_free(s.d_ex);

@@ -72,6 +72,9 @@ struct DiffSlot {
     int sp_logn = 0;
     double2 *d_sp_tw = nullptr, *d_sp_tw2 = nullptr;   // exp(-2 pi i k / nx), exp(-i pi k / (2 nx))
     double *d_sp_lam = nullptr, *d_sp_bcy = nullptr;   // eigenvalues of Gx [nx], wall diagonal of every row [ny]
+    double *d_sp_piv = nullptr;                        // [ne][sp_T][nx] first pivots of the Thomas pass (sp_T = 0: none)
+    int sp_T = 0;
+    double sp_wall_last = 0.0;
     bool krylov = false;       // stiff non-commuting solve: preconditioned BiCGStab instead of the sweep iteration (qpb_krylov.cu)
     double *d_kshift = nullptr; // [ne] shift sqrt(lo hi) of the line-solve preconditioner
     // variable-D coefficient fields (dense, per bin): links to the left / up neighbour, boundary diagonals

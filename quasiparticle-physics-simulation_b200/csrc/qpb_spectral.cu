@@ -34,23 +34,48 @@ __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
 // spreads such a warp over all eight 128-byte bank groups and leaves runs of consecutive elements conflict free.
 __device__ __forceinline__ int slot(int e) { return e ^ ((e >> 6) & 7); }
 
-// in-place radix-2 decimation-in-time passes over z[0..N) (input in bit-reversed order).  tw is packed by stage:
-// tw[half + pos] = exp(-2 pi i pos / (2 half)) for pos < half (contiguous reads in every stage), conjugated for the
-// inverse transform
+// in-place decimation-in-time passes over z[0..N) (input in bit-reversed order), two radix-2 stages fused per trip
+// through shared memory (four elements in registers: half the passes and barriers of a plain radix-2 walk).  tw is
+// packed by stage: tw[half + pos] = exp(-2 pi i pos / (2 half)) for pos < half (contiguous reads in every stage),
+// conjugated for the inverse transform.
 template <bool INV>
 __device__ __forceinline__ void fft_passes(double2 *z, const double2 *tw, int N, int logN) {
-    for (int s = 0; s < logN; ++s) {
-        const int half = 1 << s;
+    int s = 0;
+    if (logN & 1) {   // odd number of stages: the first one (twiddle 1) on its own
         __syncthreads();
         for (int q = threadIdx.x; q < N / 2; q += blockDim.x) {
-            const int pos = q & (half - 1);
-            const int i = ((q >> s) << (s + 1)) + pos;
-            double2 w = tw[half + pos];
-            if (INV) w.y = -w.y;
-            const int ia = slot(i), ib = slot(i + half);
-            const double2 a = z[ia], t = cmul(w, z[ib]);
+            const int ia = slot(2 * q), ib = slot(2 * q + 1);
+            const double2 a = z[ia], t = z[ib];
             z[ia] = make_double2(a.x + t.x, a.y + t.y);
             z[ib] = make_double2(a.x - t.x, a.y - t.y);
+        }
+        s = 1;
+    }
+    for (; s < logN; s += 2) {
+        const int h = 1 << s;
+        __syncthreads();
+        for (int q = threadIdx.x; q < N / 4; q += blockDim.x) {
+            const int pos = q & (h - 1);
+            const int i0 = ((q >> s) << (s + 2)) + pos;
+            double2 w1 = tw[h + pos], w2 = tw[2 * h + pos];
+            if (INV) {
+                w1.y = -w1.y;
+                w2.y = -w2.y;
+            }
+            // twiddle of the second pair of the later stage: exp(-+ i pi / 2) times w2
+            const double2 w3 = INV ? make_double2(-w2.y, w2.x) : make_double2(w2.y, -w2.x);
+            const int s0 = slot(i0), s1 = slot(i0 + h), s2 = slot(i0 + 2 * h), s3 = slot(i0 + 3 * h);
+            const double2 a0 = z[s0], a1 = z[s1], a2 = z[s2], a3 = z[s3];
+            double2 t = cmul(w1, a1);
+            const double2 b0 = make_double2(a0.x + t.x, a0.y + t.y), b1 = make_double2(a0.x - t.x, a0.y - t.y);
+            t = cmul(w1, a3);
+            const double2 b2 = make_double2(a2.x + t.x, a2.y + t.y), b3 = make_double2(a2.x - t.x, a2.y - t.y);
+            t = cmul(w2, b2);
+            z[s0] = make_double2(b0.x + t.x, b0.y + t.y);
+            z[s2] = make_double2(b0.x - t.x, b0.y - t.y);
+            t = cmul(w3, b3);
+            z[s1] = make_double2(b1.x + t.x, b1.y + t.y);
+            z[s3] = make_double2(b1.x - t.x, b1.y - t.y);
         }
     }
     __syncthreads();
@@ -152,6 +177,62 @@ __global__ void k_thomas_modes(int ne, int ny, int N, double *__restrict__ v, do
     }
 }
 
+// Pivots of the Thomas recurrence do not depend on the data: m_0 = 1 / (d + a (1 + wall_0)), m_t = 1 / (d + 2a -
+// a^2 m_{t-1}) in the interior, d = 1 + a lam_k.  The recurrence contracts by (a m)^2 per row, so after T rows (T from
+// the slowest bin and mode, chosen on the host) m_t has reached its fixed point to below an ulp: the first T pivots of
+// every (bin, mode) go into a table once per prepared step length, every later row uses the last of them.
+__global__ void k_thomas_pivots(int T, int N, double *__restrict__ tab, const double *__restrict__ a_bin,
+                                const double *__restrict__ lam, double wall0) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int bin = blockIdx.y;
+    if (k >= N) return;
+    const double a = a_bin[bin];
+    const double d0 = fma(a, lam[k], 1.0);
+    double m = 1.0 / fma(a, 1.0 + wall0, d0);
+    double *col = tab + (size_t)bin * T * N + k;
+    col[0] = m;
+    for (int t = 1; t < T; ++t) {
+        m = 1.0 / fma(-a * a, m, fma(a, 2.0, d0));
+        col[(size_t)t * N] = m;
+    }
+}
+
+// The same solve as k_thomas_modes with the tabulated / frozen pivots: no division and no second array between the
+// passes - b^ in and y out on the way down, y in and u^ out on the way up (32 B per cell and bin).
+__global__ void k_thomas_frozen(int ny, int N, int T, double *__restrict__ v, const double *__restrict__ tab,
+                                const double *__restrict__ a_bin, const double *__restrict__ lam, double wall_last) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int bin = blockIdx.y;
+    if (k >= N) return;
+    const double a = a_bin[bin];
+    double *col = v + (size_t)bin * ny * N + k;
+    const double *piv = tab + (size_t)bin * T * N + k;
+    const double mf = piv[(size_t)(T - 1) * N];
+    const double m_last = 1.0 / fma(-a * a, mf, fma(a, 1.0 + wall_last, fma(a, lam[k], 1.0)));
+    double yp = 0.0;
+    for (int t = 0; t < T; ++t) {
+        yp = fma(a, yp, col[(size_t)t * N]) * piv[(size_t)t * N];
+        col[(size_t)t * N] = yp;
+    }
+#pragma unroll 8
+    for (int t = T; t < ny - 1; ++t) {
+        yp = fma(a, yp, col[(size_t)t * N]) * mf;
+        col[(size_t)t * N] = yp;
+    }
+    double xn = fma(a, yp, col[(size_t)(ny - 1) * N]) * m_last;
+    col[(size_t)(ny - 1) * N] = xn;
+    const double gf = a * mf;
+#pragma unroll 8
+    for (int t = ny - 2; t >= T - 1; --t) {
+        xn = fma(gf, xn, col[(size_t)t * N]);
+        col[(size_t)t * N] = xn;
+    }
+    for (int t = T - 2; t >= 0; --t) {
+        xn = fma(a * piv[(size_t)t * N], xn, col[(size_t)t * N]);
+        col[(size_t)t * N] = xn;
+    }
+}
+
 }  // namespace
 
 // Decide whether the prepared solve can take the spectral path and build its tables.
@@ -193,6 +274,31 @@ int qpbk_prepare_spectral(qpb_ctx *c, DiffSlot &s) {
     QPB_CUDA(cudaMemcpy(s.d_sp_lam, lam.data(), sizeof(double) * nx, cudaMemcpyHostToDevice));
     QPB_CUDA(cudaMemcpy(s.d_sp_bcy, bcy_row.data(), sizeof(double) * ny, cudaMemcpyHostToDevice));
     s.sp_logn = logN;
+    // Tabulated pivots of the Thomas pass (k_thomas_pivots): possible when only the first and last row carry a wall
+    // term.  T rows until the slowest pivot recurrence (mode 0 of the bin with the largest a) is within 1e-18 of its
+    // fixed point; past 128 rows (very stiff steps) or on short grids the pass keeps its on-the-fly form.
+    s.sp_T = 0;
+    bool interior_plain = true;
+    for (int y = 1; y < ny - 1; ++y) interior_plain = interior_plain && bcy_row[y] == 0.0;
+    if (interior_plain && !(getenv("QPB_NO_PIVOT_TABLE") && getenv("QPB_NO_PIVOT_TABLE")[0] == '1')) {
+        int T = 4;
+        for (int i = 0; i < cf.ne; ++i) {
+            const double a = s.a_bin[i], d = 1.0 + 2.0 * a;
+            const double ms = (d - std::sqrt(d * d - 4.0 * a * a)) / (2.0 * a * a);
+            const double ratio = (a * ms) * (a * ms);
+            const int need = ratio > 0.0 ? (int)std::ceil(std::log(1e-18) / std::log(ratio)) + 3 : 4;
+            T = std::max(T, need);
+        }
+        if (T <= 128 && T <= ny - 2) {
+            QPB_CUDA(qpb_dev_malloc((void **)&s.d_sp_piv, sizeof(double) * (size_t)cf.ne * T * nx));
+            const dim3 grid((unsigned)((nx + 127) / 128), (unsigned)cf.ne);
+            k_thomas_pivots<<<grid, 128, 0, c->stream>>>(T, nx, s.d_sp_piv, s.d_a, s.d_sp_lam, bcy_row[0]);
+            QPB_CHECK_LAUNCH();
+            QPB_CUDA(cudaStreamSynchronize(c->stream));
+            s.sp_T = T;
+            s.sp_wall_last = bcy_row[ny - 1];
+        }
+    }
     s.spectral = true;
     return QPB_OK;
 }
@@ -219,7 +325,11 @@ int qpbk_diffuse_spectral(qpb_ctx *c, DiffSlot &s) {
     {
         ScopedTimer tm(c, 1);
         const dim3 tgrid((unsigned)((nx + 127) / 128), (unsigned)ne);
-        k_thomas_modes<<<tgrid, 128, 0, c->stream>>>(ne, ny, nx, c->d_T1, c->d_T2, s.d_a, s.d_sp_lam, s.d_sp_bcy);
+        if (s.sp_T > 0)
+            k_thomas_frozen<<<tgrid, 128, 0, c->stream>>>(ny, nx, s.sp_T, c->d_T1, s.d_sp_piv, s.d_a, s.d_sp_lam,
+                                                          s.sp_wall_last);
+        else
+            k_thomas_modes<<<tgrid, 128, 0, c->stream>>>(ne, ny, nx, c->d_T1, c->d_T2, s.d_a, s.d_sp_lam, s.d_sp_bcy);
         c->diag.kernel_launches++;
     }
     {
@@ -229,7 +339,8 @@ int qpbk_diffuse_spectral(qpb_ctx *c, DiffSlot &s) {
         c->diag.kernel_launches++;
     }
     QPB_CHECK_LAUNCH();
-    c->diag.sweeps += 2;
-    c->diag.bin_sweeps += 2LL * ne;
+    // three passes over every bin, each reading and writing it once: counted as three directional sweeps
+    c->diag.sweeps += 3;
+    c->diag.bin_sweeps += 3LL * ne;
     return QPB_OK;
 }
