@@ -148,17 +148,21 @@ def collision_only_case(ne=24, n=37, frozen=False, fmax=4.0, only=None):
     )
 
 
-def nonuniform_gap_case(ny=10, nx=14, ne=8, steps=3):
-    """Non-uniform gap: per-cell D(E,x) with harmonic-mean faces and per-gap kernel tables."""
+def nonuniform_gap_case(ny=10, nx=14, ne=8, steps=3, smooth=False):
+    """Non-uniform gap: per-cell D(E,x) with harmonic-mean faces and per-gap kernel tables.  smooth=True adds a gap
+    that varies from cell to cell inside a disc (a trap: every line has its own coefficients, 40 distinct gap values)."""
     mask = np.ones((ny, nx), dtype=bool)
     mask[0, :3] = False
     mask[-2:, -4:] = False
     n = int(mask.sum())
     yy, xx = np.mgrid[:ny, :nx]
     gap_field = np.where(xx < nx // 2, GAP, 0.9 * GAP) + np.where(yy > ny // 2, 4.0, 0.0)
+    if smooth:
+        r2 = ((xx - 0.6 * nx) ** 2 + (yy - 0.4 * ny) ** 2) / (0.2 * min(ny, nx)) ** 2
+        gap_field = gap_field - np.round(20.0 * np.exp(-r2), 0) * 0.5      # quantised: 40 levels
     gap_values = gap_field[mask]
     case = dict(
-        name=f"nonuniform_{ny}x{nx}x{ne}", mask=mask, bc="mixed", initial_field=gaussian_field(mask, sigma=0.2),
+        name=f"nonuniform_{ny}x{nx}x{ne}" + ("_trap" if smooth else ""), mask=mask, bc="mixed", initial_field=gaussian_field(mask, sigma=0.2),
         diffusion_coefficient=D0, dt=0.3, total_time=0.3 * steps, dx=1.0, store_every=1,
         energy_gap=GAP, energy_min_factor=1.0, energy_max_factor=4.0, num_energy_bins=ne,
         weights=None, enable_diffusion=True, enable_recombination=True, enable_scattering=True,
@@ -223,6 +227,12 @@ def golden_cases():
         collision_only_case(only="recomb", ne=16, n=9, fmax=5.0),
         nonuniform_gap_case(),
     ]
+
+
+def golden_cases_large():
+    """Larger recorded cases (tests/golden/make_golden.py large): kept out of golden_cases() so that the CPU suite
+    stays short; the GPU parity tests and one oracle test use them."""
+    return [nonuniform_gap_case(ny=96, nx=96, ne=16, steps=3, smooth=True)]
 
 
 def thermal_weights_for(case, physics_mod):

@@ -31,7 +31,8 @@ def main():
         build_energy_grid = staticmethod(S.build_energy_grid)
         thermal_qp_weights = staticmethod(S.thermal_qp_weights)
 
-    for case in cases.golden_cases():
+    only_large = len(sys.argv) > 1 and sys.argv[1] == "large"
+    for case in (cases.golden_cases_large() if only_large else cases.golden_cases()):
         mask = case["mask"]
         edges = extract_edge_segments(mask)
         bcs = cases.make_bcs(edges, case["bc"], BoundaryCondition)
@@ -47,10 +48,16 @@ def main():
             out["omega"] = hist["phonon_energy_bins"]
         else:
             out["state"] = np.array([f[mask] for f in frames])[:, None, :]
+        if only_large:   # thinned: two stored times in full, phonons of 512 seeded cells
+            keep = np.array([1, len(times) - 1])
+            cells = np.sort(np.random.default_rng(5).choice(out["state"].shape[2], 512, replace=False))
+            out.update(keep=keep, state=out["state"][keep], ph_cells=cells, phonons=out["phonons"][keep][:, :, cells])
         path = os.path.join(HERE, case["name"] + ".npz")
         np.savez_compressed(path, **out)
         print(f"{case['name']:40s} T={len(times)} state{out['state'].shape} -> {os.path.getsize(path)/1024:.1f} KiB")
 
+    if only_large:
+        return
     # table builders + per-pixel collision calls
     tabs = {}
     rng = np.random.default_rng(20260101)

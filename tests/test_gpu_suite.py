@@ -106,3 +106,17 @@ def test_unsafe_custom_generation_is_rejected():
                                 diffusion_coefficient=6.0, dt=0.1, total_time=0.1, dx=1.0, energy_gap=180.0,
                                 energy_min_factor=1.0, energy_max_factor=3.0, num_energy_bins=8,
                                 enable_diffusion=False, external_generation=gen)
+
+
+def test_nonuniform_gap_trap_96x96x16_matches_reference():
+    """Non-uniform gap at a size where it matters (solver.py:235-321, 1145-1164, 834-875): 96 x 96 mask with all five
+    wall kinds, 16 bins, a gap that steps across the device and dips cell by cell inside a trap (44 distinct values):
+    per-cell D(E, x) with harmonic-mean faces in the diffusion, one collision table per gap value."""
+    case = cases.golden_cases_large()[0]
+    want = helpers.load_golden(case["name"])
+    got = helpers.run_dropin(case)
+    keep = want["keep"]
+    np.testing.assert_allclose(got["times"], want["times"], rtol=0, atol=1e-12)
+    helpers.assert_close(got["state"][keep], want["state"], "n(E,cell)")
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
+    helpers.assert_close(got["phonons"][keep][:, :, want["ph_cells"]], want["phonons"], "n_ph", rtol=helpers.RTOL_PHONON)

@@ -113,3 +113,11 @@ def test_oracle_matches_reference_validation_suite(k):
     np.testing.assert_allclose(got["times"], want["times"], rtol=0, atol=1e-9)
     helpers.assert_close(got["state"], want["state"], "field", rtol=1e-11)
     np.testing.assert_allclose(got["mass"], want["mass"], rtol=1e-11, atol=1e-300)
+
+
+def test_oracle_matches_reference_on_the_nonuniform_trap():
+    case = cases.golden_cases_large()[0]
+    want = helpers.load_golden(case["name"])
+    got = helpers.run_oracle(case)
+    helpers.assert_close(got["state"][want["keep"]], want["state"], "n(E,cell)", rtol=1e-11)
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=1e-11)
