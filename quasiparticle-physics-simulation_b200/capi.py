@@ -70,7 +70,7 @@ class Generation(C.Structure):
 
 
 SOURCES = ["qpb_api.cu", "qpb_diffusion.cu", "qpb_sweep_fast.cu", "qpb_sweep_pipe.cu", "qpb_collision.cu", "qpb_aux.cu",
-           "qpb_krylov.cu", "qpb_spectral.cu"]
+           "qpb_krylov.cu", "qpb_spectral.cu", "qpb_resident.cu"]
 
 # every symbol include/qpb.h declares; tests check that the built library exports all of them
 EXPORTED = [

@@ -204,6 +204,12 @@ void qpbk_free_slot(DiffSlot &s) {
     dev_free(s.fy.d_tabg);
     dev_free(s.fy.d_cls);
     dev_free(s.fy.d_tab);
+    dev_free(s.d_resq);
+    dev_free(s.d_rescode);
+    dev_free(s.d_reslut);
+    dev_free(s.d_respax);
+    dev_free(s.d_respay);
+    s.res = DiffSlot::Resident();
     s.ready = false;
     s.fast = false;
     s.pipe = PipePlan();
@@ -704,11 +710,12 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
         int rc = qpbk_prepare_fast(c, s);
         if (rc != QPB_OK) return rc;
         if ((rc = qpbk_prepare_spectral(c, s)) != QPB_OK) return rc;
+        if ((rc = qpbr_plan(c, s)) != QPB_OK) return rc;
     }
     QPB_CUDA(cudaDeviceSynchronize());   // blocking legacy-stream copies of the table setup (see qpb_upload_collision)
     c->diag.direct_mode = s.mode != 0;
     c->diag.commuting = s.commuting;
-    c->diag.sweep_path = s.spectral ? 4 : !s.fast ? 0
+    c->diag.sweep_path = s.spectral ? 4 : s.res.ok ? 5 : !s.fast ? 0
                          : !(s.pipe.x_ok && s.pipe.y_ok) ? 1
                          : (s.pipe.x_nseg > 1 || s.pipe.y_nseg > 1) ? 3 : 2;
     return QPB_OK;

@@ -214,6 +214,37 @@ int qpbk_diffuse(qpb_ctx *c, DiffSlot &s) {
     const auto &cf = c->cfg;
     const int ne = cf.ne;
     int rc;
+    if (s.mode == 0 && !s.spectral && !s.krylov && s.res.ok) {
+        // bin-resident solve (qpb_resident.cu): right-hand side, iteration and stop test in one launch
+        std::vector<int> hd;
+        rc = qpbr_solve(c, s, hd);
+        if (rc != QPB_OK && rc != QPB_E_NOCONV) return rc;
+        int kmax = 0;
+        long long bs = 0;
+        for (int b = 0; b < ne; ++b) {
+            kmax = std::max(kmax, hd[ne + b]);
+            bs += 2 * hd[ne + b] + 1;
+        }
+        c->diag.sweeps += 2 * kmax + 1;
+        c->diag.bin_sweeps += bs;
+        if (rc == QPB_E_NOCONV) {
+            // same fall-back as the launched iteration below: this and every later step of the slot by the Krylov solve
+            if (getenv("QPB_NO_KRYLOV") && getenv("QPB_NO_KRYLOV")[0] == '1') {
+                qpb_set_error("Crank-Nicolson sweep iteration did not reach tolerance %.3g in %d iterations", cf.diff_tol,
+                              c->maxit);
+                return QPB_E_NOCONV;
+            }
+            QPB_CUDA(cudaMemcpyAsync(c->d_S, c->d_B, sizeof(double) * (size_t)ne * c->ncd, cudaMemcpyDeviceToDevice,
+                                     c->stream));
+            s.krylov = true;
+            return qpbk_diffuse_krylov(c, s);
+        }
+        s.known_iters = kmax;
+        s.solves++;
+        QPB_CUDA(cudaMemcpyAsync(s.d_known, hd.data() + ne, sizeof(int) * ne, cudaMemcpyHostToDevice, c->stream));
+        c->diag.pr_iterations += kmax;
+        return QPB_OK;
+    }
     if ((rc = qpbk_build_rhs(c, s)) != QPB_OK) return rc;
     if (s.mode != 0) {
         const int dir = s.mode == 1 ? 0 : 1;

@@ -93,6 +93,18 @@ struct DiffSlot {
     } fx, fy;
     bool fast = false;
     PipePlan pipe;
+    // bin-resident solve (qpb_resident.cu): a cluster of CS CTAs keeps a bin in shared memory for the whole iteration
+    struct Resident {
+        bool ok = false;
+        int RP = 0, QP = 0, CS = 0;   // rows per CTA, lanes per row of the row solve, CTAs per cluster
+        int pitch = 0, reach = 0;     // shared-memory row pitch (doubles), CTAs a column carry reaches
+        int nclusters = 0;            // clusters the device keeps resident at once
+        size_t smem = 0;
+    } res;
+    int *d_resq = nullptr;            // bin queue counter of the resident solve
+    uint8_t *d_rescode = nullptr;     // [ncd] geometry code of every cell
+    double *d_reslut = nullptr;       // [256] code -> linked neighbours + boundary diagonals
+    double *d_respax = nullptr, *d_respay = nullptr;   // chunk products of the row / column multipliers (double2 each)
 };
 
 struct Timer {
@@ -197,6 +209,8 @@ int qpbk_diffuse_spectral(qpb_ctx *c, DiffSlot &s);  // A u = b directly, b in d
 int qpbk_diffuse_krylov(qpb_ctx *c, DiffSlot &s);   // A u = b, b in d_B, guess/result in d_S
 void qpbk_free_krylov(qpb_ctx *c);
 int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s);
+int qpbr_plan(qpb_ctx *c, DiffSlot &s);                               // bin-resident solve: eligibility + launch shape
+int qpbr_solve(qpb_ctx *c, DiffSlot &s, std::vector<int> &h_done);    // QPB_E_NOCONV (b left in d_B) when a bin stalls
 int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode, bool check = true);
 int qpbp_chunk(int n, int dir);
 int qpbp_plan(qpb_ctx *c, DiffSlot &s, PipePlan &p);

@@ -222,6 +222,30 @@ def test_pipelined_and_legacy_sweeps_agree(monkeypatch):
     helpers.assert_close(a["state"], b["state"], "pipe vs legacy", rtol=1e-10)
 
 
+@pytest.mark.parametrize("shape", [(256, 256, "mixed"), (96, 160, "mixed"), (200, 96, "short_absorbing"), (48, 256, "mixed")],
+                         ids=["256x256", "96x160", "200x96_ragged_rows", "48x256"])
+def test_bin_resident_cluster_solve_matches_the_launched_sweeps_and_the_oracle(shape, monkeypatch):
+    """Masks of up to 256 x 256 cells with rows that are a multiple of 16 long are solved bin-resident
+    (qpb_resident.cu: a thread-block cluster keeps u, b and the correction of one bin in shared memory for the whole
+    Peaceman-Rachford iteration, sweep_path 5).  Same linear system, same stop test: the result must agree with the
+    launched sweeps (QPB_NO_RESIDENT=1) far inside the tolerance and with the oracle's SuperLU solve at 1e-9.  Shapes:
+    8 CTAs x 32 rows, 6 x 16, 7 x 32 with a last CTA that is half empty, 3 x 16; all five wall kinds."""
+    ny, nx, bc = shape
+    case = cases.meander_c2(ny=ny, nx=nx, ne=5, steps=3)
+    case["bc"] = bc
+    case["enable_recombination"] = case["enable_scattering"] = False
+    case["generation"] = None
+    got = helpers.run_dropin(case, enforce_pauli=False)
+    assert Q.solver.last_run_info["sweep_path"] == 5, Q.solver.last_run_info
+    monkeypatch.setenv("QPB_NO_RESIDENT", "1")
+    ref = helpers.run_dropin(case, enforce_pauli=False)
+    assert Q.solver.last_run_info["sweep_path"] in (1, 2), Q.solver.last_run_info
+    helpers.assert_close(got["state"], ref["state"], "resident vs launched sweeps", rtol=1e-11)
+    want = helpers.run_oracle(case)
+    helpers.assert_close(got["state"], want["state"], "n(E,cell)")
+    np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
+
+
 @pytest.mark.parametrize("flags", [(True, True), (True, False), (False, True)])
 def test_frozen_uniform_phonons_use_packed_kernels_and_match(flags, monkeypatch):
     """freeze_phonon_dynamics with the same occupations in every cell runs the fused 4-product kernel
