@@ -711,6 +711,9 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
         if (rc != QPB_OK) return rc;
         if ((rc = qpbk_prepare_spectral(c, s)) != QPB_OK) return rc;
         if ((rc = qpbr_plan(c, s)) != QPB_OK) return rc;
+    } else if (!s.krylov) {
+        int rc = qpbk_prepare_fast(c, s);   // chunked sweeps with per-line pivot tables
+        if (rc != QPB_OK) return rc;
     }
     QPB_CUDA(cudaDeviceSynchronize());   // blocking legacy-stream copies of the table setup (see qpb_upload_collision)
     c->diag.direct_mode = s.mode != 0;

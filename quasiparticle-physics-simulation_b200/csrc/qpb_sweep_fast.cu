@@ -113,18 +113,26 @@ struct SweepArgs {
     int nclass, npad, Q;
     unsigned long long *res, *unorm;
     int *done, *iters_out;
+    // per-cell coefficient fields of a non-uniform gap (dense [ne][ncd]): links to the left / upper neighbour, boundary
+    // diagonals; tab then holds one line of pivots per grid line (x: [ne][jmax][ny][npad] chunk-interleaved,
+    // y: [ne][jmax][npad][nx], position major so that lanes along x read neighbours)
+    const double *ex, *ey, *gbx, *gby;
 };
 
 // per-thread solve of one chunk given its rhs d[S] (in place -> x), pivots m[S], link bits
-template <int S>
+template <int S, bool VARD = false>
 struct Chunk {
     double v[S];
     double m[S];
     unsigned lkbits;   // bit t: element t linked to element t-1 (bit 0: to the previous chunk), bit S: next chunk
     unsigned lknext;
     double a;
+    double ev[VARD ? S + 1 : 1];   // per-cell D: coupling of element t to element t-1 (0 where there is no link)
 
-    __device__ __forceinline__ double e(int t) const { return ((t < 32 ? (lkbits >> t) : lknext) & 1u) ? a : 0.0; }
+    __device__ __forceinline__ double e(int t) const {
+        if (VARD) return ev[t];
+        return ((t < 32 ? (lkbits >> t) : lknext) & 1u) ? a : 0.0;
+    }
 
     // forward with zero carry: returns (A = prod f, B = y_last)
     __device__ __forceinline__ void fwd_probe(double &A, double &B) const {
@@ -597,6 +605,228 @@ __global__ void __launch_bounds__(512) k_sweep_y(SweepArgs A, int QW) {
     }
 }
 
+// ---- per-cell D (non-uniform gap): the same chunked solves with one line of pivots per grid line ----------------------
+// One thread per (bin, shift index, line).  e_k = coupling of cell k to cell k-1 along the line (ex / ey, 0 without a
+// link), gb_k the boundary diagonal of the line's direction:  m_k = 1 / (1/2 + rho + e_k + e_{k+1} + gb_k - e_k^2 m_{k-1}).
+__global__ void k_factor_vard(int ne, int jmax, int ny, int nx, int dir, int npad, int S, const double *__restrict__ shift,
+                              const int *__restrict__ jlen, const uint8_t *__restrict__ flags, const double *__restrict__ ef,
+                              const double *__restrict__ gb, double *__restrict__ tab) {
+    const int nlines = dir == 0 ? ny : nx, n = dir == 0 ? nx : ny;
+    const long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const long long total = (long long)ne * jmax * nlines;
+    if (gid >= total) return;
+    const int line = (int)(gid % nlines);
+    const int j = (int)((gid / nlines) % jmax);
+    const int bin = (int)(gid / ((long long)nlines * jmax));
+    if (j >= jlen[bin]) return;
+    const double rho = shift[(long long)bin * jmax + j];
+    const long long off = (long long)bin * ny * nx;
+    const int sk = dir == 0 ? 1 : nx, c0 = dir == 0 ? line * nx : line;
+    const int Q = npad / S;
+    double *out = dir == 0 ? tab + (size_t)gid * npad : tab + ((size_t)bin * jmax + j) * (size_t)npad * nx + line;
+    double mprev = 0.0;
+    for (int k = 0; k < npad; ++k) {
+        double m = 0.0;
+        if (k < n) {
+            const int c = c0 + k * sk;
+            if (flags[c] & QPB_IN) {
+                const double e = ef[off + c];
+                const double en = (k + 1 < n && (flags[c + sk] & QPB_IN)) ? ef[off + c + sk] : 0.0;
+                m = 1.0 / (0.5 + rho + e + en + gb[off + c] - e * e * mprev);
+            }
+        }
+        mprev = m;
+        if (dir == 0) out[(((k % S) / 2) * Q + k / S) * 2 + (k & 1)] = m;
+        else out[(size_t)k * nx] = m;
+    }
+}
+
+// x sweep, per-cell D.  Same structure as k_sweep_x<S, QP, 0>: the right-hand side b - (V - rho) u and the componentwise
+// stop test are formed while the tile is staged (coalesced), one thread then solves one chunk.
+template <int S, int QP>
+__global__ void __launch_bounds__(256) k_sweep_x_vard(SweepArgs A) {
+    constexpr int THREADS = 256;
+    constexpr int LINES = THREADS / QP;
+    constexpr int ROWLEN = QP * S;
+    extern __shared__ double sm[];  // [LINES][ROWLEN]
+    const int tid = threadIdx.x;
+    const int tiles = (A.ny + LINES - 1) / LINES;
+    const int bin = blockIdx.x / tiles;
+    const int y0 = (blockIdx.x - bin * tiles) * LINES;
+    if (!bin_active(A, bin, 0, false)) return;
+    const int nx = A.nx, ncd = A.ny * A.nx;
+    const long long off = (long long)bin * ncd;
+    const double rho = A.shift[(long long)bin * A.jmax + (A.iter % A.jlen[bin])];
+    const double *u = A.S + off, *b = A.B + off;
+    const double *ex = A.ex + off, *ey = A.ey + off, *gbx = A.gbx + off, *gby = A.gby + off;
+    const double tol = A.tol[bin];
+
+    double rmax = 0.0, umax = 0.0;
+    for (int e = tid; e < LINES * ROWLEN; e += THREADS) {
+        const int g = e / ROWLEN, x = e - g * ROWLEN;
+        const int y = y0 + g;
+        double d = 0.0;
+        if (y < A.ny && x < nx) {
+            const int c = y * nx + x;
+            const unsigned fl = A.flags[c];
+            if (fl & QPB_IN) {
+                const double bc_ = b[c], uc = u[c], au = fabs(uc);
+                // boundary diagonals are zero away from absorbing / Dirichlet / Robin walls: flagged, not streamed
+                const double gx = (fl & QPB_BCXNZ) ? gbx[c] : 0.0, gy = (fl & QPB_BCYNZ) ? gby[c] : 0.0;
+                double cross = gy * uc, along = gx * uc, wsum = (fabs(gy) + fabs(gx)) * au;
+                if (fl & QPB_LK_U) { const double ef = ey[c], un = u[c - nx]; cross = fma(ef, uc - un, cross); wsum = fma(ef, au + fabs(un), wsum); }
+                if (fl & QPB_LK_D) { const double ef = ey[c + nx], un = u[c + nx]; cross = fma(ef, uc - un, cross); wsum = fma(ef, au + fabs(un), wsum); }
+                if (fl & QPB_LK_L) { const double ef = ex[c], un = u[c - 1]; along = fma(ef, uc - un, along); wsum = fma(ef, au + fabs(un), wsum); }
+                if (fl & QPB_LK_R) { const double ef = ex[c + 1], un = u[c + 1]; along = fma(ef, uc - un, along); wsum = fma(ef, au + fabs(un), wsum); }
+                d = fma(rho - 0.5, uc, bc_) - cross;
+                rmax = fmax(rmax, fabs(bc_ - uc - cross - along) - tol * (fabs(bc_) + au + wsum));
+                umax = fmax(umax, au);
+            }
+        }
+        const int q = x / S, w = x - q * S;
+        const int unit = (w >> 1) ^ (q & 7);
+        sm[g * ROWLEN + q * S + unit * 2 + (w & 1)] = d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+        umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+    }
+    if ((tid & 31) == 0) {
+        atomicMax(&A.res[(long long)A.iter * A.ne + bin], (unsigned long long)__double_as_longlong(rmax));
+        atomicMax(&A.unorm[(long long)A.iter * A.ne + bin], (unsigned long long)__double_as_longlong(umax));
+    }
+    __syncthreads();
+
+    const int g = tid / QP, q = tid - g * QP;
+    const int y = min(y0 + g, A.ny - 1);
+    Chunk<S, true> ch;
+    ch.a = 0.0;
+    ch.lkbits = ch.lknext = 0u;
+    const int Qt = A.Q;
+    const bool act = q < Qt;
+    {
+        const double2 *src = reinterpret_cast<const double2 *>(sm + g * ROWLEN + q * S);
+#pragma unroll
+        for (int un = 0; un < S / 2; ++un) {
+            const double2 t = src[un ^ (q & 7)];
+            ch.v[2 * un] = t.x;
+            ch.v[2 * un + 1] = t.y;
+        }
+        const double2 *mt = reinterpret_cast<const double2 *>(
+            A.tab + ((((size_t)bin * A.jmax + (A.iter % A.jlen[bin])) * A.ny + y) * A.npad));
+        const int qq = min(q, Qt - 1);
+#pragma unroll
+        for (int un = 0; un < S / 2; ++un) {
+            const double2 t = mt[un * Qt + qq];
+            ch.m[2 * un] = act ? t.x : 1.0;
+            ch.m[2 * un + 1] = act ? t.y : 1.0;
+        }
+        // couplings of the chunk's cells to their left neighbours (and of the next chunk's first cell to my last)
+        const double *er = ex + (size_t)y * nx;
+        const uint8_t *fr = A.flags + (size_t)y * nx;
+#pragma unroll
+        for (int t = 0; t <= S; ++t) {
+            const int x = q * S + t;
+            ch.ev[t] = (act && x < nx && (fr[x] & QPB_LK_L)) ? er[x] : 0.0;
+        }
+    }
+    double Am, Bm;
+    ch.fwd_probe(Am, Bm);
+    const double yin = warp_carry<QP, false>(Am, Bm, q);
+    ch.fwd_apply(yin);
+    ch.bwd_probe(Am, Bm);
+    const double xin = warp_carry<QP, true>(Am, Bm, q);
+    ch.bwd_apply(xin);
+    __syncthreads();
+    {
+        double2 *dst = reinterpret_cast<double2 *>(sm + g * ROWLEN + q * S);
+#pragma unroll
+        for (int un = 0; un < S / 2; ++un) dst[un ^ (q & 7)] = make_double2(ch.v[2 * un], ch.v[2 * un + 1]);
+    }
+    __syncthreads();
+    double *out = A.T1 + off;
+    for (int e = tid; e < LINES * ROWLEN; e += THREADS) {
+        const int gg = e / ROWLEN, x = e - gg * ROWLEN;
+        const int yy = y0 + gg;
+        if (yy < A.ny && x < nx) {
+            const int qx = x / S, w = x - qx * S;
+            const int unit = (w >> 1) ^ (qx & 7);
+            out[yy * nx + x] = sm[gg * ROWLEN + qx * S + unit * 2 + (w & 1)];
+        }
+    }
+}
+
+// y sweep, per-cell D: CTA = 32 columns (lanes) x QW chunks (warps); rhs = u* - u, out = u + 2 rho x.
+template <int S>
+__global__ void __launch_bounds__(512) k_sweep_y_vard(SweepArgs A, int QW) {
+    extern __shared__ double sm[];  // [2][QW][32] carries
+    const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+    const int tiles = (A.nx + 31) / 32;
+    const int bin = blockIdx.x / tiles;
+    const int x0 = (blockIdx.x - bin * tiles) * 32;
+    if (!bin_active(A, bin, 1, blockIdx.x == bin * tiles && threadIdx.x == 0)) return;
+    const int nx = A.nx, ny = A.ny, ncd = ny * nx;
+    const int x = x0 + lane;
+    const bool live = x < nx;
+    const int xc = live ? x : nx - 1;
+    const int jidx = A.iter % A.jlen[bin];
+    const double rho = A.shift[(long long)bin * A.jmax + jidx];
+    const long long off = (long long)bin * ncd;
+    double *u = A.S + off;
+    const double *p = A.T1 + off, *ey = A.ey + off;
+    Chunk<S, true> ch;
+    ch.a = 0.0;
+    ch.lkbits = ch.lknext = 0u;
+    const int r0 = q * S;
+    double uold[S];
+    {
+        const double *mt = A.tab + (((size_t)bin * A.jmax + jidx) * A.npad + r0) * nx + xc;
+#pragma unroll
+        for (int t = 0; t < S; ++t) {
+            const int r = r0 + t;
+            double d = 0.0;
+            uold[t] = 0.0;
+            ch.ev[t] = 0.0;
+            if (live && r < ny) {
+                const int c = r * nx + x;
+                const double uc = u[c];
+                uold[t] = uc;
+                d = p[c] - uc;
+                if (A.flags[c] & QPB_LK_U) ch.ev[t] = ey[c];
+            }
+            ch.v[t] = d;
+            ch.m[t] = mt[(size_t)t * nx];
+        }
+        const int rn = r0 + S;
+        ch.ev[S] = (live && rn < ny && (A.flags[rn * nx + x] & QPB_LK_U)) ? ey[rn * nx + x] : 0.0;
+    }
+    double *cA = sm, *cB = sm + QW * 32;
+    double Am, Bm;
+    ch.fwd_probe(Am, Bm);
+    cA[q * 32 + lane] = Am;
+    cB[q * 32 + lane] = Bm;
+    __syncthreads();
+    double carry = 0.0;
+    for (int k = 0; k < q; ++k) carry = fma(cA[k * 32 + lane], carry, cB[k * 32 + lane]);
+    ch.fwd_apply(carry);
+    ch.bwd_probe(Am, Bm);
+    __syncthreads();
+    cA[q * 32 + lane] = Am;
+    cB[q * 32 + lane] = Bm;
+    __syncthreads();
+    carry = 0.0;
+    for (int k = QW - 1; k > q; --k) carry = fma(cA[k * 32 + lane], carry, cB[k * 32 + lane]);
+    ch.bwd_apply(carry);
+    if (live) {
+#pragma unroll
+        for (int t = 0; t < S; ++t) {
+            const int r = r0 + t;
+            if (r < ny) u[r * nx + x] = fma(2.0 * rho, ch.v[t], uold[t]);
+        }
+    }
+}
+
 // ---- host: classes and tables ------------------------------------------------------------------------------
 struct ClassInfo {
     std::vector<int> cls;          // per line
@@ -755,11 +985,52 @@ static void setup_tma(qpb_ctx *c, DiffSlot &s) {
     fd.use_tma = true;
 }
 
+// per-cell D: one line of pivots per grid line and shift (the chunked kernels k_sweep_x_vard / k_sweep_y_vard)
+static int setup_dir_vard(qpb_ctx *c, DiffSlot &s, DiffSlot::FastDir &fd, int dir) {
+    const auto &cf = c->cfg;
+    fd.n = dir == 0 ? cf.nx : cf.ny;
+    fd.S = 16;
+    fd.Q = (fd.n + fd.S - 1) / fd.S;
+    fd.npad = fd.Q * fd.S;
+    fd.nclass = dir == 0 ? cf.ny : cf.nx;
+    fd.carry_depth = fd.Q;
+    fd.use_tma = false;
+    const size_t elems = (size_t)cf.ne * s.jmax * (dir == 0 ? (size_t)cf.ny * fd.npad : (size_t)fd.npad * cf.nx);
+    if (elems * sizeof(double) > ((size_t)4 << 30)) return 1;
+    QPB_CUDA(qpb_dev_malloc((void **)&fd.d_tab, sizeof(double) * elems));
+    const long long total = (long long)cf.ne * s.jmax * fd.nclass;
+    k_factor_vard<<<(int)ceil_div64(total, 64), 64, 0, c->stream>>>(cf.ne, s.jmax, cf.ny, cf.nx, dir, fd.npad, fd.S, s.d_shift,
+                                                                   s.d_jlen, c->d_flags, dir == 0 ? s.d_ex : s.d_ey,
+                                                                   dir == 0 ? s.d_gbx : s.d_gby, fd.d_tab);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return 0;
+}
+
 int qpbk_prepare_fast(qpb_ctx *c, DiffSlot &s) {
     s.fast = false;
     const auto &cf = c->cfg;
     if (getenv("QPB_FORCE_GENERIC") && getenv("QPB_FORCE_GENERIC")[0] == '1') return QPB_OK;
-    if (cf.flags & QPB_F_VARIABLE_D) return QPB_OK;
+    if (cf.flags & QPB_F_VARIABLE_D) {
+        // non-uniform gap: chunked sweeps with per-line pivot tables where a line fits one CTA (rows up to 512 cells,
+        // columns up to 256); one-cell-thick geometries and longer lines stay with the one-thread-per-line kernels
+        if (s.mode != 0 || cf.nx > 512 || cf.ny > 256) return QPB_OK;
+        if (getenv("QPB_NO_VARD_FAST") && getenv("QPB_NO_VARD_FAST")[0] == '1') return QPB_OK;
+        {   // flag bits for non-zero boundary diagonals (read by the x sweep)
+            std::vector<uint8_t> fl = c->h_flags;
+            for (int p = 0; p < c->ncd; ++p) {
+                if (c->h_bcx[p] != 0.0) fl[p] |= QPB_BCXNZ;
+                if (c->h_bcy[p] != 0.0) fl[p] |= QPB_BCYNZ;
+            }
+            QPB_CUDA(cudaMemcpy(c->d_flags, fl.data(), c->ncd, cudaMemcpyHostToDevice));
+        }
+        int rc;
+        if ((rc = setup_dir_vard(c, s, s.fx, 0)) != 0) return rc < 0 ? rc : QPB_OK;
+        if ((rc = setup_dir_vard(c, s, s.fy, 1)) != 0) return rc < 0 ? rc : QPB_OK;
+        s.pipe = PipePlan();
+        s.fast = true;
+        return QPB_OK;
+    }
     // lines beyond the older chunked kernels: only the segmented pipelined kernels (iterated solves) take them
     const bool long_lines = cf.nx > 1024 || cf.ny > 512;
     if (long_lines && (s.mode != 0 || cf.nx % 16 != 0 || cf.ne > 2048 ||
@@ -874,6 +1145,34 @@ int qpbk_sweep_fast(qpb_ctx *c, DiffSlot &s, int dir, int iter, int mode, bool c
     const auto &cf = c->cfg;
     const DiffSlot::FastDir &fd = dir == 0 ? s.fx : s.fy;
     const int nlines = dir == 0 ? cf.ny : cf.nx;
+    if (cf.flags & QPB_F_VARIABLE_D) {
+        SweepArgs A{};
+        A.ne = cf.ne; A.ny = cf.ny; A.nx = cf.nx; A.iter = iter; A.jmax = s.jmax; A.tol = s.d_tol;
+        A.S = c->d_S; A.B = c->d_B; A.T1 = c->d_T1; A.flags = c->d_flags;
+        A.shift = s.d_shift; A.jlen = s.d_jlen; A.tab = fd.d_tab; A.nclass = fd.nclass; A.npad = fd.npad; A.Q = fd.Q;
+        A.res = c->d_res; A.unorm = c->d_unorm; A.done = c->d_done; A.iters_out = c->d_done + cf.ne;
+        A.ex = s.d_ex; A.ey = s.d_ey; A.gbx = s.d_gbx; A.gby = s.d_gby;
+        ScopedTimer tm(c, dir == 0 ? 0 : 1);
+        c->diag.kernel_launches++;
+        if (dir == 0) {
+            const int qp = next_pow2(fd.Q);
+            const int lines = 256 / qp, tiles = (cf.ny + lines - 1) / lines;
+            const size_t smem = sizeof(double) * 256 * 16;
+            switch (qp) {
+                case 1: k_sweep_x_vard<16, 1><<<cf.ne * tiles, 256, smem, c->stream>>>(A); break;
+                case 2: k_sweep_x_vard<16, 2><<<cf.ne * tiles, 256, smem, c->stream>>>(A); break;
+                case 4: k_sweep_x_vard<16, 4><<<cf.ne * tiles, 256, smem, c->stream>>>(A); break;
+                case 8: k_sweep_x_vard<16, 8><<<cf.ne * tiles, 256, smem, c->stream>>>(A); break;
+                case 16: k_sweep_x_vard<16, 16><<<cf.ne * tiles, 256, smem, c->stream>>>(A); break;
+                default: k_sweep_x_vard<16, 32><<<cf.ne * tiles, 256, smem, c->stream>>>(A); break;
+            }
+        } else {
+            const int QW = fd.Q, tiles = (cf.nx + 31) / 32;
+            k_sweep_y_vard<16><<<cf.ne * tiles, 32 * QW, sizeof(double) * 2 * QW * 32, c->stream>>>(A, QW);
+        }
+        QPB_CHECK_LAUNCH();
+        return QPB_OK;
+    }
     SweepArgs A;
     A.ne = cf.ne; A.ny = cf.ny; A.nx = cf.nx; A.iter = iter; A.jmax = s.jmax; A.tol = s.d_tol;
     A.S = c->d_S; A.B = c->d_B; A.T1 = c->d_T1; A.flags = c->d_flags; A.bcx = c->d_bcx; A.bcy = c->d_bcy;
