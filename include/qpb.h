@@ -163,6 +163,10 @@ int qpb_frames_download(qpb_ctx *ctx, double *frames);
 #define QPB_GEN_RESIDENT 4   /* the array the last QPB_GEN_ARRAY call left on the device: a time-independent custom body
                               * is evaluated and uploaded once per run */
 
+#define QPB_GEN_PROGRAM  5   /* the program of qpb_upload_generation_program, evaluated on the device at the time of
+                              * every step: time-dependent custom bodies without a host evaluation and an NE x N
+                              * upload per step */
+
 typedef struct qpb_generation {
     int32_t mode;
     int32_t reserved;
@@ -171,6 +175,41 @@ typedef struct qpb_generation {
     double  pulse_duration;
     const double *array;   /* QPB_GEN_ARRAY only */
 } qpb_generation;
+
+/*
+ * A custom generation body g(E, x, y, t, params) (evaluate_external_generation, solver.py:918-962) as a postfix program
+ * over a stack of doubles, one value per (energy bin, cell).  The host layer translates the body's expression tree
+ * (userexpr.compile_program); params are folded into constants.  Binary operators pop b then a and push a OP b.
+ * cell_x / cell_y [ncell]: the normalised cell-centre coordinates the reference passes as x and y; E_bins [ne].
+ * Values that are not finite or negative make qpb_advance fail with the reference's messages.
+ */
+typedef struct qpb_gen_op {
+    int32_t op;       /* QPB_OP_* */
+    int32_t reserved;
+    double  value;    /* QPB_OP_CONST */
+} qpb_gen_op;
+enum {
+    QPB_OP_CONST = 0, QPB_OP_E, QPB_OP_X, QPB_OP_Y, QPB_OP_T,
+    QPB_OP_ADD, QPB_OP_SUB, QPB_OP_MUL, QPB_OP_DIV, QPB_OP_POW, QPB_OP_MOD, QPB_OP_FLOORDIV,
+    QPB_OP_NEG, QPB_OP_NOT, QPB_OP_TRUTH,
+    QPB_OP_LT, QPB_OP_LE, QPB_OP_GT, QPB_OP_GE, QPB_OP_EQ, QPB_OP_NE,
+    QPB_OP_AND,       /* Python: a and b  ->  b if a else a */
+    QPB_OP_OR,        /* Python: a or b   ->  a if a else b */
+    QPB_OP_SELECT,    /* pops b, a, cond; pushes a where cond is true else b  (np.where, a if c else b) */
+    QPB_OP_MIN, QPB_OP_MAX,         /* Python builtins on two values */
+    QPB_OP_NPMIN, QPB_OP_NPMAX,     /* np.minimum / np.maximum: NaN propagates */
+    QPB_OP_HEAVISIDE,
+    QPB_OP_ABS, QPB_OP_SQRT, QPB_OP_EXP, QPB_OP_LOG, QPB_OP_LOG10, QPB_OP_SIN, QPB_OP_COS, QPB_OP_TAN,
+    QPB_OP_ASIN, QPB_OP_ACOS, QPB_OP_ATAN, QPB_OP_SINH, QPB_OP_COSH, QPB_OP_TANH, QPB_OP_FLOOR, QPB_OP_CEIL,
+    QPB_OP_TRUNC,
+    QPB_OP_COUNT
+};
+#define QPB_GEN_MAX_OPS   512
+#define QPB_GEN_MAX_STACK 24
+int qpb_upload_generation_program(qpb_ctx *ctx, const qpb_gen_op *ops, int32_t nops, const double *E_bins,
+                                  const double *cell_x, const double *cell_y);
+/* g(E, x, y, t) of the uploaded program on the host, [ne][ncell] (tests; the run itself never downloads it) */
+int qpb_eval_generation_program(qpb_ctx *ctx, double t, double *out);
 
 /*
  * Advance nsteps time steps of length dt starting at time t_start — the loop body of

@@ -29,7 +29,7 @@ F_VARIABLE_D = 1 << 4
 F_PAULI = 1 << 5
 F_SCALAR = 1 << 6
 
-GEN_NONE, GEN_CONSTANT, GEN_PULSE, GEN_ARRAY, GEN_RESIDENT = 0, 1, 2, 3, 4
+GEN_NONE, GEN_CONSTANT, GEN_PULSE, GEN_ARRAY, GEN_RESIDENT, GEN_PROGRAM = 0, 1, 2, 3, 4, 5
 
 E_NOCONV = -5
 
@@ -38,6 +38,7 @@ class QpbError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"libqpb error {code}: {message}")
         self.code = code
+        self.message = message
 
 
 class Config(C.Structure):
@@ -69,6 +70,10 @@ class Generation(C.Structure):
     ]
 
 
+class GenOp(C.Structure):
+    _fields_ = [("op", C.c_int32), ("reserved", C.c_int32), ("value", C.c_double)]
+
+
 SOURCES = ["qpb_api.cu", "qpb_diffusion.cu", "qpb_sweep_fast.cu", "qpb_sweep_pipe.cu", "qpb_collision.cu", "qpb_aux.cu",
            "qpb_krylov.cu", "qpb_spectral.cu", "qpb_resident.cu"]
 
@@ -81,7 +86,7 @@ EXPORTED = [
     "qpb_device_ptr", "qpb_measure_fp64", "qpb_measure_copy", "qpb_scatter_block", "qpb_gather_block",
     "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons", "qpb_pauli_record", "qpb_pauli_fetch", "qpb_set_exchange", "qpb_collide_exchange",
     "qpb_ipc_export", "qpb_ipc_open", "qpb_ipc_close", "qpb_euler_step", "qpb_set_state_separable",
-    "qpb_frames_snapshot", "qpb_frames_download",
+    "qpb_frames_snapshot", "qpb_frames_download", "qpb_upload_generation_program", "qpb_eval_generation_program",
 ]
 
 
@@ -177,6 +182,8 @@ def load_library():
     lib.qpb_frames_download.argtypes = [vp, vp]
     lib.qpb_trim_cache.argtypes = []
     lib.qpb_advance.argtypes = [vp, i32, dbl, i32, dbl, C.POINTER(Generation), vp]
+    lib.qpb_upload_generation_program.argtypes = [vp, C.POINTER(GenOp), i32, vp, vp, vp]
+    lib.qpb_eval_generation_program.argtypes = [vp, dbl, vp]
     lib.qpb_collide.argtypes = [vp, dbl]
     lib.qpb_diffuse.argtypes = [vp, i32]
     lib.qpb_pauli.argtypes = [vp, C.POINTER(PauliRec)]
@@ -376,6 +383,21 @@ class Context:
             return None
         transfer_stats["d2h"] += 24 * int(nsteps)
         return [(recs[k].max_occ, recs[k].max_index, recs[k].forbidden) for k in range(int(nsteps))]
+
+    def upload_generation_program(self, program, E_bins, cell_x, cell_y):
+        """A custom generation body as a postfix program ``[(op, value), ...]`` (userexpr.compile_program) with the
+        inputs it is evaluated on: E per bin, normalised x / y per cell.  Afterwards gen_mode=GEN_PROGRAM."""
+        ops = (GenOp * len(program))(*[GenOp(int(op), 0, float(v)) for op, v in program])
+        e, x, y = _f64(E_bins, (self.ne,)), _f64(cell_x, (self.ncell,)), _f64(cell_y, (self.ncell,))
+        for a in (e, x, y):
+            _up(a)
+        self._check(self.lib.qpb_upload_generation_program(self.handle, ops, len(program), _ptr(e), _ptr(x), _ptr(y)))
+
+    def eval_generation_program(self, t):
+        out = np.empty((self.ne, self.ncell), dtype=np.float64)
+        self._check(self.lib.qpb_eval_generation_program(self.handle, float(t), _ptr(out)))
+        transfer_stats["d2h"] += out.nbytes
+        return out
 
     def collide(self, dt):
         self._check(self.lib.qpb_collide(self.handle, float(dt)))

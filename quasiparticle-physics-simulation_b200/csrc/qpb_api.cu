@@ -339,7 +339,7 @@ extern "C" void qpb_destroy(qpb_ctx *c) {
     dev_free(c->d_Kr); dev_free(c->d_Ks); dev_free(c->d_KrT); dev_free(c->d_KsT); dev_free(c->d_rho);
     dev_free(c->d_gapid); dev_free(c->d_idxd); dev_free(c->d_idxs); dev_free(c->d_idxdT);
     dev_free(c->d_sign); dev_free(c->d_signT); dev_free(c->d_dmap); dev_free(c->d_smap);
-    dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_Mg); dev_free(c->d_Xn); dev_free(c->d_Xp); dev_free(c->d_scratch); dev_free(c->d_gen);
+    dev_free(c->d_kof); dev_free(c->d_mof); dev_free(c->d_P); dev_free(c->d_K4); dev_free(c->d_Mg); dev_free(c->d_Xn); dev_free(c->d_Xp); dev_free(c->d_scratch); dev_free(c->d_gen); dev_free(c->d_genprog); dev_free(c->d_gen_E); dev_free(c->d_gen_x); dev_free(c->d_gen_y); dev_free(c->d_gen_flag);
     qpbk_free_krylov(c);
     dev_free(c->d_integrated); dev_free(c->d_pauli); dev_free(c->d_xdense); dev_free(c->d_cperm); dev_free(c->d_ggid); dev_free(c->d_euler);
     if (c->d_pauli_part) qpb_dev_free(c->d_pauli_part);
@@ -1302,7 +1302,13 @@ extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, 
             qpb_set_error("qpb_advance: no generation array is resident (run a QPB_GEN_ARRAY batch first)");
             return QPB_E_INVALID;
         }
-    } else if (gmode < QPB_GEN_NONE || gmode > QPB_GEN_RESIDENT) {
+    } else if (gmode == QPB_GEN_PROGRAM) {
+        if (!c->d_genprog || c->gen_nops <= 0) {
+            qpb_set_error("qpb_advance: no generation program was uploaded (qpb_upload_generation_program)");
+            return QPB_E_INVALID;
+        }
+        QPB_CUDA(cudaMemsetAsync(c->d_gen_flag, 0, sizeof(int), c->stream));
+    } else if (gmode < QPB_GEN_NONE || gmode > QPB_GEN_PROGRAM) {
         qpb_set_error("qpb_advance: unknown generation mode %d", gmode);
         return QPB_E_INVALID;
     }
@@ -1329,6 +1335,8 @@ extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, 
                 if ((rc = qpbk_add_generation(c, dt, gen->rate, nullptr)) != QPB_OK) return rc;
         } else if (gmode == QPB_GEN_ARRAY || gmode == QPB_GEN_RESIDENT) {
             if ((rc = qpbk_add_generation(c, dt, 0.0, c->d_gen)) != QPB_OK) return rc;
+        } else if (gmode == QPB_GEN_PROGRAM) {
+            if ((rc = qpbk_generation_program(c, dt, t, nullptr)) != QPB_OK) return rc;
         }
         if (coll && diff) {  // solver.py:1469-1472
             if ((rc = qpbk_collide(c, 0.5 * dt)) != QPB_OK) return rc;
@@ -1346,10 +1354,85 @@ extern "C" int qpb_advance(qpb_ctx *c, int32_t nsteps, double dt, int32_t slot, 
     if (pauli && pauli_out && nsteps > 0)
         QPB_CUDA(cudaMemcpyAsync(pauli_out, c->d_pauli, sizeof(qpb_pauli_rec) * nsteps, cudaMemcpyDeviceToHost,
                                  c->stream));
+    int gflag = 0;
+    if (gmode == QPB_GEN_PROGRAM)
+        QPB_CUDA(cudaMemcpyAsync(&gflag, c->d_gen_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     QPB_CUDA(cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     QPB_CUDA(cudaEventElapsedTime(&ms, ea, eb));
     c->diag.last_advance_ms = ms;
+    if (gflag & 1) {   // the reference's checks of evaluate_external_generation (solver.py:954-962), same messages
+        qpb_set_error("External generation mode 'custom' produced non-finite values.");
+        return QPB_E_INVALID;
+    }
+    if (gflag & 2) {
+        qpb_set_error("External generation mode 'custom' produced negative values. Generation rates must be non-negative.");
+        return QPB_E_INVALID;
+    }
+    return QPB_OK;
+}
+
+extern "C" int qpb_upload_generation_program(qpb_ctx *c, const qpb_gen_op *ops, int32_t nops, const double *E_bins,
+                                             const double *cell_x, const double *cell_y) {
+    QPB_ENTER(c);
+    const auto &cf = c->cfg;
+    if (!ops || nops <= 0 || nops > QPB_GEN_MAX_OPS || !E_bins || !cell_x || !cell_y) {
+        qpb_set_error("qpb_upload_generation_program: null argument or a program of %d operators (1..%d)", nops,
+                      QPB_GEN_MAX_OPS);
+        return QPB_E_INVALID;
+    }
+    // the program must leave exactly one value and never outgrow the stack: checked here, not per thread
+    int depth = 0, peak = 0;
+    for (int k = 0; k < nops; ++k) {
+        const int op = ops[k].op;
+        if (op < 0 || op >= QPB_OP_COUNT) {
+            qpb_set_error("qpb_upload_generation_program: unknown operator %d at %d", op, k);
+            return QPB_E_INVALID;
+        }
+        const int pops = op <= QPB_OP_T ? 0 : op == QPB_OP_SELECT ? 3
+                         : (op >= QPB_OP_ABS || op == QPB_OP_NEG || op == QPB_OP_NOT || op == QPB_OP_TRUTH) ? 1 : 2;
+        if (depth < pops) {
+            qpb_set_error("qpb_upload_generation_program: operator %d at %d finds %d values on the stack", op, k, depth);
+            return QPB_E_INVALID;
+        }
+        depth += 1 - pops;
+        peak = std::max(peak, depth);
+    }
+    if (depth != 1 || peak > QPB_GEN_MAX_STACK) {
+        qpb_set_error("qpb_upload_generation_program: the program leaves %d values (must be 1), stack depth %d (max %d)",
+                      depth, peak, QPB_GEN_MAX_STACK);
+        return QPB_E_INVALID;
+    }
+    dev_free(c->d_genprog);
+    QPB_CUDA(qpb_dev_malloc(&c->d_genprog, sizeof(qpb_gen_op) * (size_t)nops));
+    if (!c->d_gen_E) QPB_ALLOC(c->d_gen_E, (size_t)cf.ne);
+    if (!c->d_gen_x) QPB_ALLOC(c->d_gen_x, (size_t)cf.ncell);
+    if (!c->d_gen_y) QPB_ALLOC(c->d_gen_y, (size_t)cf.ncell);
+    if (!c->d_gen_flag) QPB_CUDA(qpb_dev_malloc((void **)&c->d_gen_flag, sizeof(int)));
+    QPB_CUDA(cudaMemcpyAsync(c->d_genprog, ops, sizeof(qpb_gen_op) * (size_t)nops, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaMemcpyAsync(c->d_gen_E, E_bins, sizeof(double) * cf.ne, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaMemcpyAsync(c->d_gen_x, cell_x, sizeof(double) * cf.ncell, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaMemcpyAsync(c->d_gen_y, cell_y, sizeof(double) * cf.ncell, cudaMemcpyHostToDevice, c->stream));
+    QPB_CUDA(cudaMemsetAsync(c->d_gen_flag, 0, sizeof(int), c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    c->gen_nops = nops;
+    return QPB_OK;
+}
+
+extern "C" int qpb_eval_generation_program(qpb_ctx *c, double t, double *out) {
+    QPB_ENTER(c);
+    const auto &cf = c->cfg;
+    if (!out || !c->d_genprog || c->gen_nops <= 0) {
+        qpb_set_error("qpb_eval_generation_program: no program uploaded or null output");
+        return QPB_E_INVALID;
+    }
+    const size_t n = (size_t)cf.ne * cf.ncell;
+    if (!c->d_gen) QPB_ALLOC(c->d_gen, n);
+    c->gen_resident = false;
+    int rc = qpbk_generation_program(c, 0.0, t, c->d_gen);
+    if (rc != QPB_OK) return rc;
+    QPB_CUDA(cudaMemcpyAsync(out, c->d_gen, sizeof(double) * n, cudaMemcpyDeviceToHost, c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
     return QPB_OK;
 }
 

@@ -67,6 +67,98 @@ __global__ void k_add_generation(int ne, int ncell, int ncd, double *__restrict_
         row[c2d[q]] += g ? scale * g[q] : add;
 }
 
+// state += scale * g(E, x, y, t) with g given as a postfix program (qpb.h: qpb_gen_op) - a custom generation body evaluated
+// where the state lives (evaluate_external_generation, solver.py:918-962, 1459-1464).  One thread per (bin, cell); every
+// thread of the grid runs the same operator sequence (no divergence), the program sits in shared memory.  Python's
+// scalar semantics (the reference falls back to a per-value loop whenever a body is not vectorisable).
+__global__ void k_generation_program(int ne, int ncell, int ncd, double *__restrict__ S, const int32_t *__restrict__ c2d,
+                                     double scale, double t, int nops, const qpb_gen_op *__restrict__ prog,
+                                     const double *__restrict__ Eb, const double *__restrict__ cx,
+                                     const double *__restrict__ cy, double *__restrict__ out, int *__restrict__ flag) {
+    __shared__ qpb_gen_op ops[QPB_GEN_MAX_OPS];
+    for (int k = threadIdx.x; k < nops; k += blockDim.x) ops[k] = prog[k];
+    __syncthreads();
+    const int i = blockIdx.y;
+    const double E = Eb[i];
+    int bad = 0;
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < ncell; q += gridDim.x * blockDim.x) {
+        const double x = cx[q], y = cy[q];
+        double st[QPB_GEN_MAX_STACK];
+        int sp = 0;   // number of values on the stack
+        for (int k = 0; k < nops; ++k) {
+            const int op = ops[k].op;
+            if (op <= QPB_OP_T) {
+                st[sp++] = op == QPB_OP_CONST ? ops[k].value : op == QPB_OP_E ? E : op == QPB_OP_X ? x : op == QPB_OP_Y ? y : t;
+            } else if (op == QPB_OP_SELECT) {
+                const double b = st[--sp], a = st[--sp], c = st[sp - 1];
+                st[sp - 1] = c != 0.0 ? a : b;
+            } else if (op >= QPB_OP_ABS || op == QPB_OP_NEG || op == QPB_OP_NOT || op == QPB_OP_TRUTH) {
+                const double a = st[sp - 1];
+                double r;
+                switch (op) {
+                    case QPB_OP_NEG: r = -a; break;
+                    case QPB_OP_NOT: r = a == 0.0 ? 1.0 : 0.0; break;
+                    case QPB_OP_TRUTH: r = a != 0.0 ? 1.0 : 0.0; break;
+                    case QPB_OP_ABS: r = fabs(a); break;
+                    case QPB_OP_SQRT: r = sqrt(a); break;
+                    case QPB_OP_EXP: r = exp(a); break;
+                    case QPB_OP_LOG: r = log(a); break;
+                    case QPB_OP_LOG10: r = log10(a); break;
+                    case QPB_OP_SIN: r = sin(a); break;
+                    case QPB_OP_COS: r = cos(a); break;
+                    case QPB_OP_TAN: r = tan(a); break;
+                    case QPB_OP_ASIN: r = asin(a); break;
+                    case QPB_OP_ACOS: r = acos(a); break;
+                    case QPB_OP_ATAN: r = atan(a); break;
+                    case QPB_OP_SINH: r = sinh(a); break;
+                    case QPB_OP_COSH: r = cosh(a); break;
+                    case QPB_OP_TANH: r = tanh(a); break;
+                    case QPB_OP_FLOOR: r = floor(a); break;
+                    case QPB_OP_CEIL: r = ceil(a); break;
+                    default: r = trunc(a); break;
+                }
+                st[sp - 1] = r;
+            } else {
+                const double b = st[--sp], a = st[sp - 1];
+                double r;
+                switch (op) {
+                    case QPB_OP_ADD: r = a + b; break;
+                    case QPB_OP_SUB: r = a - b; break;
+                    case QPB_OP_MUL: r = a * b; break;
+                    case QPB_OP_DIV: r = a / b; break;
+                    case QPB_OP_POW: r = pow(a, b); break;
+                    case QPB_OP_MOD: {   // Python / numpy: the result takes the sign of the divisor
+                        r = fmod(a, b);
+                        if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
+                        break;
+                    }
+                    case QPB_OP_FLOORDIV: r = floor(a / b); break;
+                    case QPB_OP_LT: r = a < b ? 1.0 : 0.0; break;
+                    case QPB_OP_LE: r = a <= b ? 1.0 : 0.0; break;
+                    case QPB_OP_GT: r = a > b ? 1.0 : 0.0; break;
+                    case QPB_OP_GE: r = a >= b ? 1.0 : 0.0; break;
+                    case QPB_OP_EQ: r = a == b ? 1.0 : 0.0; break;
+                    case QPB_OP_NE: r = a != b ? 1.0 : 0.0; break;
+                    case QPB_OP_AND: r = a != 0.0 ? b : a; break;
+                    case QPB_OP_OR: r = a != 0.0 ? a : b; break;
+                    case QPB_OP_MIN: r = b < a ? b : a; break;     // min(a, b): the first smallest
+                    case QPB_OP_MAX: r = b > a ? b : a; break;
+                    case QPB_OP_NPMIN: r = (a != a || b != b) ? a + b : (b < a ? b : a); break;
+                    case QPB_OP_NPMAX: r = (a != a || b != b) ? a + b : (b > a ? b : a); break;
+                    default: r = a != a ? a : (a < 0.0 ? 0.0 : (a == 0.0 ? b : 1.0)); break;   // heaviside(a, b)
+                }
+                st[sp - 1] = r;
+            }
+        }
+        const double g = st[0];
+        if (!(fabs(g) <= 1.79769313486231570e308)) bad |= 1;
+        else if (g < 0.0) bad |= 2;
+        if (out) out[(long long)i * ncell + q] = g;
+        else S[(long long)i * ncd + c2d[q]] += scale * g;
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
 // integrated[q] = (sum_i n[i][q]) * dE, bins added in order like np.sum(state, axis=0)
 __global__ void k_integrate(int ne, int ncell, int ncd, const double *__restrict__ S,
                             const int32_t *__restrict__ c2d, double dE, double *__restrict__ out) {
@@ -229,6 +321,17 @@ int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_a
     const dim3 grid((unsigned)std::max(1, std::min((cf.ncell + 255) / 256, 64)), (unsigned)cf.ne);
     k_add_generation<<<grid, 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S, c->d_cell2dense, scale, rate,
                                                   d_array);
+    c->diag.kernel_launches++;
+    QPB_CHECK_LAUNCH();
+    return QPB_OK;
+}
+
+int qpbk_generation_program(qpb_ctx *c, double scale, double t, double *d_out) {
+    const auto &cf = c->cfg;
+    const dim3 grid((unsigned)std::max(1, std::min((cf.ncell + 255) / 256, 64)), (unsigned)cf.ne);
+    k_generation_program<<<grid, 256, 0, c->stream>>>(cf.ne, cf.ncell, c->ncd, c->d_S, c->d_cell2dense, scale, t, c->gen_nops,
+                                                      (const qpb_gen_op *)c->d_genprog, c->d_gen_E, c->d_gen_x, c->d_gen_y,
+                                                      d_out, c->d_gen_flag);
     c->diag.kernel_launches++;
     QPB_CHECK_LAUNCH();
     return QPB_OK;

@@ -182,6 +182,11 @@ struct qpb_ctx {
     // generation array
     double *d_gen = nullptr;          // [ne][ncell]
     bool gen_resident = false;        // d_gen holds the array of the last QPB_GEN_ARRAY batch
+    // device-side custom generation body (qpb_upload_generation_program): postfix program, its inputs, its verdict
+    void *d_genprog = nullptr;        // qpb_gen_op[nops]
+    int gen_nops = 0;
+    double *d_gen_E = nullptr, *d_gen_x = nullptr, *d_gen_y = nullptr;   // [ne], [ncell], [ncell]
+    int *d_gen_flag = nullptr;        // bit 0: a value was not finite, bit 1: a value was negative
     // reductions
     double *d_integrated = nullptr;   // [ncell]
     qpb_pauli_rec *d_pauli = nullptr; // [capacity]
@@ -224,6 +229,7 @@ int qpbk_uniform_setup(qpb_ctx *c, const double *n_ph, bool per_bin = false);   
 int qpbk_broadcast_phonons(qpb_ctx *c, const double *d_bins);  // P[o][q] = bins[o]
 
 int qpbk_add_generation(qpb_ctx *c, double scale, double rate, const double *d_array);
+int qpbk_generation_program(qpb_ctx *c, double scale, double t, double *d_out);   // d_out: write g there instead of adding scale*g to the state
 int qpbk_pauli(qpb_ctx *c, qpb_pauli_rec *d_out);
 int qpbk_integrate(qpb_ctx *c);
 int qpbk_scatter_state(qpb_ctx *c, const double *d_compact);  // [ne][ncell] -> dense

@@ -8,6 +8,7 @@ C ABI of ``include/qpb.h``.  Nothing in this module computes a time step on the 
 """
 from __future__ import annotations
 
+import os
 import threading
 
 import warnings
@@ -39,7 +40,9 @@ class _Generation:
     """External generation (solver.py:878-964) as qpb_advance arguments.  ``constant`` / ``pulse`` are evaluated on the
     device.  ``custom`` bodies are evaluated on the host by :mod:`userexpr`; a body that never names ``t`` is
     evaluated once, uploaded with the first batch and stays resident (later batches: QPB_GEN_RESIDENT, any number of
-    steps); a time-dependent body is re-evaluated and uploaded for every step, as the reference does."""
+    steps); a time-dependent body is translated into a postfix program that the device evaluates at the time of every
+    step (QPB_GEN_PROGRAM, any number of steps per batch).  Only a body without a per-value meaning (``len(x)``,
+    subscripts, ``np.arange`` ...) is still re-evaluated on the host and uploaded for every step, as the reference does."""
 
     def __init__(self, spec, E_bins, mask):
         self.mode = "none" if spec is None else spec.mode.strip().lower()
@@ -55,8 +58,17 @@ class _Generation:
             self.custom = userexpr.CustomGeneration(spec, E_bins, mask)
 
     @property
+    def on_device(self) -> bool:
+        return (self.custom is not None and self.custom.program is not None
+                and os.environ.get("QPB_NO_GEN_PROGRAM", "0") != "1")
+
+    def upload_program(self, ctx) -> None:
+        if self.on_device:
+            ctx.upload_generation_program(self.custom.program, self.custom.E, self.custom.x, self.custom.y)
+
+    @property
     def one_step_batches(self) -> bool:
-        return self.custom is not None and self.custom.time_dependent
+        return self.custom is not None and self.custom.time_dependent and not self.on_device
 
     def advance_args(self, t: float) -> dict:
         sp = self.spec
@@ -66,6 +78,8 @@ class _Generation:
             return dict(gen_mode=capi.GEN_PULSE, rate=float(sp.pulse_rate), pulse_start=float(sp.pulse_start),
                         pulse_duration=float(sp.pulse_duration))
         if self.mode == "custom":
+            if self.on_device:
+                return dict(gen_mode=capi.GEN_PROGRAM)
             if self.uploaded and not self.custom.time_dependent:
                 return dict(gen_mode=capi.GEN_RESIDENT)
             self.uploaded = True
@@ -471,6 +485,7 @@ def run_2d_crank_nicolson(
             current_time = 0.0
             step = 0
             generation = _Generation(external_generation, E_bins, mask_b)
+            generation.upload_program(ctx)
             while step < total_steps:
                 nxt = min(((step // store_every) + 1) * store_every, total_steps)
                 if nxt > full_steps and step < full_steps:
@@ -481,8 +496,14 @@ def run_2d_crank_nicolson(
                 h = remainder_dt if is_final else dt
                 count = nxt - step
                 gen_kwargs = generation.advance_args(current_time)
-                recs = ctx.advance(count, h, slot=1 if is_final else 0, t_start=current_time, want_pauli=True,
-                                   **gen_kwargs)
+                try:
+                    recs = ctx.advance(count, h, slot=1 if is_final else 0, t_start=current_time, want_pauli=True,
+                                       **gen_kwargs)
+                except capi.QpbError as exc:
+                    # the device-side checks of a custom generation body carry the reference's messages (solver.py:954-962)
+                    if exc.message.startswith("External generation mode 'custom'"):
+                        raise ValueError(exc.message) from None
+                    raise
                 for k in range(count):
                     policy.check(recs[k], step + k + 1, current_time + h)
                     current_time += h
@@ -507,6 +528,7 @@ def run_2d_crank_nicolson(
                 th.join()
         info.update(ctx.diag())
         info["generation_uploads"] = generation.uploads
+        info["generation_on_device"] = bool(generation.on_device)
 
     limits = _color_limits(frames)
     if phonon_history_out is not None:

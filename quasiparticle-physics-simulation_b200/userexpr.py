@@ -121,6 +121,187 @@ class Expression:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# translation of a body into a postfix program for the device (include/qpb.h: qpb_gen_op)
+# ---------------------------------------------------------------------------------------------------------------
+OPS = ("CONST E X Y T ADD SUB MUL DIV POW MOD FLOORDIV NEG NOT TRUTH LT LE GT GE EQ NE AND OR SELECT MIN MAX NPMIN NPMAX "
+       "HEAVISIDE ABS SQRT EXP LOG LOG10 SIN COS TAN ASIN ACOS ATAN SINH COSH TANH FLOOR CEIL TRUNC").split()
+OP = {name: k for k, name in enumerate(OPS)}
+MAX_OPS, MAX_STACK = 512, 24
+_UNARY_NP = {"abs": "ABS", "sqrt": "SQRT", "exp": "EXP", "log": "LOG", "log10": "LOG10", "sin": "SIN", "cos": "COS",
+             "tan": "TAN", "arcsin": "ASIN", "arccos": "ACOS", "arctan": "ATAN", "sinh": "SINH", "cosh": "COSH",
+             "tanh": "TANH"}
+_UNARY_MATH = {"sqrt": "SQRT", "exp": "EXP", "log": "LOG", "log10": "LOG10", "sin": "SIN", "cos": "COS", "tan": "TAN",
+               "asin": "ASIN", "acos": "ACOS", "atan": "ATAN", "sinh": "SINH", "cosh": "COSH", "tanh": "TANH",
+               "floor": "FLOOR", "ceil": "CEIL"}
+_BINOPS = {ast.Add: "ADD", ast.Sub: "SUB", ast.Mult: "MUL", ast.Div: "DIV", ast.Pow: "POW", ast.Mod: "MOD",
+           ast.FloorDiv: "FLOORDIV"}
+_CMPOPS = {ast.Lt: "LT", ast.LtE: "LE", ast.Gt: "GT", ast.GtE: "GE", ast.Eq: "EQ", ast.NotEq: "NE"}
+_VALUES = {("np", "pi"): math.pi, ("np", "e"): math.e, ("np", "inf"): math.inf, ("np", "nan"): math.nan,
+           ("math", "pi"): math.pi, ("math", "e"): math.e, ("math", "tau"): math.tau, ("math", "inf"): math.inf,
+           ("math", "nan"): math.nan}
+
+
+class _NotTranslatable(Exception):
+    pass
+
+
+def compile_program(expr: "Expression", params: dict, variables=("E", "x", "y", "t")):
+    """Translate a validated body into a postfix program ``[(op, value), ...]`` with the value semantics of one scalar
+    evaluation per (E, x, y, t) - what the reference's per-value fallback loop computes - or return None when the body
+    uses something that has no per-value meaning on the device (``len``, ``.size``, subscripts, ``np.arange``, keyword
+    arguments, non-numeric params): such bodies keep the host evaluation.  ``params`` are folded into constants."""
+    prog = []
+
+    def const(v):
+        if isinstance(v, (bool, np.bool_)):
+            v = 1.0 if v else 0.0
+        if not isinstance(v, (int, float, np.integer, np.floating)):
+            raise _NotTranslatable(f"constant {v!r}")
+        prog.append((OP["CONST"], float(v)))
+
+    def param_value(node):
+        # params.get("key"[, default]) and params["key"], keys and defaults constant
+        if isinstance(node, ast.Subscript):
+            key = node.slice
+            if not (isinstance(key, ast.Constant) and key.value in params):
+                raise _NotTranslatable("params subscript")
+            return params[key.value]
+        args = node.args
+        if node.keywords or not (1 <= len(args) <= 2) or not isinstance(args[0], ast.Constant):
+            raise _NotTranslatable("params.get")
+        if args[0].value in params:
+            return params[args[0].value]
+        if len(args) == 1:
+            raise _NotTranslatable("params.get without default")   # None
+        return ast.literal_eval(args[1]) if not isinstance(args[1], ast.Constant) else args[1].value
+
+    def fold(args, op):   # left fold of a two-argument operator over a call's arguments
+        if len(args) < 2:
+            raise _NotTranslatable("min/max of one argument")
+        emit(args[0])
+        for a in args[1:]:
+            emit(a)
+            prog.append((OP[op], 0.0))
+
+    def emit(node):
+        if isinstance(node, ast.Expression):
+            return emit(node.body)
+        if isinstance(node, ast.Constant):
+            return const(node.value)
+        if isinstance(node, ast.Name):
+            if node.id in variables:
+                prog.append((OP[node.id.upper()], 0.0))
+                return
+            raise _NotTranslatable(f"name {node.id}")
+        if isinstance(node, ast.Attribute):
+            key = (getattr(node.value, "id", None), node.attr)
+            if key in _VALUES:
+                return const(_VALUES[key])
+            raise _NotTranslatable(f"attribute {key}")
+        if isinstance(node, ast.Subscript):
+            if isinstance(node.value, ast.Name) and node.value.id == "params":
+                return const(param_value(node))
+            raise _NotTranslatable("subscript")
+        if isinstance(node, ast.UnaryOp):
+            emit(node.operand)
+            if isinstance(node.op, ast.USub):
+                prog.append((OP["NEG"], 0.0))
+            elif isinstance(node.op, ast.Not):
+                prog.append((OP["NOT"], 0.0))
+            elif not isinstance(node.op, ast.UAdd):
+                raise _NotTranslatable("unary operator")
+            return
+        if isinstance(node, ast.BinOp):
+            if type(node.op) not in _BINOPS:
+                raise _NotTranslatable("binary operator")
+            emit(node.left)
+            emit(node.right)
+            prog.append((OP[_BINOPS[type(node.op)]], 0.0))
+            return
+        if isinstance(node, ast.BoolOp):
+            emit(node.values[0])
+            for v in node.values[1:]:
+                emit(v)
+                prog.append((OP["AND" if isinstance(node.op, ast.And) else "OR"], 0.0))
+            return
+        if isinstance(node, ast.Compare):
+            if any(type(o) not in _CMPOPS for o in node.ops):
+                raise _NotTranslatable("comparison operator")
+            # a < b < c  ->  (a < b) and (b < c); operands have no side effects, so b may be evaluated twice
+            operands = [node.left] + list(node.comparators)
+            for k, o in enumerate(node.ops):
+                emit(operands[k])
+                emit(operands[k + 1])
+                prog.append((OP[_CMPOPS[type(o)]], 0.0))
+                if k:
+                    prog.append((OP["AND"], 0.0))
+            return
+        if isinstance(node, ast.IfExp):
+            emit(node.test)
+            emit(node.body)
+            emit(node.orelse)
+            prog.append((OP["SELECT"], 0.0))
+            return
+        if isinstance(node, ast.Call):
+            if node.keywords:
+                raise _NotTranslatable("keyword arguments")
+            f, args = node.func, node.args
+            if isinstance(f, ast.Name):
+                if f.id == "abs" and len(args) == 1:
+                    emit(args[0]); prog.append((OP["ABS"], 0.0)); return
+                if f.id in ("min", "max"):
+                    return fold(args, f.id.upper())
+                if f.id == "pow" and len(args) == 2:
+                    emit(args[0]); emit(args[1]); prog.append((OP["POW"], 0.0)); return
+                if f.id == "float" and len(args) == 1:
+                    return emit(args[0])
+                if f.id == "int" and len(args) == 1:
+                    emit(args[0]); prog.append((OP["TRUNC"], 0.0)); return
+                if f.id == "bool" and len(args) == 1:
+                    emit(args[0]); prog.append((OP["TRUTH"], 0.0)); return
+                raise _NotTranslatable(f"builtin {f.id}")
+            base, name = f.value.id, f.attr
+            if base == "params":
+                return const(param_value(node))
+            table = _UNARY_NP if base == "np" else _UNARY_MATH
+            if name in table and len(args) == 1:
+                emit(args[0]); prog.append((OP[table[name]], 0.0)); return
+            if base == "np":
+                if name == "where" and len(args) == 3:
+                    emit(args[0]); emit(args[1]); emit(args[2]); prog.append((OP["SELECT"], 0.0)); return
+                if name in ("maximum", "minimum") and len(args) == 2:
+                    emit(args[0]); emit(args[1]); prog.append((OP["NPMAX" if name == "maximum" else "NPMIN"], 0.0)); return
+                if name == "clip" and len(args) == 3:
+                    emit(args[0]); emit(args[1]); prog.append((OP["NPMAX"], 0.0))
+                    emit(args[2]); prog.append((OP["NPMIN"], 0.0)); return
+                if name == "power" and len(args) == 2:
+                    emit(args[0]); emit(args[1]); prog.append((OP["POW"], 0.0)); return
+                if name == "heaviside" and len(args) == 2:
+                    emit(args[0]); emit(args[1]); prog.append((OP["HEAVISIDE"], 0.0)); return
+                if name in ("zeros_like", "ones_like") and len(args) == 1:
+                    return const(0.0 if name == "zeros_like" else 1.0)
+                if name == "full_like" and len(args) == 2:
+                    return emit(args[1])
+            raise _NotTranslatable(f"call {base}.{name}")
+        raise _NotTranslatable(type(node).__name__)
+
+    try:
+        emit(ast.parse(expr.source, mode="eval"))
+    except (_NotTranslatable, ValueError, SyntaxError):
+        return None
+    # stack discipline (the library checks it again)
+    depth = peak = 0
+    for op, _ in prog:
+        name = OPS[op]
+        pops = 0 if op <= OP["T"] else 3 if name == "SELECT" else 1 if (op >= OP["ABS"] or name in ("NEG", "NOT", "TRUTH")) else 2
+        depth += 1 - pops
+        peak = max(peak, depth)
+    if depth != 1 or peak > MAX_STACK or len(prog) > MAX_OPS:
+        return None
+    return prog
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # grids
 # ---------------------------------------------------------------------------------------------------------------
 def cell_coordinates(mask: np.ndarray):
@@ -143,6 +324,8 @@ class CustomGeneration:
         self.E = np.asarray(E_bins, dtype=float)
         self.x, self.y = cell_coordinates(np.asarray(mask, dtype=bool))
         self.time_dependent = self.expr.uses("t")
+        # a time-dependent body that has a per-value meaning runs on the device (qpb_upload_generation_program)
+        self.program = compile_program(self.expr, self.params) if self.time_dependent else None
 
     def __call__(self, t: float) -> np.ndarray:
         ne, n = self.E.size, self.x.size

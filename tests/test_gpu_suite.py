@@ -74,7 +74,7 @@ CUSTOM = cases.custom_mode_cases()
 
 @pytest.mark.parametrize("case", CUSTOM, ids=[c["name"] for c in CUSTOM])
 def test_user_expression_options_match_reference(case):
-    """Custom generation bodies (resident when time independent, per-step uploads otherwise), initial-condition specs
+    """Custom generation bodies (resident when time independent, evaluated on the device otherwise), initial-condition specs
     and gap expressions through the drop-in, against the unmodified reference (solver.py:918-962, 1094-1124,
     1186-1196; reference tests: tests/test_initial_condition_split.py:144-173, tests/test_regressions.py:435-499)."""
     import qpsim_b200 as Q
@@ -90,7 +90,61 @@ def test_user_expression_options_match_reference(case):
     if case["name"] == "custom_gen_static":
         assert info["generation_uploads"] == 1          # evaluated and uploaded once, resident afterwards
     if case["name"] == "custom_gen_timedep":
-        assert info["generation_uploads"] == info["steps_done"] == 6
+        # the body runs on the device at the time of every step: no host evaluation, no NE x N upload
+        assert info["generation_uploads"] == 0 and info["steps_done"] == 6 and info["generation_on_device"]
+
+
+def test_time_dependent_custom_generation_on_the_device_and_on_the_host_agree(monkeypatch):
+    """The same time-dependent body translated into a device program (QPB_GEN_PROGRAM, whole batches of steps) and
+    evaluated on the host with one upload per step (QPB_NO_GEN_PROGRAM=1): same run to rounding of the libm calls."""
+    import qpsim_b200 as Q
+    case = [c for c in CUSTOM if c["name"] == "custom_gen_timedep"][0]
+    a = helpers.run_dropin(case)
+    assert Q.solver.last_run_info["generation_on_device"]
+    monkeypatch.setenv("QPB_NO_GEN_PROGRAM", "1")
+    b = helpers.run_dropin(case)
+    assert not Q.solver.last_run_info["generation_on_device"] and Q.solver.last_run_info["generation_uploads"] == 6
+    helpers.assert_close(a["state"], b["state"], "device program vs host evaluation", rtol=1e-12)
+
+
+GEN_BODIES = [
+    "params['a'] * np.exp(-t / 0.5) * np.where(E < 400.0, 1.0, 0.25) * (0.5 + y * x)",
+    "1e-8 * (1 + math.sin(6.0 * t) ** 2) * max(E, 250.0) / 250.0 * abs(x - 0.5)",
+    "(2e-8 if E < 300 else 5e-9) * (t < 0.4 or x > 0.7) + 1e-9 * (0.2 < y <= 0.6)",
+    "np.clip(1e-8 * np.power(E / 200.0, -1.5) * np.heaviside(0.5 - t, 0.5), 1e-10, 4e-9) + 1e-9 * (int(10 * x) % 3) + 0 * t",
+    "1e-8 * np.minimum(np.maximum(x, 0.3), y + 0.1) * np.tanh(t) * np.sqrt(E) / (1.0 + np.log10(E)) + 1e-9 * (7 // 2) * float(t > 0)",
+    "np.full_like(x, 3e-9) * (not (t > 1.0)) * np.ones_like(y) + pow(x, 2) * 1e-9 * bool(E > 0) * np.cos(t) ** 2",
+]
+
+
+@pytest.mark.parametrize("body", GEN_BODIES)
+def test_generation_program_reproduces_the_host_evaluator(body):
+    """qpb_eval_generation_program: the device's value of g(E, x, y, t) for every bin and cell against the package's
+    host evaluator (itself pinned bit for bit to the reference's, tests/test_userexpr.py)."""
+    import qpsim_b200 as Q
+    from qpsim_b200 import capi, userexpr
+    mask = cases.annulus_mask(24)
+    n = int(mask.sum())
+    E, dE = Q.build_energy_grid(180.0, 1.0, 4.0, 9)
+    spec = Q.ExternalGenerationSpec(mode="custom", custom_body=body, custom_params={"a": 3e-8})
+    gen = userexpr.CustomGeneration(spec, E, mask)
+    assert gen.program is not None
+    with capi.Context(ny=mask.shape[0], nx=mask.shape[1], ne=E.size, nw=0, ncell=n, flags=0, dx=1.0, dE=dE) as ctx:
+        ctx.upload_generation_program(gen.program, gen.E, gen.x, gen.y)
+        for t in (0.0, 0.3, 1.7):
+            got, want = ctx.eval_generation_program(t), gen(t)
+            np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-30)
+
+
+@pytest.mark.parametrize("body,msg", [("1e-8 * (0.5 - t) * x", "negative values"), ("1e-8 * np.sqrt(0.7 - t) + 0 * x", "non-finite")])
+def test_generation_program_values_are_checked_like_the_reference(body, msg):
+    """solver.py:954-962: a custom body that turns negative or non-finite during the run raises ValueError with the
+    reference's messages - also when the values never reach the host."""
+    import qpsim_b200 as Q
+    case = dict([c for c in CUSTOM if c["name"] == "custom_gen_timedep"][0])
+    case["generation"] = dict(mode="custom", custom_body=body, custom_params={})
+    with pytest.raises(ValueError, match=msg):
+        helpers.run_dropin(case)
 
 
 def test_unsafe_custom_generation_is_rejected():
