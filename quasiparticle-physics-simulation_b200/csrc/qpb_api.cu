@@ -268,6 +268,10 @@ extern "C" int qpb_create(const qpb_config *cfg, qpb_ctx **out) {
     if (!(c->cfg.diff_tol > 0.0)) c->cfg.diff_tol = 5e-14;   // componentwise: see qpb_prepare_diffusion
     c->ncd = cfg->ny * cfg->nx;
     c->maxit = 512;
+    if (const char *e = getenv("QPB_MAXIT")) {   // iteration cap of the sweep iteration (tests: force the Krylov fall-back)
+        const int v = atoi(e);
+        if (v >= 1 && v <= 512) c->maxit = v;
+    }
     auto fail = [&](int rc) {
         qpb_destroy(c);
         return rc;

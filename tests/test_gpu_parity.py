@@ -246,6 +246,25 @@ def test_bin_resident_cluster_solve_matches_the_launched_sweeps_and_the_oracle(s
     np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
 
 
+@pytest.mark.parametrize("resident", ["1", "0"], ids=["launched_sweeps", "bin_resident"])
+def test_a_sweep_iteration_that_hits_its_cap_falls_back_to_the_krylov_solve(resident, monkeypatch):
+    """The reference's SuperLU solve always returns; the sweep iteration has a cap (512 iterations, QPB_MAXIT here to
+    reach it on purpose).  A solve that hits the cap restarts from b with the preconditioned BiCGStab solve - from the
+    launched sweeps and from the bin-resident solve (which has written b out for exactly this case) - and the run still
+    matches the oracle."""
+    case = cases.meander_c2(ny=64, nx=128, ne=4, steps=2)
+    case["enable_recombination"] = case["enable_scattering"] = False
+    case["generation"] = None
+    monkeypatch.setenv("QPB_MAXIT", "3")
+    monkeypatch.setenv("QPB_NO_RESIDENT", resident)
+    got = helpers.run_dropin(case, enforce_pauli=False)
+    want = helpers.run_oracle(case)
+    helpers.assert_close(got["state"], want["state"], "n(E,cell)")
+    monkeypatch.setenv("QPB_NO_KRYLOV", "1")
+    with pytest.raises(Exception, match="did not reach tolerance"):
+        helpers.run_dropin(case, enforce_pauli=False)
+
+
 @pytest.mark.parametrize("flags", [(True, True), (True, False), (False, True)])
 def test_frozen_uniform_phonons_use_packed_kernels_and_match(flags, monkeypatch):
     """freeze_phonon_dynamics with the same occupations in every cell runs the fused 4-product kernel
