@@ -264,6 +264,14 @@ int qpb_device_ptr(qpb_ctx *ctx, int which, void **ptr, int64_t *bytes);
 int qpb_scatter_block(qpb_ctx *ctx, const double *d_block, int32_t cell0, int32_t count);
 int qpb_gather_block(qpb_ctx *ctx, double *d_block, int32_t cell0, int32_t count);
 int qpb_add_generation(qpb_ctx *ctx, double scale, double rate);
+/* The custom forms of the same stage (evaluate_external_generation, solver.py:918-962) for a context that holds a slice
+ * of the cells:  state += scale * g  with g the uploaded program evaluated at time t (qpb_upload_generation_program with
+ * the slice's coordinates), or a host array g[ne][ncell] (uploaded by the call and kept; NULL = the array of the last
+ * call: a time-independent body).  Stream ordered.  qpb_generation_status waits for the stream and returns and clears
+ * the program's verdict: bit 0 = a value was not finite, bit 1 = a value was negative. */
+int qpb_add_generation_program(qpb_ctx *ctx, double scale, double t);
+int qpb_add_generation_array(qpb_ctx *ctx, double scale, const double *array);
+int qpb_generation_status(qpb_ctx *ctx, int32_t *flags);
 /* Enqueue all further work of the context on the caller's CUDA stream (a cudaStream_t; NULL = back to the stream
  * the library created).  The host driver passes the stream its NCCL calls are ordered against, so stages and
  * exchanges need no host synchronisation between them.  scatter/gather_block and add_generation are stream

@@ -87,6 +87,7 @@ EXPORTED = [
     "qpb_add_generation", "qpb_set_stream", "qpb_get_frames", "qpb_trim_cache", "qpb_set_state_uniform_phonons", "qpb_pauli_record", "qpb_pauli_fetch", "qpb_set_exchange", "qpb_collide_exchange",
     "qpb_ipc_export", "qpb_ipc_open", "qpb_ipc_close", "qpb_euler_step", "qpb_set_state_separable",
     "qpb_frames_snapshot", "qpb_frames_download", "qpb_upload_generation_program", "qpb_eval_generation_program",
+    "qpb_add_generation_program", "qpb_add_generation_array", "qpb_generation_status",
 ]
 
 
@@ -204,6 +205,9 @@ def load_library():
     lib.qpb_scatter_block.argtypes = [vp, vp, i32, i32]
     lib.qpb_gather_block.argtypes = [vp, vp, i32, i32]
     lib.qpb_add_generation.argtypes = [vp, dbl, dbl]
+    lib.qpb_add_generation_program.argtypes = [vp, dbl, dbl]
+    lib.qpb_add_generation_array.argtypes = [vp, dbl, vp]
+    lib.qpb_generation_status.argtypes = [vp, C.POINTER(i32)]
     lib.qpb_set_stream.argtypes = [vp, vp]
     lib.qpb_measure_fp64.argtypes = [C.c_int, C.POINTER(dbl)]
     lib.qpb_measure_copy.argtypes = [C.c_int, i64, C.POINTER(dbl)]
@@ -469,6 +473,23 @@ class Context:
 
     def add_generation(self, scale: float, rate: float):
         self._check(self.lib.qpb_add_generation(self.handle, float(scale), float(rate)))
+
+    def add_generation_program(self, scale: float, t: float):
+        self._check(self.lib.qpb_add_generation_program(self.handle, float(scale), float(t)))
+
+    def add_generation_array(self, scale: float, array=None):
+        """state += scale * g with g[ne][ncell] a host array (kept on the device), or the array of the last call."""
+        if array is None:
+            self._check(self.lib.qpb_add_generation_array(self.handle, float(scale), None))
+            return
+        a = _f64(array, (self.ne, self.ncell))
+        _up(a)
+        self._check(self.lib.qpb_add_generation_array(self.handle, float(scale), _ptr(a)))
+
+    def generation_status(self) -> int:
+        v = C.c_int32(0)
+        self._check(self.lib.qpb_generation_status(self.handle, C.byref(v)))
+        return int(v.value)
 
     def set_stream(self, cuda_stream: int | None):
         self._check(self.lib.qpb_set_stream(self.handle, C.c_void_p(int(cuda_stream)) if cuda_stream else None))

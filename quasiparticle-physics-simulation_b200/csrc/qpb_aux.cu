@@ -415,6 +415,51 @@ extern "C" int qpb_add_generation(qpb_ctx *c, double scale, double rate) {
     return qpbk_add_generation(c, scale, rate, nullptr);
 }
 
+extern "C" int qpb_add_generation_program(qpb_ctx *c, double scale, double t) {
+    if (!c || !c->have_geom || !c->d_genprog || c->gen_nops <= 0) {
+        qpb_set_error("qpb_add_generation_program: context without geometry or without an uploaded program");
+        return QPB_E_INVALID;
+    }
+    QPB_CUDA(cudaSetDevice(c->cfg.device));
+    return qpbk_generation_program(c, scale, t, nullptr);
+}
+
+extern "C" int qpb_add_generation_array(qpb_ctx *c, double scale, const double *array) {
+    if (!c || !c->have_geom) {
+        qpb_set_error("qpb_add_generation_array: context without geometry");
+        return QPB_E_INVALID;
+    }
+    QPB_CUDA(cudaSetDevice(c->cfg.device));
+    const size_t n = (size_t)c->cfg.ne * c->cfg.ncell;
+    if (array) {
+        if (!c->d_gen) QPB_CUDA(qpb_dev_malloc((void **)&c->d_gen, sizeof(double) * n));
+        c->gen_resident = false;
+        QPB_CUDA(cudaMemcpyAsync(c->d_gen, array, sizeof(double) * n, cudaMemcpyHostToDevice, c->stream));
+        QPB_CUDA(cudaStreamSynchronize(c->stream));   // the caller's buffer is free again
+        c->gen_resident = true;
+    } else if (!c->d_gen || !c->gen_resident) {
+        qpb_set_error("qpb_add_generation_array: no generation array is resident");
+        return QPB_E_INVALID;
+    }
+    return qpbk_add_generation(c, scale, 0.0, c->d_gen);
+}
+
+extern "C" int qpb_generation_status(qpb_ctx *c, int32_t *flags) {
+    if (!c || !flags) {
+        qpb_set_error("qpb_generation_status: null argument");
+        return QPB_E_INVALID;
+    }
+    QPB_CUDA(cudaSetDevice(c->cfg.device));
+    *flags = 0;
+    if (!c->d_gen_flag) return QPB_OK;
+    int v = 0;
+    QPB_CUDA(cudaMemcpyAsync(&v, c->d_gen_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    QPB_CUDA(cudaMemsetAsync(c->d_gen_flag, 0, sizeof(int), c->stream));
+    QPB_CUDA(cudaStreamSynchronize(c->stream));
+    *flags = v;
+    return QPB_OK;
+}
+
 // ---- roofline denominators ------------------------------------------------------------------------------
 namespace {
 __global__ void k_fp64_peak(double *out, int iters) {

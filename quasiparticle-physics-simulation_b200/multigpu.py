@@ -396,6 +396,18 @@ class DeviceStages:
     def add_generation(self, scale, rate):
         self.ctx_c.add_generation(scale, rate)
 
+    def upload_generation_program(self, program, E_bins, x, y):
+        self.ctx_c.upload_generation_program(program, E_bins, x, y)
+
+    def add_generation_program(self, scale, t):
+        self.ctx_c.add_generation_program(scale, t)
+
+    def add_generation_array(self, scale, array=None):
+        self.ctx_c.add_generation_array(scale, array)
+
+    def generation_status(self):
+        return self.ctx_c.generation_status()
+
     def diffuse(self, slot):
         self.ctx_d.diffuse(slot)
 
@@ -483,10 +495,17 @@ def _run_spmd(su: dict, progress_callback=None) -> dict:
     mask, ne, n, nw = su["mask"], su["ne"], su["n"], su["nw"]
     gen = su["generation"]
     gmode = "none" if gen is None else gen.mode.strip().lower()
-    if gmode == "custom":
-        raise ValueError("external_generation mode 'custom' is not available with devices=[...]; run it on one device")
     plan = ShardPlan(ne, n, world, rank, interleave=True)
     c0, c1 = plan.cells()
+    custom = None
+    if gmode == "custom":
+        # evaluate_external_generation (solver.py:918-962) on this rank's cells: a time-dependent body as a device program,
+        # a time-independent one as an array that is evaluated and uploaded once; a body without a per-value meaning on
+        # the host, one slice per step
+        from . import userexpr
+        custom = userexpr.CustomGeneration(gen, su["E_bins"], mask)
+        if os.environ.get("QPB_NO_GEN_PROGRAM", "0") == "1":
+            custom.program = None
     coll = su["scattering"] or su["recombination"]
     state_local = (su["state"][:, c0:c1] if su["state"] is not None
                    else su["weights"][:, None] * su["spatial"][None, c0:c1])
@@ -556,6 +575,9 @@ def _run_spmd(su: dict, progress_callback=None) -> dict:
             store(0.0)
             full_steps, total_steps, store_every = su["full_steps"], su["total_steps"], su["store_every"]
             t, step = 0.0, 0
+            gen_uploads = 0
+            if custom is not None and custom.program is not None:
+                stages.upload_generation_program(custom.program, custom.E, custom.x[c0:c1], custom.y[c0:c1])
             while step < total_steps:
                 nxt = min(((step // store_every) + 1) * store_every, total_steps)
                 if nxt > full_steps and step < full_steps:
@@ -566,6 +588,14 @@ def _run_spmd(su: dict, progress_callback=None) -> dict:
                 tt = t
                 for k in range(count):
                     rate = None
+                    if custom is not None:
+                        if custom.program is not None:
+                            stages.add_generation_program(h, tt)
+                        elif custom.time_dependent or gen_uploads == 0:
+                            stages.add_generation_array(h, np.ascontiguousarray(custom(tt)[:, c0:c1]))
+                            gen_uploads += 1
+                        else:
+                            stages.add_generation_array(h, None)
                     if gmode == "constant":
                         rate = float(gen.rate)
                     elif gmode == "pulse" and gen.pulse_start <= tt < gen.pulse_start + gen.pulse_duration:
@@ -573,6 +603,17 @@ def _run_spmd(su: dict, progress_callback=None) -> dict:
                     stepper.step(h, 1 if is_final else 0, rate, pauli_slot=k)
                     tt += h
                 merged = stepper.merge_pauli(stages.pauli_fetch(count))
+                if custom is not None and custom.program is not None:
+                    # the device-side checks of the body, agreed between the ranks (solver.py:954-962, same messages)
+                    bad = stages.generation_status()
+                    flag = torch.tensor([bad & 1, (bad >> 1) & 1], dtype=torch.int32, device=f"cuda:{device}")
+                    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+                    bad = int(flag[0].item()) | (int(flag[1].item()) << 1)
+                    if bad & 1:
+                        raise ValueError("External generation mode 'custom' produced non-finite values.")
+                    if bad & 2:
+                        raise ValueError("External generation mode 'custom' produced negative values. "
+                                         "Generation rates must be non-negative.")
                 for k in range(count):
                     policy.check(merged[k], step + k + 1, t + h)
                     t += h
@@ -581,6 +622,8 @@ def _run_spmd(su: dict, progress_callback=None) -> dict:
                     times.append(float(t))
                     store(t)
             info = dict(stages.ctx_c.diag())
+            info.update(generation_uploads=gen_uploads,
+                        generation_on_device=bool(custom is not None and custom.program is not None))
             info.update(world=world, fused_exchange=bool(fused), exchanges=stepper.exchanges,
                         exchange_bytes_per_gpu=plan.exchange_bytes())
             if stages.ctx_d is not None:
@@ -644,7 +687,15 @@ def run_dropin(setup: dict, progress_callback=None) -> dict:
         port = sk.getsockname()[1]
     with tempfile.TemporaryDirectory() as tmp:
         outpath = os.path.join(tmp, "result.pkl")
-        mp.spawn(_spawn_worker, args=(world, setup, port, outpath), nprocs=world, join=True)
+        try:
+            mp.spawn(_spawn_worker, args=(world, setup, port, outpath), nprocs=world, join=True)
+        except mp.ProcessRaisedException as exc:
+            # a ValueError of the loop (Pauli limits, custom generation checks) stays a ValueError for the caller, like
+            # in the single-device path and in the reference
+            last = str(exc).strip().splitlines()[-1]
+            if last.startswith("ValueError: "):
+                raise ValueError(last[len("ValueError: "):]) from None
+            raise
         with open(outpath, "rb") as f:
             return pickle.load(f)
 

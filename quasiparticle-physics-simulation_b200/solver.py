@@ -208,7 +208,9 @@ def run_2d_crank_nicolson(
         raise ValueError("Diffusion coefficient must be positive.")
     if store_every <= 0:
         store_every = 1
-    if devices is not None and len(devices) == 1:
+    # QPB_FORCE_SHARDED=1 (tests): a one-entry device list also takes the sharded loop, as a world of one rank
+    force_sharded = devices is not None and os.environ.get("QPB_FORCE_SHARDED", "0") == "1"
+    if devices is not None and len(devices) == 1 and not force_sharded:
         device = int(devices[0])
     mask = np.asarray(mask)
     if initial_field.shape != mask.shape:
@@ -380,7 +382,7 @@ def run_2d_crank_nicolson(
         flags |= capi.F_FREEZE_PHONONS
 
     want_ph_hist = phonon_history_out is not None
-    if devices is not None and len(devices) > 1:
+    if devices is not None and (len(devices) > 1 or force_sharded):
         from . import multigpu
 
         setup = dict(

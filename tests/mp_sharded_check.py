@@ -26,6 +26,7 @@ def main():
             ("annulus_32x5_mixed", next(c for c in cases.golden_cases() if c["name"] == "annulus_32x5_mixed")),
             ("nonuniform_10x14x8", next(c for c in cases.golden_cases() if c["name"] == "nonuniform_10x14x8")),
             ("c2_meander_96x80x24", cases.meander_c2(ny=96, nx=80, ne=24, steps=3))]
+    runs += [(c["name"], c) for c in cases.custom_mode_cases() if c["name"] in ("custom_gen_static", "custom_gen_timedep")]
     for name, case in runs:
         single = helpers.run_dropin(case, device=local) if rank == 0 else None
         for fused in (True, False):

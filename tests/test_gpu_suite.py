@@ -174,3 +174,33 @@ def test_nonuniform_gap_trap_96x96x16_matches_reference():
     helpers.assert_close(got["state"][keep], want["state"], "n(E,cell)")
     np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
     helpers.assert_close(got["phonons"][keep][:, :, want["ph_cells"]], want["phonons"], "n_ph", rtol=helpers.RTOL_PHONON)
+
+
+@pytest.mark.parametrize("name", ["custom_gen_static", "custom_gen_timedep", "custom_gen_scalar_body"])
+def test_custom_generation_in_the_sharded_loop(name, monkeypatch):
+    """The sharded loop behind devices=[...] (multigpu._run_spmd; here as a world of one spawned rank,
+    QPB_FORCE_SHARDED=1) applies custom generation per rank on its own cells: the device program for time-dependent
+    bodies, one evaluated-and-uploaded slice for time-independent ones.  Against the unmodified reference."""
+    import qpsim_b200 as Q
+    case = [c for c in CUSTOM if c["name"] == name][0]
+    gold = helpers.load_golden("custom_modes")
+    monkeypatch.setenv("QPB_FORCE_SHARDED", "1")
+    got = helpers.run_dropin(case, devices=[0])
+    info = dict(Q.solver.last_run_info)
+    assert info.get("world") == 1, info
+    p = name + "/"
+    helpers.assert_close(got["state"], gold[p + "state"], "n(E,cell)")
+    np.testing.assert_allclose(got["mass"], gold[p + "mass"], rtol=helpers.RTOL)
+    if name == "custom_gen_timedep":
+        assert info["generation_on_device"] and info["generation_uploads"] == 0
+    else:
+        assert info["generation_uploads"] == 1
+
+
+def test_sharded_custom_generation_raises_the_reference_errors(monkeypatch):
+    import qpsim_b200 as Q
+    case = dict([c for c in CUSTOM if c["name"] == "custom_gen_timedep"][0])
+    case["generation"] = dict(mode="custom", custom_body="1e-8 * (0.5 - t) * x", custom_params={})
+    monkeypatch.setenv("QPB_FORCE_SHARDED", "1")
+    with pytest.raises(ValueError, match="negative values"):
+        helpers.run_dropin(case, devices=[0])
