@@ -750,6 +750,7 @@ def run_sharded(args, strong: bool):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": n * ne * K / float(t_e2e.item()), "unit": UNIT, "seconds": float(t_e2e.item()),
                     "h2d_bytes_per_step": float(xfer[0].item()) / K, "d2h_bytes_per_step": float(xfer[1].item()) / K,
+                    "breakdown_rank0_s": dict(Q.solver.last_run_info.get("seconds", {})) if world > 1 else None,
                     "note": e2e_note + "; bytes counted at the copy calls of the binding, summed over ranks"},
             "roofline": dominant, "roofline_sweeps": roof_sweep, "roofline_collision": roof_coll,
             "time_shares": shares, "parity": parity, "max_occupation": max(r[0] for r in merged),

@@ -406,57 +406,100 @@ extern "C" int qpb_upload_geometry(qpb_ctx *c, const uint8_t *mask, const double
             qpb_set_error("qpb_upload_geometry: boundary arrays are required when diffusion is enabled");
             return QPB_E_INVALID;
         }
-        c->h_bcx.assign(bcx, bcx + ncd);
-        c->h_bcy.assign(bcy, bcy + ncd);
-        c->h_src.assign(source, source + ncd);
+        {   // host copies (qpb_prepare_diffusion reads them), first touched by three threads at once
+            std::thread ta([&] { c->h_bcx.assign(bcx, bcx + ncd); }), tb([&] { c->h_bcy.assign(bcy, bcy + ncd); });
+            c->h_src.assign(source, source + ncd);
+            ta.join();
+            tb.join();
+        }
         QPB_CUDA(cudaMemcpyAsync(c->d_bcx, bcx, sizeof(double) * ncd, cudaMemcpyHostToDevice, c->stream));
         QPB_CUDA(cudaMemcpyAsync(c->d_bcy, bcy, sizeof(double) * ncd, cudaMemcpyHostToDevice, c->stream));
         QPB_CUDA(cudaMemcpyAsync(c->d_srcgeom, source, sizeof(double) * ncd, cudaMemcpyHostToDevice, c->stream));
-        // Gershgorin bounds and a commutator probe of Gx, Gy (unit coefficient)
+        // Gershgorin bounds and a commutator probe of Gx, Gy (unit coefficient); the passes over the grid run on a few
+        // host threads (row blocks): at 2048 x 2048 they were 0.15 s of every run's setup
+        const int nth = std::max(1, std::min(8, std::min(ny / 64, (int)std::thread::hardware_concurrency())));
+        auto rows_parallel = [&](auto &&fn) {
+            if (nth <= 1) {
+                fn(0, 0, ny);
+                return;
+            }
+            std::vector<std::thread> th;
+            for (int t = 0; t < nth; ++t)
+                th.emplace_back([&, t] { fn(t, (int)((long long)ny * t / nth), (int)((long long)ny * (t + 1) / nth)); });
+            for (auto &x : th) x.join();
+        };
+        std::vector<double> pgx(nth, 0.0), pgy(nth, 0.0), pgm(nth, 0.0);
+        std::vector<double> r((size_t)ncd);
+        rows_parallel([&](int t, int ya, int yb) {
+            double gx = 0.0, gy = 0.0, gmin = 0.0;
+            for (int p = ya * nx; p < yb * nx; ++p) {
+                const unsigned f = c->h_flags[p];
+                double rv = 0.0;
+                if (f & QPB_IN) {
+                    const int dxl = ((f & QPB_LK_L) ? 1 : 0) + ((f & QPB_LK_R) ? 1 : 0);
+                    const int dyl = ((f & QPB_LK_U) ? 1 : 0) + ((f & QPB_LK_D) ? 1 : 0);
+                    gx = std::max(gx, 2.0 * dxl + std::fabs(bcx[p]));
+                    gy = std::max(gy, 2.0 * dyl + std::fabs(bcy[p]));
+                    gmin = std::min(gmin, std::min(bcx[p], bcy[p]));
+                    // probe vector: a fixed pseudo-random value in [0.5, 1.5) per cell (splitmix64 of the index)
+                    unsigned long long z = (unsigned long long)p * 0x9E3779B97F4A7C15ull + 0x2545F4914F6CDD1Dull;
+                    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                    z ^= z >> 31;
+                    rv = 0.5 + (double)(z >> 11) * (1.0 / 9007199254740992.0);
+                }
+                r[p] = rv;
+            }
+            pgx[t] = gx; pgy[t] = gy; pgm[t] = gmin;
+        });
         double gx = 0.0, gy = 0.0, gmin = 0.0;
-        for (int p = 0; p < ncd; ++p) {
-            const unsigned f = c->h_flags[p];
-            if (!(f & QPB_IN)) continue;
-            const int dxl = ((f & QPB_LK_L) ? 1 : 0) + ((f & QPB_LK_R) ? 1 : 0);
-            const int dyl = ((f & QPB_LK_U) ? 1 : 0) + ((f & QPB_LK_D) ? 1 : 0);
-            gx = std::max(gx, 2.0 * dxl + std::fabs(bcx[p]));
-            gy = std::max(gy, 2.0 * dyl + std::fabs(bcy[p]));
-            gmin = std::min(gmin, std::min(bcx[p], bcy[p]));
+        for (int t = 0; t < nth; ++t) {
+            gx = std::max(gx, pgx[t]);
+            gy = std::max(gy, pgy[t]);
+            gmin = std::min(gmin, pgm[t]);
         }
         c->gmin = gmin;
         c->gmax_x = gx;
         c->gmax_y = gy;
-        std::mt19937_64 rng(12345);
-        std::uniform_real_distribution<double> U(0.5, 1.5);
-        std::vector<double> r(ncd, 0.0), t1(ncd), t2(ncd), t3(ncd), t4(ncd);
-        for (int p = 0; p < ncd; ++p)
-            if (c->h_flags[p] & QPB_IN) r[p] = U(rng);
-        auto apply = [&](const std::vector<double> &in, std::vector<double> &o, bool xdir) {
-            for (int p = 0; p < ncd; ++p) {
-                const unsigned f = c->h_flags[p];
-                double v = 0.0;
-                if (f & QPB_IN) {
-                    if (xdir) {
-                        v = bcx[p] * in[p];
-                        if (f & QPB_LK_L) v += in[p] - in[p - 1];
-                        if (f & QPB_LK_R) v += in[p] - in[p + 1];
-                    } else {
-                        v = bcy[p] * in[p];
-                        if (f & QPB_LK_U) v += in[p] - in[p - nx];
-                        if (f & QPB_LK_D) v += in[p] - in[p + nx];
-                    }
-                }
-                o[p] = v;
-            }
+        // (Gy Gx - Gx Gy) r in one pass: both products of a cell from the 3 x 3 neighbourhood of r, no grid-sized
+        // temporaries (they were 130 MB of first-touch page faults at 2048 x 2048)
+        auto gxr = [&](int p) {   // (Gx r)(p)
+            const unsigned f = c->h_flags[p];
+            if (!(f & QPB_IN)) return 0.0;
+            double v = bcx[p] * r[p];
+            if (f & QPB_LK_L) v += r[p] - r[p - 1];
+            if (f & QPB_LK_R) v += r[p] - r[p + 1];
+            return v;
         };
-        apply(r, t1, true);
-        apply(t1, t2, false);  // Gy Gx r
-        apply(r, t3, false);
-        apply(t3, t4, true);   // Gx Gy r
+        auto gyr = [&](int p) {   // (Gy r)(p)
+            const unsigned f = c->h_flags[p];
+            if (!(f & QPB_IN)) return 0.0;
+            double v = bcy[p] * r[p];
+            if (f & QPB_LK_U) v += r[p] - r[p - nx];
+            if (f & QPB_LK_D) v += r[p] - r[p + nx];
+            return v;
+        };
+        std::vector<double> pd(nth, 0.0), pv(nth, 0.0);
+        rows_parallel([&](int t, int ya, int yb) {
+            double dm = 0.0, vm = 0.0;
+            for (int p = ya * nx; p < yb * nx; ++p) {
+                const unsigned f = c->h_flags[p];
+                if (!(f & QPB_IN)) continue;
+                const double ax = gxr(p), ay = gyr(p);
+                double yx = bcy[p] * ax, xy = bcx[p] * ay;   // Gy (Gx r), Gx (Gy r)
+                if (f & QPB_LK_U) yx += ax - gxr(p - nx);
+                if (f & QPB_LK_D) yx += ax - gxr(p + nx);
+                if (f & QPB_LK_L) xy += ay - gyr(p - 1);
+                if (f & QPB_LK_R) xy += ay - gyr(p + 1);
+                dm = std::max(dm, std::fabs(yx - xy));
+                vm = std::max(vm, std::max(std::fabs(yx), std::fabs(xy)));
+            }
+            pd[t] = dm; pv[t] = vm;
+        });
         double dmax = 0.0, vmax = 0.0;
-        for (int p = 0; p < ncd; ++p) {
-            dmax = std::max(dmax, std::fabs(t2[p] - t4[p]));
-            vmax = std::max(vmax, std::max(std::fabs(t2[p]), std::fabs(t4[p])));
+        for (int t = 0; t < nth; ++t) {
+            dmax = std::max(dmax, pd[t]);
+            vmax = std::max(vmax, pv[t]);
         }
         c->commuting = dmax <= 1e-12 * std::max(vmax, 1.0);
     }
@@ -711,10 +754,13 @@ extern "C" int qpb_prepare_diffusion(qpb_ctx *c, int slot, double dt) {
     s.ready = true;
     s.fast = false;
     if (!vard) {
-        int rc = qpbk_prepare_fast(c, s);
+        // a full rectangle that takes the direct spectral solve needs none of the sweep tables
+        int rc = qpbk_prepare_spectral(c, s);
         if (rc != QPB_OK) return rc;
-        if ((rc = qpbk_prepare_spectral(c, s)) != QPB_OK) return rc;
-        if ((rc = qpbr_plan(c, s)) != QPB_OK) return rc;
+        if (!s.spectral) {
+            if ((rc = qpbk_prepare_fast(c, s)) != QPB_OK) return rc;
+            if ((rc = qpbr_plan(c, s)) != QPB_OK) return rc;
+        }
     } else if (!s.krylov) {
         int rc = qpbk_prepare_fast(c, s);   // chunked sweeps with per-line pivot tables
         if (rc != QPB_OK) return rc;

@@ -274,6 +274,9 @@ class ShardedProblem:
     # large grids: a rank never materialises arrays of the whole run
     state_local: np.ndarray | None = None    # [NE, N_g] this rank's cells only (used when state is None)
     phonon_bins: np.ndarray | None = None    # [Nw] the same occupations in every cell (used when phonons is None)
+    # default initial state as its factors, state[i] = spatial * weights[i] (solver.py:1281-1283): formed on the device
+    weights: np.ndarray | None = None        # [NE]
+    spatial_local: np.ndarray | None = None  # [N_g] this rank's cells
 
     def local_state(self, c0: int, c1: int):
         return self.state[:, c0:c1] if self.state is not None else self.state_local
@@ -327,6 +330,16 @@ class DeviceStages:
     def load_state(self, prob: "ShardedProblem"):
         """Upload this rank's cells (host -> device) into the collision layout."""
         c0, c1 = self.plan.cells()
+        if (prob.state is None and prob.state_local is None and prob.weights is not None
+                and prob.spatial_local is not None):
+            # the outer product never exists on the host: NE + N_g + Nw doubles travel instead of NE x N_g
+            if not self.collisions_on(prob):
+                self.ctx_c.set_state_separable(prob.weights, prob.spatial_local, None)
+                return
+            if prob.phonons is None and prob.phonon_bins is not None:
+                self.ctx_c.set_state_separable(prob.weights, prob.spatial_local, prob.phonon_bins)
+                return
+            prob.state_local = np.ascontiguousarray(prob.weights[:, None] * prob.spatial_local[None, :])
         if prob.phonons is None and prob.phonon_bins is not None and self.collisions_on(prob):
             self.ctx_c.set_state_uniform_phonons(prob.local_state(c0, c1), prob.phonon_bins)
         else:
@@ -507,18 +520,23 @@ def _run_spmd(su: dict, progress_callback=None) -> dict:
         if os.environ.get("QPB_NO_GEN_PROGRAM", "0") == "1":
             custom.program = None
     coll = su["scattering"] or su["recombination"]
-    state_local = (su["state"][:, c0:c1] if su["state"] is not None
-                   else su["weights"][:, None] * su["spatial"][None, c0:c1])
+    separable = su["state"] is None
+    state_local = su["state"][:, c0:c1] if not separable else None
     prob = ShardedProblem(
         mask=mask, bcx=su["bcx"], bcy=su["bcy"], src=su["src"], dx=su["dx"], dE=su["dE"], D=np.asarray(su["D"]),
         variable_D=su["variable_D"], rho=su["rho"], Kr=su["Kr"], Ks=su["Ks"], gap_id=su["gap_id"],
         idx_diff=su["idx_diff"], idx_sum=su["idx_sum"], sign=su["sign"], nw=nw, state=None,
         phonons=su["phonon_state"], diffusion=su["diffusion"], scattering=su["scattering"],
         recombination=su["recombination"], freeze_phonons=su["freeze_phonons"], pauli_floor=su["pauli_floor"],
-        diff_tol=su["diff_tol"], state_local=np.ascontiguousarray(state_local),
-        phonon_bins=su["phonon_bins"] if su["phonon_state"] is None else None)
+        diff_tol=su["diff_tol"], state_local=None if separable else np.ascontiguousarray(state_local),
+        phonon_bins=su["phonon_bins"] if su["phonon_state"] is None else None,
+        weights=np.asarray(su["weights"], dtype=float) if separable else None,
+        spatial_local=np.ascontiguousarray(su["spatial"][c0:c1], dtype=float) if separable else None)
     dt, rem = su["dt"], su["remainder_dt"]
+    import time
+    t_enter = time.perf_counter()
     stages = DeviceStages(plan, prob, device, dt, rem)
+    t_stages = time.perf_counter()
     policy = su["policy"]
     try:
         fused = stages.enable_fused_exchange(prob)
@@ -570,6 +588,7 @@ def _run_spmd(su: dict, progress_callback=None) -> dict:
                         ph_frames.append(reconstruct_field(mask, np.sum(ph * widths[:, None], axis=0)))
                 _callback(progress_callback, float(t), frame)
 
+            t_ready = time.perf_counter()
             rec0 = stepper.merge_pauli([stages.pauli()])[0]
             policy.check(rec0, 0, 0.0)
             store(0.0)
@@ -622,6 +641,8 @@ def _run_spmd(su: dict, progress_callback=None) -> dict:
                     times.append(float(t))
                     store(t)
             info = dict(stages.ctx_c.diag())
+            info.update(seconds={"contexts_tables_state": t_stages - t_enter, "exchange_setup": t_ready - t_stages,
+                                 "loop_and_stores": time.perf_counter() - t_ready})
             info.update(generation_uploads=gen_uploads,
                         generation_on_device=bool(custom is not None and custom.program is not None))
             info.update(world=world, fused_exchange=bool(fused), exchanges=stepper.exchanges,
