@@ -610,11 +610,8 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
 template <int RP, int QP, int NXT>
 int launch_resident(qpb_ctx *c, const DiffSlot &s, const ResArgs &A, bool query, int *nclusters) {
     auto kern = k_pr_resident<RP, QP, NXT>;
-    static bool configured = false;
-    if (!configured) {
-        QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.res.smem));
-        configured = true;
-    }
+    // per device and per launch: the attribute is device state, and grids of different row lengths share an instance
+    QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(std::max(1, s.res.nclusters) * s.res.CS));
     cfg.blockDim = dim3(RNT);
@@ -630,7 +627,6 @@ int launch_resident(qpb_ctx *c, const DiffSlot &s, const ResArgs &A, bool query,
     if (query) {
         int n = 0;
         cfg.gridDim = dim3((unsigned)(64 * s.res.CS));
-        QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s.res.smem));
         if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) {
             cudaGetLastError();
             n = 0;
