@@ -662,6 +662,7 @@ __global__ void __launch_bounds__(256) k_sweep_x_vard(SweepArgs A) {
     const double tol = A.tol[bin];
 
     double rmax = 0.0, umax = 0.0;
+#pragma unroll 4
     for (int e = tid; e < LINES * ROWLEN; e += THREADS) {
         const int g = e / ROWLEN, x = e - g * ROWLEN;
         const int y = y0 + g;
@@ -669,15 +670,20 @@ __global__ void __launch_bounds__(256) k_sweep_x_vard(SweepArgs A) {
         if (y < A.ny && x < nx) {
             const int c = y * nx + x;
             const unsigned fl = A.flags[c];
+            // The face arrays hold 0 where there is no link, so the stencil needs no link tests: every load below is
+            // independent of the flags (one memory round trip per cell instead of flags -> branch -> neighbour).
+            const int cu = y > 0 ? c - nx : c, cd = y + 1 < A.ny ? c + nx : c, cl = x > 0 ? c - 1 : c, cr = x + 1 < nx ? c + 1 : c;
+            const double bc_ = b[c], uc = u[c], uU = u[cu], uD = u[cd], uL = u[cl], uR = u[cr];
+            const double eU = ey[c], eD = cd != c ? ey[cd] : 0.0, eL = ex[c], eR = cr != c ? ex[cr] : 0.0;
             if (fl & QPB_IN) {
-                const double bc_ = b[c], uc = u[c], au = fabs(uc);
+                const double au = fabs(uc);
                 // boundary diagonals are zero away from absorbing / Dirichlet / Robin walls: flagged, not streamed
                 const double gx = (fl & QPB_BCXNZ) ? gbx[c] : 0.0, gy = (fl & QPB_BCYNZ) ? gby[c] : 0.0;
                 double cross = gy * uc, along = gx * uc, wsum = (fabs(gy) + fabs(gx)) * au;
-                if (fl & QPB_LK_U) { const double ef = ey[c], un = u[c - nx]; cross = fma(ef, uc - un, cross); wsum = fma(ef, au + fabs(un), wsum); }
-                if (fl & QPB_LK_D) { const double ef = ey[c + nx], un = u[c + nx]; cross = fma(ef, uc - un, cross); wsum = fma(ef, au + fabs(un), wsum); }
-                if (fl & QPB_LK_L) { const double ef = ex[c], un = u[c - 1]; along = fma(ef, uc - un, along); wsum = fma(ef, au + fabs(un), wsum); }
-                if (fl & QPB_LK_R) { const double ef = ex[c + 1], un = u[c + 1]; along = fma(ef, uc - un, along); wsum = fma(ef, au + fabs(un), wsum); }
+                cross = fma(eU, uc - uU, cross); wsum = fma(eU, au + fabs(uU), wsum);
+                cross = fma(eD, uc - uD, cross); wsum = fma(eD, au + fabs(uD), wsum);
+                along = fma(eL, uc - uL, along); wsum = fma(eL, au + fabs(uL), wsum);
+                along = fma(eR, uc - uR, along); wsum = fma(eR, au + fabs(uR), wsum);
                 d = fma(rho - 0.5, uc, bc_) - cross;
                 rmax = fmax(rmax, fabs(bc_ - uc - cross - along) - tol * (fabs(bc_) + au + wsum));
                 umax = fmax(umax, au);
@@ -724,11 +730,10 @@ __global__ void __launch_bounds__(256) k_sweep_x_vard(SweepArgs A) {
         }
         // couplings of the chunk's cells to their left neighbours (and of the next chunk's first cell to my last)
         const double *er = ex + (size_t)y * nx;
-        const uint8_t *fr = A.flags + (size_t)y * nx;
 #pragma unroll
         for (int t = 0; t <= S; ++t) {
             const int x = q * S + t;
-            ch.ev[t] = (act && x < nx && (fr[x] & QPB_LK_L)) ? er[x] : 0.0;
+            ch.ev[t] = (act && x < nx) ? er[x] : 0.0;   // 0 where the cell has no left neighbour in the mask
         }
     }
     double Am, Bm;
@@ -793,13 +798,13 @@ __global__ void __launch_bounds__(512) k_sweep_y_vard(SweepArgs A, int QW) {
                 const double uc = u[c];
                 uold[t] = uc;
                 d = p[c] - uc;
-                if (A.flags[c] & QPB_LK_U) ch.ev[t] = ey[c];
+                ch.ev[t] = ey[c];   // 0 where the cell has no upper neighbour in the mask
             }
             ch.v[t] = d;
             ch.m[t] = mt[(size_t)t * nx];
         }
         const int rn = r0 + S;
-        ch.ev[S] = (live && rn < ny && (A.flags[rn * nx + x] & QPB_LK_U)) ? ey[rn * nx + x] : 0.0;
+        ch.ev[S] = (live && rn < ny) ? ey[rn * nx + x] : 0.0;
     }
     double *cA = sm, *cB = sm + QW * 32;
     double Am, Bm;
