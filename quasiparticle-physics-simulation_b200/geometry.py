@@ -172,19 +172,21 @@ def compile_boundaries(mask: np.ndarray, edges, edge_conditions, dx: float):
             f"All edges must be assigned boundary conditions before simulation. Missing: {len(missing)}"
         )
     need = boundary_face_masks(m)
-    bad = np.zeros((ny, nx), dtype=bool)
-    for d in _FACE_DIRS:
-        bad |= need[d] & ~covered[d]
-    if bad.any():
-        r, c = (int(v) for v in np.argwhere(bad)[0])
+    # the boundary faces are a thin set: work on their flat indices, not on grid-sized boolean selections
+    faces = {d: np.flatnonzero(need[d].ravel()) for d in _FACE_DIRS}
+    uncovered = {d: faces[d][~covered[d].ravel()[faces[d]]] for d in _FACE_DIRS}
+    if any(u.size for u in uncovered.values()):
+        first = min(int(u[0]) for u in uncovered.values() if u.size)   # first offending cell in row-major order
+        r, c = divmod(first, nx)
         for d in _FACE_DIRS:
             if need[d][r, c] and not covered[d][r, c]:
                 raise BoundaryAssignmentError(
                     f"Missing boundary condition for face at cell ({r}, {c}) direction '{d}'."
                 )
+    flat_src = src.ravel()
     for d in _FACE_DIRS:
-        use = need[d]
-        tgt = bcx if d in ("left", "right") else bcy
-        tgt[use] += face_diag[d][use]
-        src[use] += face_src[d][use]
+        idx = faces[d]
+        tgt = (bcx if d in ("left", "right") else bcy).ravel()
+        tgt[idx] += face_diag[d].ravel()[idx]
+        flat_src[idx] += face_src[d].ravel()[idx]
     return bcx, bcy, src

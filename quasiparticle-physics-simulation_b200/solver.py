@@ -91,17 +91,24 @@ class _Generation:
 class _PauliPolicy:
     """solver.py:1296-1344: forbidden-state and occupation checks after every step."""
 
-    def __init__(self, E_bins, coords, warn_thr, err_thr, enforce):
-        self.E, self.coords = E_bins, coords
+    def __init__(self, E_bins, mask, warn_thr, err_thr, enforce):
+        # the (row, col) of a cell is only needed inside a message: found on demand, not tabulated for every cell
+        self.E, self.mask = E_bins, np.asarray(mask, dtype=bool)
+        self._flat = None
         self.warn_thr, self.err_thr, self.enforce = warn_thr, err_thr, enforce
         self.warned = False
-        self.n = coords.shape[0]
+        self.n = int(self.mask.sum())
+
+    def _pixel(self, px: int):
+        if self._flat is None:
+            self._flat = np.flatnonzero(self.mask.ravel())
+        return divmod(int(self._flat[px]), self.mask.shape[1])
 
     def check(self, rec, step_idx: int, time_ns: float) -> None:
         max_occ, max_index, forbidden = rec
         if forbidden >= 0:
             ie, px = divmod(int(forbidden), self.n)
-            row, col = self.coords[px]
+            row, col = self._pixel(px)
             msg = (
                 f"Detected non-zero quasiparticle density in forbidden state "
                 f"(rho≈0): step={step_idx}, t={time_ns:.6g} ns, "
@@ -113,8 +120,8 @@ class _PauliPolicy:
                 warnings.warn(msg, stacklevel=3)
                 self.warned = True
         ie, px = divmod(int(max_index), self.n)
-        row, col = self.coords[px]
         if self.err_thr is not None and max_occ > self.err_thr:
+            row, col = self._pixel(px)
             msg = (
                 f"Pauli occupation exceeded limit: f={max_occ:.6g} > {self.err_thr:.6g} "
                 f"at step={step_idx}, t={time_ns:.6g} ns, "
@@ -126,6 +133,7 @@ class _PauliPolicy:
                 warnings.warn(msg, stacklevel=3)
                 self.warned = True
         if self.warn_thr is not None and max_occ > self.warn_thr and not self.warned:
+            row, col = self._pixel(px)
             warnings.warn(
                 "High occupation detected (Pauli blocking regime): "
                 f"max f={max_occ:.6g} at step={step_idx}, t={time_ns:.6g} ns, "
@@ -366,8 +374,7 @@ def run_2d_crank_nicolson(
         # (NE, N) host array is only materialised when an explicit phonon state has to travel with it
         state = None
 
-    coords = np.argwhere(mask_b)
-    policy = _PauliPolicy(E_bins, coords, pauli_warn_threshold, pauli_error_threshold, enforce_pauli)
+    policy = _PauliPolicy(E_bins, mask_b, pauli_warn_threshold, pauli_error_threshold, enforce_pauli)
 
     flags = capi.F_PAULI
     if enable_diffusion:
