@@ -246,6 +246,23 @@ def test_bin_resident_cluster_solve_matches_the_launched_sweeps_and_the_oracle(s
     np.testing.assert_allclose(got["mass"], want["mass"], rtol=helpers.RTOL)
 
 
+def test_bin_resident_cluster_solve_is_reproducible_run_to_run():
+    """The CTAs of a cluster hand carries, halo rows and verdicts to each other through shared memory (st.async +
+    mbarrier) with single-buffered slots: a missing ordering would show as a result that changes from run to run.  Eight
+    runs of the same solve (many bins per cluster in flight, different arrival orders) must agree bit for bit."""
+    case = cases.meander_c2(ny=256, nx=256, ne=40, steps=2)
+    case["enable_recombination"] = case["enable_scattering"] = False
+    case["generation"] = None
+    first = None
+    for _ in range(8):
+        got = helpers.run_dropin(case, enforce_pauli=False)["state"]
+        assert Q.solver.last_run_info["sweep_path"] == 5
+        if first is None:
+            first = got
+        else:
+            assert np.array_equal(first, got)
+
+
 @pytest.mark.parametrize("resident", ["1", "0"], ids=["launched_sweeps", "bin_resident"])
 def test_a_sweep_iteration_that_hits_its_cap_falls_back_to_the_krylov_solve(resident, monkeypatch):
     """The reference's SuperLU solve always returns; the sweep iteration has a cap (512 iterations, QPB_MAXIT here to
