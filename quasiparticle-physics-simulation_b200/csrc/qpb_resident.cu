@@ -122,39 +122,46 @@ __device__ __forceinline__ unsigned code_byte(const uint4 &f, int t) {
 // ---- first-order recurrences of the scaled Thomas algorithm on one chunk ------------------------------------------
 // forward   y_t = v_t + g_{t-1} y_{t-1}      (g_{-1} = gprev, the last multiplier of the previous chunk)
 // backward  x_t = z_t + g_t x_{t+1},  z_t = m_t y_t
+// With one D per bin the multiplier is g_t = a m_t wherever cell t has a neighbour t+1 in the mask, and where it has
+// none the product a m_t only reaches a cell outside the mask (m = 0 there: its value is dropped and the chain starts
+// anew).  So the kernel reads ONE table, m, per solve and forms g on the fly: half the table bytes through L1, and the
+// pivots are in registers before the stencil is through (no load in the middle of the solve).
 // The probes run a chunk with a zero carry; how a carry passes through the chunk (the product of its multipliers) is
 // tabulated per (bin, shift, line class, chunk) at plan time (k_chunk_products).
 template <int N>
-__device__ __forceinline__ double fwd_probe(const double (&v)[N], const double (&g)[N]) {
+__device__ __forceinline__ double fwd_probe(const double (&v)[N], const double (&m)[N], double a) {
     double y = v[0];
 #pragma unroll
-    for (int t = 1; t < N; ++t) y = fma(g[t - 1], y, v[t]);
+    for (int t = 1; t < N; ++t) y = fma(a * m[t - 1], y, v[t]);
     return y;
 }
 template <int N>
-__device__ __forceinline__ void fwd_apply(double (&v)[N], const double (&g)[N], double gprev, double cin) {
+__device__ __forceinline__ void fwd_apply(double (&v)[N], const double (&m)[N], double a, double gprev, double cin) {
     double y = fma(gprev, cin, v[0]);
     v[0] = y;
 #pragma unroll
     for (int t = 1; t < N; ++t) {
-        y = fma(g[t - 1], y, v[t]);
+        y = fma(a * m[t - 1], y, v[t]);
         v[t] = y;
     }
 }
+// z = m y, then the backward recurrence with a zero carry
 template <int N>
-__device__ __forceinline__ double bwd_probe(const double (&z)[N], const double (&g)[N]) {
+__device__ __forceinline__ double bwd_probe(double (&z)[N], const double (&m)[N], double a) {
+#pragma unroll
+    for (int t = 0; t < N; ++t) z[t] *= m[t];
     double x = z[N - 1];
 #pragma unroll
-    for (int t = N - 2; t >= 0; --t) x = fma(g[t], x, z[t]);
+    for (int t = N - 2; t >= 0; --t) x = fma(a * m[t], x, z[t]);
     return x;
 }
 template <int N>
-__device__ __forceinline__ void bwd_apply(double (&z)[N], const double (&g)[N], double xin) {
-    double x = fma(g[N - 1], xin, z[N - 1]);
+__device__ __forceinline__ void bwd_apply(double (&z)[N], const double (&m)[N], double a, double xin) {
+    double x = fma(a * m[N - 1], xin, z[N - 1]);
     z[N - 1] = x;
 #pragma unroll
     for (int t = N - 2; t >= 0; --t) {
-        x = fma(g[t], x, z[t]);
+        x = fma(a * m[t], x, z[t]);
         z[t] = x;
     }
 }
@@ -393,12 +400,14 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
             // -- rows: d* = (H + r)^-1 (b - A u)
             int sgn = -1;
             if (xrow) {   // whole warps: lanes beyond the last chunk of a row run the scans on the neutral map
-                double v[16], gt[16];
+                double v[16], mt[16];
                 double gp = 0.0;   // last multiplier of the chunk to the left
                 const size_t tb = (((size_t)bin * A.jmax + j) * A.nclx + clsr) * A.npadx;
+                double2 pa = make_double2(0.0, 0.0);
                 if (rowl) {
-                    load_xtab(A.gx + tb, Q, q, gt);
-                    if (q > 0) gp = A.gx[tb + (7 * Q + q - 1) * 2 + 1];
+                    load_xtab(A.mx + tb, Q, q, mt);
+                    if (q > 0) gp = a * A.mx[tb + (7 * Q + q - 1) * 2 + 1];
+                    pa = A.pax[(((size_t)bin * A.jmax + j) * A.nclx + clsr) * Q + q];
                     const double w0 = U[iw], e15 = U[ie];
                     if (checking)
                         row_stencil<2>(U, Bs, lut, ku, kd, rwb, w0, e15, cd, a, sc, tol, A.src, c0, v, sgn);
@@ -406,20 +415,12 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
                         row_stencil<1>(U, Bs, lut, ku, kd, rwb, w0, e15, cd, a, sc, tol, A.src, c0, v, sgn);
                 } else {
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) gt[t] = v[t] = 0.0;
+                    for (int t = 0; t < 16; ++t) mt[t] = v[t] = 0.0;
                 }
-                double2 pa = make_double2(0.0, 0.0);
-                if (rowl) pa = A.pax[(((size_t)bin * A.jmax + j) * A.nclx + clsr) * Q + q];
-                const double yin = lane_carry<QP, false>(pa.x, fwd_probe(v, gt), q, A.xdepth);
-                fwd_apply(v, gt, gp, yin);
-                if (rowl) {
-                    double mt[16];
-                    load_xtab(A.mx + tb, Q, q, mt);
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) v[t] *= mt[t];
-                }
-                const double xin = lane_carry<QP, true>(pa.y, bwd_probe(v, gt), q, A.xdepth);
-                bwd_apply(v, gt, xin);
+                const double yin = lane_carry<QP, false>(pa.x, fwd_probe(v, mt, a), q, A.xdepth);
+                fwd_apply(v, mt, a, gp, yin);
+                const double xin = lane_carry<QP, true>(pa.y, bwd_probe(v, mt, a), q, A.xdepth);
+                bwd_apply(v, mt, a, xin);
                 if (xact) {
 #pragma unroll
                     for (int un = 0; un < 8; ++un) sts2(D, kd, un, make_double2(v[2 * un], v[2 * un + 1]));
@@ -433,7 +434,6 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
                 const size_t tby = (((size_t)bin * A.jmax + j) * A.ncly + clsc) * A.npady + yr0;
                 if (yr0 < A.npady) {
                     prefetch_l1(A.pay + (tby >> 4));
-                    prefetch_l1(A.gy + tby);
                     prefetch_l1(A.my + tby);
                 }
             }
@@ -447,32 +447,30 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
                          peer_addr(mb0 + 8 * (3 + (it & 1)), tid));
             }
             // -- columns: d = (V + r)^-1 d*, forward elimination
-            double v[16], gt[16], gp = 0.0;
+            double v[16], mt[16], gp = 0.0;
             const bool ytab = yact && yr0 < A.npady;   // the chunk lies inside the tables (they end on a multiple of 16)
-            const double *mty = nullptr;
             double Af = 0.0, Bf = 0.0;
             double2 pa = make_double2(0.0, 0.0);
             if (yact) {
                 const size_t tb = (((size_t)bin * A.jmax + j) * A.ncly + clsc) * A.npady;
-                mty = A.my + tb + yr0;
                 if (ytab) {
-                    const double2 *g2 = reinterpret_cast<const double2 *>(A.gy + tb + yr0);
+                    const double2 *m2 = reinterpret_cast<const double2 *>(A.my + tb + yr0);
 #pragma unroll
                     for (int un = 0; un < 8; ++un) {
-                        const double2 t2 = g2[un];
-                        gt[2 * un] = t2.x;
-                        gt[2 * un + 1] = t2.y;
+                        const double2 t2 = m2[un];
+                        mt[2 * un] = t2.x;
+                        mt[2 * un + 1] = t2.y;
                     }
-                    if (yr0 > 0) gp = A.gy[tb + yr0 - 1];
+                    if (yr0 > 0) gp = a * A.my[tb + yr0 - 1];
                     pa = A.pay[(tb + yr0) >> 4];
                 } else {
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) gt[t] = 0.0;
+                    for (int t = 0; t < 16; ++t) mt[t] = 0.0;
                 }
 #pragma unroll
                 for (int t = 0; t < 16; ++t) v[t] = D[(16 * h + t) * RW + ycol];
                 Af = pa.x;
-                Bf = fwd_probe(v, gt);
+                Bf = fwd_probe(v, mt, a);
                 if (NH == 2 && h == 0) pairs[yx] = make_double2(Af, Bf);
             }
             if (NH == 2) __syncthreads();
@@ -518,21 +516,9 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
                     const double2 up = pairs[yx];
                     cin = fma(up.x, cin, up.y);
                 }
-                fwd_apply(v, gt, gp, cin);
-                if (ytab) {
-                    const double2 *m2 = reinterpret_cast<const double2 *>(mty);
-#pragma unroll
-                    for (int un = 0; un < 8; ++un) {
-                        const double2 t2 = m2[un];
-                        v[2 * un] *= t2.x;
-                        v[2 * un + 1] *= t2.y;
-                    }
-                } else {
-#pragma unroll
-                    for (int t = 0; t < 16; ++t) v[t] = 0.0;
-                }
+                fwd_apply(v, mt, a, gp, cin);
                 Ab = pa.y;
-                Bb = bwd_probe(v, gt);
+                Bb = bwd_probe(v, mt, a);
                 if (NH == 2 && h == 1) pairs[RNX_MAX + yx] = make_double2(Ab, Bb);
             }
             if (NH == 2) __syncthreads();
@@ -562,7 +548,7 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
                     const double2 dn = pairs[RNX_MAX + yx];
                     xin = fma(dn.x, xin, dn.y);
                 }
-                bwd_apply(v, gt, xin);
+                bwd_apply(v, mt, a, xin);
                 const double r2 = 2.0 * r;
                 double *uc = U + (16 * h + 1) * RW + ycol;
                 double first = 0.0, last = 0.0;
@@ -582,7 +568,6 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
             if (rowl && it + 1 < A.maxit) {
                 const size_t tbn = (((size_t)bin * A.jmax + (it + 1) % jl) * A.nclx + clsr) * A.npadx;
                 const size_t o = ((size_t)(q & 7) * Q + q) * 2;
-                prefetch_l1(A.gx + tbn + o);
                 prefetch_l1(A.mx + tbn + o);
                 prefetch_l1(A.pax + (tbn >> 4) + q);
             }
