@@ -56,8 +56,8 @@ struct ResArgs {
     const int *clsx, *clsy;
     const double *mx, *gx;   // [ne][jmax][nclx][npadx], chunk-interleaved 16-byte units
     const double *my, *gy;   // [ne][jmax][ncly][npady]
-    const double2 *pax;      // [ne][jmax][nclx][Q]   products of the multipliers a forward / backward carry meets in a chunk
-    const double2 *pay;      // [ne][jmax][ncly][npady / 16]
+    const double4 *pax;      // [ne][jmax][nclx][Q]   (forward product, backward product, multiplier into the chunk, -)
+    const double4 *pay;      // [ne][jmax][ncly][npady / 16]
     int nclx, ncly, npadx, npady;
     int *done, *iters_out, *queue;
 };
@@ -245,21 +245,23 @@ __device__ __forceinline__ void row_stencil(const double *__restrict__ U, double
 }
 
 // Products of the multipliers a carry meets on its way through a chunk: forward  g_{16q-1} g_{16q} ... g_{16q+14}
-// (into the chunk and up to its last cell), backward  g_{16q} ... g_{16q+15}.  One thread per (table row, chunk).
-__global__ void k_chunk_products(long long nrows, int Qc, int interleaved, const double *__restrict__ g, double2 *__restrict__ out) {
+// (into the chunk and up to its last cell), backward  g_{16q} ... g_{16q+15}; with them g_{16q-1} itself, so that a solve
+// reads nothing outside its own chunk of the tables.  One thread per (table row, chunk).
+__global__ void k_chunk_products(long long nrows, int Qc, int interleaved, const double *__restrict__ g, double4 *__restrict__ out) {
     const long long id = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (id >= nrows * Qc) return;
     const long long row = id / Qc;
     const int q = (int)(id - row * Qc);
     const double *gr = g + row * (long long)Qc * 16;
     auto at = [&](int k) { return interleaved ? gr[(((k % 16) / 2) * Qc + k / 16) * 2 + (k & 1)] : gr[k]; };
-    double f = q > 0 ? at(16 * q - 1) : 0.0, b = 1.0;
+    const double gin = q > 0 ? at(16 * q - 1) : 0.0;   // multiplier between the previous chunk's last cell and this chunk
+    double f = gin, b = 1.0;
     for (int t = 0; t < 16; ++t) {
         const double gv = at(16 * q + t);
         if (t < 15) f *= gv;
         b *= gv;
     }
-    out[id] = make_double2(f, b);
+    out[id] = make_double4(f, b, gin, 0.0);
 }
 
 // RP rows per CTA (16 or 32), QP lanes per row in the row solve (power of two >= chunks per row)
@@ -276,7 +278,8 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
     double2 *slots = reinterpret_cast<double2 *>(Bs + (size_t)RP * RW);   // [2 RREACH][RNX_MAX] carry maps of other CTAs
     double2 *pairs = slots + 2 * RREACH * RNX_MAX;    // [2][RNX_MAX]  maps of the CTA's own other half (down / up)
     double *lut = reinterpret_cast<double *>(pairs + 2 * RNX_MAX);        // [256] 1 + a dg per geometry code
-    int *ism = reinterpret_cast<int *>(lut + 256);
+    double *shf = lut + 256;                          // [64] shifts of the bin
+    int *ism = reinterpret_cast<int *>(shf + 64);
     int *conv = ism;           // [2][RCS_MAX] "some cell of CTA r is over its bound", by iteration parity
     int *binslot = ism + 16;   // bin handed out by CTA 0
     int *red = ism + 20;       // [16] per-warp verdicts
@@ -346,6 +349,7 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
 
         // ---- the bin comes on chip ------------------------------------------------------------------------------
         if (tid < 256) lut[tid] = fma(a, A.dgl[tid], 1.0);
+        if (tid < jl && tid < 64) shf[tid] = A.shift[(size_t)bin * A.jmax + tid];   // visible after the barrier below
         if (xact) {
             double2 w[8];
             if (rowl) {
@@ -389,9 +393,10 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
         // ---- iterate ------------------------------------------------------------------------------------------------
         int it = 0;
         bool converged = false;
+        int j = -1;
         for (; it < A.maxit; ++it) {
-            const int j = it % jl;
-            const double r = A.shift[(size_t)bin * A.jmax + j];
+            j = j + 1 == jl ? 0 : j + 1;   // it % jl
+            const double r = shf[j];
             const bool checking = it >= check_from;
             if (tid == 0) {
                 if (nA) mbar_expect(mb0, (uint32_t)(nA * nx * 16));
@@ -403,11 +408,11 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
                 double v[16], mt[16];
                 double gp = 0.0;   // last multiplier of the chunk to the left
                 const size_t tb = (((size_t)bin * A.jmax + j) * A.nclx + clsr) * A.npadx;
-                double2 pa = make_double2(0.0, 0.0);
+                double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
                 if (rowl) {
                     load_xtab(A.mx + tb, Q, q, mt);
-                    if (q > 0) gp = a * A.mx[tb + (7 * Q + q - 1) * 2 + 1];
                     pa = A.pax[(((size_t)bin * A.jmax + j) * A.nclx + clsr) * Q + q];
+                    gp = pa.z;
                     const double w0 = U[iw], e15 = U[ie];
                     if (checking)
                         row_stencil<2>(U, Bs, lut, ku, kd, rwb, w0, e15, cd, a, sc, tol, A.src, c0, v, sgn);
@@ -450,7 +455,7 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
             double v[16], mt[16], gp = 0.0;
             const bool ytab = yact && yr0 < A.npady;   // the chunk lies inside the tables (they end on a multiple of 16)
             double Af = 0.0, Bf = 0.0;
-            double2 pa = make_double2(0.0, 0.0);
+            double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
             if (yact) {
                 const size_t tb = (((size_t)bin * A.jmax + j) * A.ncly + clsc) * A.npady;
                 if (ytab) {
@@ -461,8 +466,8 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
                         mt[2 * un] = t2.x;
                         mt[2 * un + 1] = t2.y;
                     }
-                    if (yr0 > 0) gp = a * A.my[tb + yr0 - 1];
                     pa = A.pay[(tb + yr0) >> 4];
+                    gp = pa.z;
                 } else {
 #pragma unroll
                     for (int t = 0; t < 16; ++t) mt[t] = 0.0;
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
             }
             // the factor tables of the next row solve: into L1 while the halo rows travel
             if (rowl && it + 1 < A.maxit) {
-                const size_t tbn = (((size_t)bin * A.jmax + (it + 1) % jl) * A.nclx + clsr) * A.npadx;
+                const size_t tbn = (((size_t)bin * A.jmax + (j + 1 == jl ? 0 : j + 1)) * A.nclx + clsr) * A.npadx;
                 const size_t o = ((size_t)(q & 7) * Q + q) * 2;
                 prefetch_l1(A.mx + tbn + o);
                 prefetch_l1(A.pax + (tbn >> 4) + q);
@@ -644,7 +649,7 @@ int qpbr_plan(qpb_ctx *c, DiffSlot &s) {
         if (e[0] == '1') return QPB_OK;
     const auto &cf = c->cfg;
     if (cf.flags & QPB_F_VARIABLE_D) return QPB_OK;
-    if (s.mode != 0 || !s.fast || s.spectral || s.krylov) return QPB_OK;
+    if (s.mode != 0 || !s.fast || s.spectral || s.krylov || s.jmax > 64) return QPB_OK;
     if (!s.fx.d_tab || !s.fx.d_tabg || !s.fy.d_tab || !s.fy.d_tabg || s.fx.S != 16 || s.fy.S != 16) return QPB_OK;
     if (cf.nx % 16 != 0 || cf.nx < 96 || cf.nx > RNX_MAX || cf.ny < 32 || cf.ny > 32 * RCS_MAX) return QPB_OK;
     DiffSlot::Resident r;
@@ -661,7 +666,7 @@ int qpbr_plan(qpb_ctx *c, DiffSlot &s) {
     }
     if (r.RP > 32) return QPB_OK;   // carries that cross more than 2 CTAs of 32 rows: the launched sweeps take the solve
     r.smem = sizeof(double) * (size_t)(3 * r.RP + 2) * r.pitch + sizeof(double2) * (2 * RREACH + 2) * RNX_MAX +
-             sizeof(double) * 256 + 512;
+             sizeof(double) * (256 + 64) + 512;
     // geometry codes: one byte per cell into the table of distinct diagonals (linked neighbours + boundary terms)
     std::vector<uint8_t> code(c->ncd, 0);
     std::vector<double> dgl(256, 0.0);
@@ -696,10 +701,10 @@ int qpbr_plan(qpb_ctx *c, DiffSlot &s) {
     {
         const long long rx = (long long)cf.ne * s.jmax * s.fx.nclass, ry = (long long)cf.ne * s.jmax * s.fy.nclass;
         const int Qx = s.fx.npad / 16, Qy = s.fy.npad / 16;
-        QPB_CUDA(qpb_dev_malloc((void **)&s.d_respax, sizeof(double2) * (size_t)(rx * Qx)));
-        QPB_CUDA(qpb_dev_malloc((void **)&s.d_respay, sizeof(double2) * (size_t)(ry * Qy)));
-        k_chunk_products<<<(unsigned)ceil_div64(rx * Qx, 128), 128, 0, c->stream>>>(rx, Qx, 1, s.fx.d_tabg, (double2 *)s.d_respax);
-        k_chunk_products<<<(unsigned)ceil_div64(ry * Qy, 128), 128, 0, c->stream>>>(ry, Qy, 0, s.fy.d_tabg, (double2 *)s.d_respay);
+        QPB_CUDA(qpb_dev_malloc((void **)&s.d_respax, sizeof(double4) * (size_t)(rx * Qx)));
+        QPB_CUDA(qpb_dev_malloc((void **)&s.d_respay, sizeof(double4) * (size_t)(ry * Qy)));
+        k_chunk_products<<<(unsigned)ceil_div64(rx * Qx, 128), 128, 0, c->stream>>>(rx, Qx, 1, s.fx.d_tabg, (double4 *)s.d_respax);
+        k_chunk_products<<<(unsigned)ceil_div64(ry * Qy, 128), 128, 0, c->stream>>>(ry, Qy, 0, s.fy.d_tabg, (double4 *)s.d_respay);
         QPB_CHECK_LAUNCH();
         c->diag.kernel_launches += 2;
     }
@@ -720,7 +725,7 @@ int qpbr_solve(qpb_ctx *c, DiffSlot &s, std::vector<int> &h_done) {
     A.ne = ne; A.ny = cf.ny; A.nx = cf.nx; A.ncd = c->ncd; A.jmax = s.jmax;
     A.Q = cf.nx / 16; A.CS = s.res.CS; A.reach = s.res.reach; A.maxit = c->maxit;
     A.xdepth = std::max(1, s.fx.carry_depth);
-    A.pax = (const double2 *)s.d_respax; A.pay = (const double2 *)s.d_respay;
+    A.pax = (const double4 *)s.d_respax; A.pay = (const double4 *)s.d_respay;
     A.check_all = !(s.known_iters > 0 && (s.solves % 16) != 0);
     A.S = c->d_S; A.B = c->d_B; A.code = s.d_rescode; A.dgl = s.d_reslut; A.src = c->d_srcgeom;
     A.a_bin = s.d_a; A.shift = s.d_shift; A.srccoef = s.d_src; A.tol = s.d_tol; A.jlen = s.d_jlen; A.known = s.d_known;
