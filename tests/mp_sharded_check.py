@@ -25,7 +25,10 @@ def main():
     runs = [("c2_meander_40x40x12", next(c for c in cases.golden_cases() if c["name"] == "c2_meander_40x40x12")),
             ("annulus_32x5_mixed", next(c for c in cases.golden_cases() if c["name"] == "annulus_32x5_mixed")),
             ("nonuniform_10x14x8", next(c for c in cases.golden_cases() if c["name"] == "nonuniform_10x14x8")),
-            ("c2_meander_96x80x24", cases.meander_c2(ny=96, nx=80, ne=24, steps=3))]
+            ("c2_meander_96x80x24", cases.meander_c2(ny=96, nx=80, ne=24, steps=3)),
+            # rows of 128 cells: every rank's diffusion context solves its bins bin-resident (k_pr_resident) on the state
+            # the other ranks' collision kernels have stored into
+            ("c2_meander_64x128x10", cases.meander_c2(ny=64, nx=128, ne=10, steps=3))]
     runs += [(c["name"], c) for c in cases.custom_mode_cases() if c["name"] in ("custom_gen_static", "custom_gen_timedep")]
     for name, case in runs:
         single = helpers.run_dropin(case, device=local) if rank == 0 else None
@@ -36,6 +39,8 @@ def main():
             if rank != 0:
                 continue
             assert info["world"] == world and info["exchanges"] > 0 or not case["enable_diffusion"]
+            if name == "c2_meander_64x128x10":
+                assert info["sweep_path"] == 5, info
             if fused and case["enable_recombination"] and "gap_values" not in case:
                 assert info["fused_exchange"], info
             e_single = helpers.rel_err(got["state"], single["state"])
