@@ -266,7 +266,9 @@ __global__ void k_chunk_products(long long nrows, int Qc, int interleaved, const
 
 // RP rows per CTA (16 or 32), QP lanes per row in the row solve (power of two >= chunks per row)
 // NXT: row length when it is known at compile time (every shared-memory address becomes an immediate), 0 otherwise
-template <int RP, int QP, int NXT>
+// FULL: the grid fills the cluster exactly (every thread owns a row chunk and a column chunk that exist, ny = CS * RP):
+// the guards and the neutral values of absent chunks fall away at compile time
+template <int RP, int QP, int NXT, bool FULL>
 __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ ResArgs A) {
     cg::cluster_group cluster = cg::this_cluster();
     extern __shared__ __align__(128) double sm[];
@@ -292,12 +294,12 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
     const int y0 = rank * RP;
     // row solve: row g of the CTA, chunk q
     const int g = tid / QP, q = tid % QP;
-    const bool xrow = g < RP;                   // whole warps
-    const bool xact = xrow && q < Q;
-    const bool rowl = xact && y0 + g < ny;      // the row exists
+    const bool xrow = FULL || g < RP;                       // whole warps
+    const bool xact = FULL || (xrow && q < Q);
+    const bool rowl = FULL || (xact && y0 + g < ny);        // the row exists
     // column solve: column yx, rows [16 h, 16 h + 16) of the CTA
     const int yx = tid & (RNX_MAX - 1), h = tid / RNX_MAX;
-    const bool yact = yx < nx && h < NH;
+    const bool yact = FULL || (yx < nx && h < NH);
     const int ycol = scol(yact ? yx : 0);
     const int yr0 = y0 + 16 * h;                // first row of the column chunk in the grid
 
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
             }
             // -- columns: d = (V + r)^-1 d*, forward elimination
             double v[16], mt[16], gp = 0.0;
-            const bool ytab = yact && yr0 < A.npady;   // the chunk lies inside the tables (they end on a multiple of 16)
+            const bool ytab = FULL || (yact && yr0 < A.npady);   // the chunk lies inside the tables (they end on a multiple of 16)
             double Af = 0.0, Bf = 0.0;
             double4 pa = make_double4(0.0, 0.0, 0.0, 0.0);
             if (yact) {
@@ -597,9 +599,9 @@ __global__ void __launch_bounds__(RNT, 1) k_pr_resident(const __grid_constant__ 
     }
 }
 
-template <int RP, int QP, int NXT>
+template <int RP, int QP, int NXT, bool FULL = false>
 int launch_resident(qpb_ctx *c, const DiffSlot &s, const ResArgs &A, bool query, int *nclusters) {
-    auto kern = k_pr_resident<RP, QP, NXT>;
+    auto kern = k_pr_resident<RP, QP, NXT, FULL>;
     // per device and per launch: the attribute is device state, and grids of different row lengths share an instance
     QPB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     cudaLaunchConfig_t cfg = {};
@@ -631,6 +633,8 @@ int launch_resident(qpb_ctx *c, const DiffSlot &s, const ResArgs &A, bool query,
 int dispatch_resident(qpb_ctx *c, const DiffSlot &s, const ResArgs &A, bool query, int *nclusters) {
     const bool n256 = c->cfg.nx == 256;
     if (s.res.RP == 32) {
+        // 256 x 256 (BASELINE configs[1]): RNT = 32 rows x 16 chunks = 256 columns x 2 halves, nothing is absent
+        if (n256 && c->cfg.ny == 256 && s.fy.npad == 256) return launch_resident<32, 16, 256, true>(c, s, A, query, nclusters);
         if (n256) return launch_resident<32, 16, 256>(c, s, A, query, nclusters);
         if (s.res.QP == 16) return launch_resident<32, 16, 0>(c, s, A, query, nclusters);
         return launch_resident<32, 8, 0>(c, s, A, query, nclusters);
