@@ -79,7 +79,9 @@ typedef struct qpb_diag {
                                 kernels, 2 persistent TMA-pipelined kernels (x and y), 3 the same with lines cut
                                 into overlapping segments (lines longer than 512 cells), 4 direct spectral
                                 solve (cosine transform along x + one tridiagonal solve along y per mode: full
-                                rectangles with reflective left / right walls)                          */
+                                rectangles with reflective left / right walls), 5 bin-resident solve (masks of
+                                up to 256 x 256 cells: a thread-block cluster keeps a bin in shared memory for
+                                the whole iteration, one launch per solve)                              */
     int32_t reserved;
 } qpb_diag;
 
