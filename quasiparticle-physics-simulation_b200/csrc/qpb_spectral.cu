@@ -95,9 +95,21 @@ __global__ void k_dct_forward(int ny, int N, int logN, const double *__restrict_
     const size_t base = (size_t)blockIdx.y * ny * N;
     const double *a = in + base + (size_t)r0 * N, *b = in + base + (size_t)r1 * N;
     for (int k = threadIdx.x; k < N; k += blockDim.x) tw[k] = twg[k];
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
-        const int n = reorder(j, N);
-        z[slot(__brev((unsigned)n) >> (32 - logN))] = make_double2(a[j], two ? b[j] : 0.0);
+    // four row elements per thread in flight before the first shared-memory store (N is a multiple of 4 blockDim.x
+    // for the row lengths the launch uses: 128 threads below 1024, 256 from there on)
+    for (int j0 = threadIdx.x; j0 < N; j0 += 4 * blockDim.x) {
+        double va[4], vb[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * blockDim.x;
+            va[u] = j < N ? a[j] : 0.0;
+            vb[u] = (two && j < N) ? b[j] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int j = j0 + u * blockDim.x;
+            if (j < N) z[slot(__brev((unsigned)reorder(j, N)) >> (32 - logN))] = make_double2(va[u], vb[u]);
+        }
     }
     fft_passes<false>(z, tw, N, logN);
     double *oa = out + base + (size_t)r0 * N, *ob = out + base + (size_t)r1 * N;
@@ -122,6 +134,7 @@ __global__ void k_dct_inverse(int ny, int N, int logN, const double *__restrict_
     const size_t base = (size_t)blockIdx.y * ny * N;
     const double *a = in + base + (size_t)r0 * N, *b = in + base + (size_t)r1 * N;
     for (int k = threadIdx.x; k < N; k += blockDim.x) tw[k] = twg[k];
+#pragma unroll 2
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
         const double ca = a[k], car = k ? a[N - k] : 0.0;
         const double cb = two ? b[k] : 0.0, cbr = (two && k) ? b[N - k] : 0.0;
@@ -214,18 +227,51 @@ __global__ void k_thomas_frozen(int ny, int N, int T, double *__restrict__ v, co
         yp = fma(a, yp, col[(size_t)t * N]) * piv[(size_t)t * N];
         col[(size_t)t * N] = yp;
     }
-#pragma unroll 8
-    for (int t = T; t < ny - 1; ++t) {
-        yp = fma(a, yp, col[(size_t)t * N]) * mf;
-        col[(size_t)t * N] = yp;
+    // The rows below are a first-order recurrence: one dependent FMA + MUL per row, but the loads do not depend on it.
+    // The compiler cannot move a load of row t+1 above the store of row t (the row stride is a run-time value), so the
+    // walk is pipelined by hand: the next PF rows are in registers before the current ones are stored - PF loads in
+    // flight per thread instead of one (the first version spent two memory latencies per row and thread).
+    constexpr int PF = 8;
+    {
+        double cur[PF], nxt[PF];
+        int t = T;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) cur[u] = t + u < ny - 1 ? col[(size_t)(t + u) * N] : 0.0;
+        for (; t < ny - 1; t += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) nxt[u] = t + PF + u < ny - 1 ? col[(size_t)(t + PF + u) * N] : 0.0;
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                if (t + u < ny - 1) {
+                    yp = fma(a, yp, cur[u]) * mf;
+                    col[(size_t)(t + u) * N] = yp;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
+        }
     }
     double xn = fma(a, yp, col[(size_t)(ny - 1) * N]) * m_last;
     col[(size_t)(ny - 1) * N] = xn;
     const double gf = a * mf;
-#pragma unroll 8
-    for (int t = ny - 2; t >= T - 1; --t) {
-        xn = fma(gf, xn, col[(size_t)t * N]);
-        col[(size_t)t * N] = xn;
+    {
+        double cur[PF], nxt[PF];
+        int t = ny - 2;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) cur[u] = t - u >= T - 1 ? col[(size_t)(t - u) * N] : 0.0;
+        for (; t >= T - 1; t -= PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) nxt[u] = t - PF - u >= T - 1 ? col[(size_t)(t - PF - u) * N] : 0.0;
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                if (t - u >= T - 1) {
+                    xn = fma(gf, xn, cur[u]);
+                    col[(size_t)(t - u) * N] = xn;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
+        }
     }
     for (int t = T - 2; t >= 0; --t) {
         xn = fma(a * piv[(size_t)t * N], xn, col[(size_t)t * N]);
