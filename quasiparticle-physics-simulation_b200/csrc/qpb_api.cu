@@ -190,6 +190,8 @@ void qpbk_free_slot(DiffSlot &s) {
     dev_free(s.d_sp_lam);
     dev_free(s.d_sp_bcy);
     dev_free(s.d_sp_piv);
+    dev_free(s.d_sp_srchat);
+    s.sp_fused = false;
     s.sp_T = 0;
     s.spectral = false;
     dev_free(s.d_known);

@@ -245,6 +245,7 @@ int qpbk_diffuse(qpb_ctx *c, DiffSlot &s) {
         c->diag.pr_iterations += kmax;
         return QPB_OK;
     }
+    if (s.mode == 0 && s.spectral && s.sp_fused) return qpbk_diffuse_spectral(c, s);   // forms its right-hand side itself
     if ((rc = qpbk_build_rhs(c, s)) != QPB_OK) return rc;
     if (s.mode != 0) {
         const int dir = s.mode == 1 ? 0 : 1;

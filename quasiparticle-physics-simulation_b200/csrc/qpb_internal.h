@@ -74,7 +74,9 @@ struct DiffSlot {
     double *d_sp_lam = nullptr, *d_sp_bcy = nullptr;   // eigenvalues of Gx [nx], wall diagonal of every row [ny]
     double *d_sp_piv = nullptr;                        // [ne][sp_T][nx] first pivots of the Thomas pass (sp_T = 0: none)
     int sp_T = 0;
-    double sp_wall_last = 0.0;
+    double sp_wall_last = 0.0, sp_wall0 = 0.0;
+    bool sp_fused = false;             // the Thomas pass forms the right-hand side itself (no k_build_rhs pass, no b)
+    double *d_sp_srchat = nullptr;     // [ny][nx] cosine transform of the boundary sources (null: they are all zero)
     bool krylov = false;       // stiff non-commuting solve: preconditioned BiCGStab instead of the sweep iteration (qpb_krylov.cu)
     double *d_kshift = nullptr; // [ne] shift sqrt(lo hi) of the line-solve preconditioner
     // variable-D coefficient fields (dense, per bin): links to the left / up neighbour, boundary diagonals

@@ -279,7 +279,94 @@ __global__ void k_thomas_frozen(int ny, int N, int T, double *__restrict__ v, co
     }
 }
 
+// k_thomas_frozen with the right-hand side formed on the way down: the input is the transform of u itself, not of
+// b = (I + a L) u + dt D s.  In the cosine basis the x part of L is the number lam_k, so
+//     b^_k(t) = (1 - a (lam_k + links_t + wall_t)) u^_k(t) + a (u^_k(t-1) + u^_k(t+1)) + dt D s^_k(t)
+// (links_t = 2 inside, 1 in the first and last row; wall terms only there; s^ = transform of the boundary sources, absent
+// when they are all zero) needs nothing but the neighbouring rows the walk already holds in registers: the k_build_rhs
+// pass over the bin (16 B per cell and bin) and the array b fall away.
+__global__ void k_thomas_fused(int ny, int N, int T, double *__restrict__ v, const double *__restrict__ tab,
+                               const double *__restrict__ a_bin, const double *__restrict__ lam, double wall0,
+                               double wall_last, const double *__restrict__ srchat, const double *__restrict__ srccoef) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int bin = blockIdx.y;
+    if (k >= N) return;
+    const double a = a_bin[bin], lk = lam[k];
+    const double sc = srchat ? srccoef[bin] : 0.0;
+    double *col = v + (size_t)bin * ny * N + k;
+    const double *piv = tab + (size_t)bin * T * N + k;
+    const double *sh = srchat ? srchat + k : nullptr;
+    const double mf = piv[(size_t)(T - 1) * N];
+    const double m_last = 1.0 / fma(-a * a, mf, fma(a, 1.0 + wall_last, fma(a, lk, 1.0)));
+    const double c_in = 1.0 - a * (lk + 2.0), c_first = 1.0 - a * (lk + 1.0 + wall0), c_last = 1.0 - a * (lk + 1.0 + wall_last);
+    constexpr int PF = 8;
+    double yp = 0.0, um = 0.0;   // y of the previous row, u^ of the previous row
+    {
+        double cur[PF + 1], nxt[PF];   // cur[PF]: the row behind the batch (needed as the lower neighbour of its last row)
+        int t = 0;
+#pragma unroll
+        for (int u = 0; u <= PF; ++u) cur[u] = t + u < ny ? col[(size_t)(t + u) * N] : 0.0;
+        for (; t < ny - 1; t += PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) nxt[u] = t + PF + 1 + u < ny ? col[(size_t)(t + PF + 1 + u) * N] : 0.0;
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int r = t + u;
+                if (r < ny - 1) {
+                    double rhs = fma(r == 0 ? c_first : c_in, cur[u], a * (um + cur[u + 1]));
+                    if (sh) rhs = fma(sc, sh[(size_t)r * N], rhs);
+                    const double m = r < T ? piv[(size_t)r * N] : mf;
+                    yp = fma(a, yp, rhs) * m;
+                    col[(size_t)r * N] = yp;
+                    um = cur[u];
+                }
+            }
+            cur[0] = cur[PF];
+#pragma unroll
+            for (int u = 0; u < PF; ++u) cur[u + 1] = nxt[u];
+        }
+        // last row: its u^ is the entry of the window that follows the last processed row
+        // (after the loop t >= ny - 1 and cur[0] holds row t; row ny - 1 is cur[ny - 1 - t + ... ] only when t == ny - 1)
+    }
+    double ul = col[(size_t)(ny - 1) * N];
+    double rhs = fma(c_last, ul, a * um);
+    if (sh) rhs = fma(sc, sh[(size_t)(ny - 1) * N], rhs);
+    double xn = fma(a, yp, rhs) * m_last;
+    col[(size_t)(ny - 1) * N] = xn;
+    const double gf = a * mf;
+    {
+        double cur[PF], nxt[PF];
+        int t = ny - 2;
+#pragma unroll
+        for (int u = 0; u < PF; ++u) cur[u] = t - u >= 0 ? col[(size_t)(t - u) * N] : 0.0;
+        for (; t >= 0; t -= PF) {
+#pragma unroll
+            for (int u = 0; u < PF; ++u) nxt[u] = t - PF - u >= 0 ? col[(size_t)(t - PF - u) * N] : 0.0;
+#pragma unroll
+            for (int u = 0; u < PF; ++u) {
+                const int r = t - u;
+                if (r >= 0) {
+                    xn = fma(r < T - 1 ? a * piv[(size_t)r * N] : gf, xn, cur[u]);
+                    col[(size_t)r * N] = xn;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PF; ++u) cur[u] = nxt[u];
+        }
+    }
+}
+
 }  // namespace
+
+static int configure_dct() {
+    static bool configured = false;
+    if (!configured) {
+        QPB_CUDA(cudaFuncSetAttribute(k_dct_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        QPB_CUDA(cudaFuncSetAttribute(k_dct_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+        configured = true;
+    }
+    return QPB_OK;
+}
 
 // Decide whether the prepared solve can take the spectral path and build its tables.
 int qpbk_prepare_spectral(qpb_ctx *c, DiffSlot &s) {
@@ -343,6 +430,24 @@ int qpbk_prepare_spectral(qpb_ctx *c, DiffSlot &s) {
             QPB_CUDA(cudaStreamSynchronize(c->stream));
             s.sp_T = T;
             s.sp_wall_last = bcy_row[ny - 1];
+            s.sp_wall0 = bcy_row[0];
+            // with tabulated pivots the Thomas pass also forms the right-hand side (k_thomas_fused); it needs the
+            // transform of the boundary sources when there are any
+            if (!(getenv("QPB_NO_SPECTRAL_FUSED") && getenv("QPB_NO_SPECTRAL_FUSED")[0] == '1')) {
+                bool any_src = false;
+                for (size_t p = 0; p < c->h_src.size() && !any_src; ++p) any_src = c->h_src[p] != 0.0;
+                if (any_src) {
+                    int rc = configure_dct();
+                    if (rc != QPB_OK) return rc;
+                    QPB_CUDA(qpb_dev_malloc((void **)&s.d_sp_srchat, sizeof(double) * (size_t)ny * nx));
+                    k_dct_forward<<<dim3((unsigned)((ny + 1) / 2), 1), nx >= 1024 ? 256 : 128,
+                                    sizeof(double2) * ((size_t)nx + nx), c->stream>>>(
+                        ny, nx, logN, c->d_srcgeom, s.d_sp_srchat, (const double2 *)s.d_sp_tw, (const double2 *)s.d_sp_tw2);
+                    QPB_CHECK_LAUNCH();
+                    QPB_CUDA(cudaStreamSynchronize(c->stream));
+                }
+                s.sp_fused = true;
+            }
         }
     }
     s.spectral = true;
@@ -354,24 +459,25 @@ int qpbk_diffuse_spectral(qpb_ctx *c, DiffSlot &s) {
     const auto &cf = c->cfg;
     const int ne = cf.ne, ny = cf.ny, nx = cf.nx;
     const size_t smem = sizeof(double2) * ((size_t)nx + nx);
-    static bool configured = false;
-    if (!configured) {
-        QPB_CUDA(cudaFuncSetAttribute(k_dct_forward, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        QPB_CUDA(cudaFuncSetAttribute(k_dct_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-        configured = true;
+    {
+        int rc = configure_dct();
+        if (rc != QPB_OK) return rc;
     }
     const dim3 rgrid((unsigned)((ny + 1) / 2), (unsigned)ne);
     const int fthreads = nx >= 1024 ? 256 : 128;
     {
         ScopedTimer tm(c, 0);
-        k_dct_forward<<<rgrid, fthreads, smem, c->stream>>>(ny, nx, s.sp_logn, c->d_B, c->d_T1,
+        k_dct_forward<<<rgrid, fthreads, smem, c->stream>>>(ny, nx, s.sp_logn, s.sp_fused ? c->d_S : c->d_B, c->d_T1,
                                                             (const double2 *)s.d_sp_tw, (const double2 *)s.d_sp_tw2);
         c->diag.kernel_launches++;
     }
     {
         ScopedTimer tm(c, 1);
         const dim3 tgrid((unsigned)((nx + 127) / 128), (unsigned)ne);
-        if (s.sp_T > 0)
+        if (s.sp_fused)
+            k_thomas_fused<<<tgrid, 128, 0, c->stream>>>(ny, nx, s.sp_T, c->d_T1, s.d_sp_piv, s.d_a, s.d_sp_lam, s.sp_wall0,
+                                                         s.sp_wall_last, s.d_sp_srchat, s.d_src);
+        else if (s.sp_T > 0)
             k_thomas_frozen<<<tgrid, 128, 0, c->stream>>>(ny, nx, s.sp_T, c->d_T1, s.d_sp_piv, s.d_a, s.d_sp_lam,
                                                           s.sp_wall_last);
         else

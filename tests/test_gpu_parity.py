@@ -484,10 +484,17 @@ def test_spectral_direct_solve_matches_oracle(shape, walls, monkeypatch):
         warnings.simplefilter("ignore")
         _, _, mass, _, ef, _ = Q.run_2d_crank_nicolson(**kw)
         info = dict(Q.solver.last_run_info)
+        # the same solve with the right-hand side built by its own pass (k_build_rhs) instead of inside the Thomas pass
+        monkeypatch.setenv("QPB_NO_SPECTRAL_FUSED", "1")
+        _, _, _, _, ef_unfused, _ = Q.run_2d_crank_nicolson(**kw)
+        assert Q.solver.last_run_info["sweep_path"] == 4
+        monkeypatch.delenv("QPB_NO_SPECTRAL_FUSED")
         monkeypatch.setenv("QPB_NO_SPECTRAL", "1")
         _, _, mass_pr, _, ef_pr, _ = Q.run_2d_crank_nicolson(**kw)
         info_pr = dict(Q.solver.last_run_info)
     assert info["sweep_path"] == 4 and info_pr["sweep_path"] != 4
+    helpers.assert_close(np.array([[f[mask] for f in t] for t in ef]), np.array([[f[mask] for f in t] for t in ef_unfused]),
+                         "fused vs separate right-hand side", rtol=1e-10)   # rounding order only (b formed in real / mode space)
     res = O.run(mask, edges, bcs, field, cases.D0, 0.4, 1.0, 1.0, store_every=1, gap=cases.GAP, fmin=1.0, fmax=3.0,
                 ne=5, gamma=cases.GAMMA)
     want = np.array(res.state_frames)
