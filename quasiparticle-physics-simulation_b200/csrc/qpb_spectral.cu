@@ -89,12 +89,12 @@ __device__ __forceinline__ int reorder(int j, int N) { return (j & 1) ? N - 1 - 
 __global__ void k_dct_forward(int ny, int N, int logN, const double *__restrict__ in, double *__restrict__ out,
                               const double2 *__restrict__ twg, const double2 *__restrict__ tw2) {
     extern __shared__ __align__(16) double2 smz[];
-    double2 *z = smz, *tw = smz + N;
+    double2 *z = smz;
+    const double2 *tw = twg;   // twiddles straight from L1 / L2 (32 KB shared by every CTA): half the shared memory, twice the CTAs per SM
     const int r0 = 2 * blockIdx.x, r1 = r0 + 1;
     const bool two = r1 < ny;
     const size_t base = (size_t)blockIdx.y * ny * N;
     const double *a = in + base + (size_t)r0 * N, *b = in + base + (size_t)r1 * N;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) tw[k] = twg[k];
     // four row elements per thread in flight before the first shared-memory store (N is a multiple of 4 blockDim.x
     // for the row lengths the launch uses: 128 threads below 1024, 256 from there on)
     for (int j0 = threadIdx.x; j0 < N; j0 += 4 * blockDim.x) {
@@ -128,12 +128,12 @@ __global__ void k_dct_forward(int ny, int N, int logN, const double *__restrict_
 __global__ void k_dct_inverse(int ny, int N, int logN, const double *__restrict__ in, double *__restrict__ out,
                               const double2 *__restrict__ twg, const double2 *__restrict__ tw2) {
     extern __shared__ __align__(16) double2 smz[];
-    double2 *z = smz, *tw = smz + N;
+    double2 *z = smz;
+    const double2 *tw = twg;   // twiddles straight from L1 / L2 (32 KB shared by every CTA): half the shared memory, twice the CTAs per SM
     const int r0 = 2 * blockIdx.x, r1 = r0 + 1;
     const bool two = r1 < ny;
     const size_t base = (size_t)blockIdx.y * ny * N;
     const double *a = in + base + (size_t)r0 * N, *b = in + base + (size_t)r1 * N;
-    for (int k = threadIdx.x; k < N; k += blockDim.x) tw[k] = twg[k];
 #pragma unroll 2
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
         const double ca = a[k], car = k ? a[N - k] : 0.0;
@@ -441,7 +441,7 @@ int qpbk_prepare_spectral(qpb_ctx *c, DiffSlot &s) {
                     if (rc != QPB_OK) return rc;
                     QPB_CUDA(qpb_dev_malloc((void **)&s.d_sp_srchat, sizeof(double) * (size_t)ny * nx));
                     k_dct_forward<<<dim3((unsigned)((ny + 1) / 2), 1), nx >= 1024 ? 256 : 128,
-                                    sizeof(double2) * ((size_t)nx + nx), c->stream>>>(
+                                    sizeof(double2) * (size_t)nx, c->stream>>>(
                         ny, nx, logN, c->d_srcgeom, s.d_sp_srchat, (const double2 *)s.d_sp_tw, (const double2 *)s.d_sp_tw2);
                     QPB_CHECK_LAUNCH();
                     QPB_CUDA(cudaStreamSynchronize(c->stream));
@@ -458,7 +458,7 @@ int qpbk_prepare_spectral(qpb_ctx *c, DiffSlot &s) {
 int qpbk_diffuse_spectral(qpb_ctx *c, DiffSlot &s) {
     const auto &cf = c->cfg;
     const int ne = cf.ne, ny = cf.ny, nx = cf.nx;
-    const size_t smem = sizeof(double2) * ((size_t)nx + nx);
+    const size_t smem = sizeof(double2) * (size_t)nx;
     {
         int rc = configure_dct();
         if (rc != QPB_OK) return rc;
