@@ -72,7 +72,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Copy one TI-row tile (UPR 16-byte units per row) from global to this sub-slot's ring stage.
+// Copy one TI-row tile (UPR 16-byte units per row) from global to this sub-slot's ring stage (k_collide_uniform).
 template <int CC, int UPR>
 __device__ __forceinline__ void ring_prefetch(char *stage, const char *gsrc, size_t row_stride, int cl) {
     constexpr int U = TI * UPR;
@@ -83,17 +83,57 @@ __device__ __forceinline__ void ring_prefetch(char *stage, const char *gsrc, siz
     }
 }
 
+__device__ __forceinline__ void cp_async16_s(uint32_t sdst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+
+// Feeds a sub-slot's ring with TI-row tiles (UPR 16-byte units per row) that follow each other along a row of the
+// table.  Everything that does not change from tile to tile is formed once per walk: the lane's source pointer (row
+// and unit of its first element), its destination inside a stage, the stride between its elements; a tile then costs
+// one pointer increment and the copies themselves (ncu source page of the 256-bin kernel before this: 68 instructions
+// of 64-bit index arithmetic, a division by the ring depth and the copies per tile, next to the 331 of the tile body).
+template <int CC, int UPR>
+struct RingFeed {
+    static constexpr int U = TI * UPR;                 // 16-byte units per tile
+    static constexpr int N = (U + CC - 1) / CC;        // units per lane
+    static constexpr int STAGE = TI * TJ * 16;         // bytes per stage (the largest tile)
+    static_assert(CC % UPR == 0 || CC < UPR, "lanes of a sub-slot cover whole rows");
+    const char *src;      // this lane's first element of the next tile to load
+    size_t lane_step;     // bytes between consecutive elements of the lane in the table (whole rows)
+    uint32_t dst0;        // shared address of the lane's first element in stage 0
+    uint32_t load_stage;  // stage the next load goes to
+    bool mine;            // lane takes part (tiles smaller than the sub-slot)
+    __device__ __forceinline__ void start(char *ring, const char *tile0, size_t row_stride, int cl) {
+        src = tile0 + (size_t)(cl / UPR) * row_stride + (cl % UPR) * 16;
+        lane_step = (size_t)(CC / UPR) * row_stride;
+        dst0 = (uint32_t)__cvta_generic_to_shared(ring) + cl * 16;
+        load_stage = 0;
+        mine = U % CC == 0 || cl < U;
+    }
+    // load the next tile (when there is one) and step to the tile after it
+    __device__ __forceinline__ void load(bool there, int tile_bytes) {
+        if (there && mine) {
+            const uint32_t d = dst0 + load_stage * STAGE;
+#pragma unroll
+            for (int n = 0; n < N; ++n) cp_async16_s(d + n * CC * 16, src + n * lane_step);
+        }
+        src += tile_bytes;
+        load_stage = load_stage + 1 == NSTAGE ? 0 : load_stage + 1;
+    }
+};
+
 // quasiparticle tile, one side of the diagonal (SIDE 0: i > j everywhere, 1: i < j everywhere, 2: mixed)
 template <int CC, bool SC, bool RC, int SIDE>
-__device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const double *__restrict__ cn,
-                                        const double *__restrict__ cp, const double *__restrict__ cnd,
+__device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const double2 *__restrict__ cnp,
+                                        const double *__restrict__ cnd,
                                         const double *__restrict__ cns, int i0, int j0, double (&L)[TI],
                                         double (&G)[TI]) {
     double nj[TJ], pj[TJ];
 #pragma unroll
     for (int s = 0; s < TJ; ++s) {
-        nj[s] = cn[(j0 + s) * CC];
-        pj[s] = cp[(j0 + s) * CC];
+        const double2 v = cnp[(j0 + s) * CC];   // (n_j, p_j): one 128-bit read
+        nj[s] = v.x;
+        pj[s] = v.y;
     }
     double nsw[TI + TJ - 1], ndw[TI + TJ - 1];
     if (RC) {
@@ -141,15 +181,16 @@ __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const do
 // quasiparticle tile that contains the diagonal: i0 is a multiple of TI and j0 of TJ, so kb = i0 - j0 is 0 or -TJ and
 // every element's side of the diagonal is known at compile time (the diagonal itself carries Ks = 0)
 template <int CC, bool SC, bool RC, int KB>
-__device__ __forceinline__ void qp_tile_diag(const double2 *__restrict__ kt, const double *__restrict__ cn,
-                                             const double *__restrict__ cp, const double *__restrict__ cnd,
+__device__ __forceinline__ void qp_tile_diag(const double2 *__restrict__ kt, const double2 *__restrict__ cnp,
+                                             const double *__restrict__ cnd,
                                              const double *__restrict__ cns, int i0, int j0, double (&L)[TI],
                                              double (&G)[TI]) {
     double nj[TJ], pj[TJ];
 #pragma unroll
     for (int s = 0; s < TJ; ++s) {
-        nj[s] = cn[(j0 + s) * CC];
-        pj[s] = cp[(j0 + s) * CC];
+        const double2 v = cnp[(j0 + s) * CC];   // (n_j, p_j): one 128-bit read
+        nj[s] = v.x;
+        pj[s] = v.y;
     }
     double nsw[TI + TJ - 1], nda[TI];   // nda[m] = n_ph at |i-j| = m, m < TI covers both values of KB
     if (RC) {
@@ -194,9 +235,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
     constexpr int SUBS = 32 / CC;
     constexpr int NWARP = NT / 32;
     constexpr int STAGE_BYTES = TI * TJ * 16;               // one K2 tile (the largest)
-    double *sn = sm;                                   // [ncol][CC]
-    double *sp = sn + (size_t)ncol * CC;               // [ncol][CC]
-    double *snd = sp + (size_t)ncol * CC;              // [nep][CC]   n_ph at |i-j| ; later: stash a (diag family)
+    double2 *snp = reinterpret_cast<double2 *>(sm);    // [ncol][CC]  (n, p) interleaved: a window element is one 128-bit read
+    double *snd = sm + (size_t)2 * ncol * CC;          // [nep][CC]   n_ph at |i-j| ; later: stash a (diag family)
     double *sns = snd + (size_t)nep * CC;              // [2nep][CC]  n_ph at i+j   ; later: stash b (diag family)
     char *ring_all = reinterpret_cast<char *>(sns + (size_t)2 * nep * CC);
     const int tid = threadIdx.x;
@@ -230,9 +270,9 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
         for (int col = row_me; col < ncol; col += RPT) {
             const int i = col - PADF;
             if (live_me && i >= 0 && i < A.ne)
-                cp_async8(&sn[col * CC + c_me],
+                cp_async8(&snp[col * CC + c_me].x,
                           A.xmode == 2 ? exchange_slot(A, i, d_me) : &A.S[(long long)i * A.ncd + d_me]);
-            else sn[col * CC + c_me] = 0.0;
+            else snp[col * CC + c_me].x = 0.0;
         }
         // phonon occupations of the two index families (snd and sns are contiguous: 3*nep rows)
         for (int idx = row_me; idx < 3 * nep; idx += RPT) {
@@ -253,13 +293,12 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
         for (int col = row_me; col < ncol; col += RPT) {
             const int i = col - PADF;
             const double rv = (i >= 0 && i < A.ne) ? trho[i] : 0.0;
-            const double nv = sn[col * CC + c_me];
-            sp[col * CC + c_me] = rv * fmax(1.0 - nv / fmax(rv, 1e-30), 0.0);
+            const double nv = snp[col * CC + c_me].x;
+            snp[col * CC + c_me].y = rv * fmax(1.0 - nv / fmax(rv, 1e-30), 0.0);
         }
     }
     __syncthreads();
-    const double *cn = sn + (size_t)PADF * CC + cl;   // cn[idx*CC] = n[idx] of this lane's cell
-    const double *cp = sp + (size_t)PADF * CC + cl;
+    const double2 *cnp = snp + (size_t)PADF * CC + cl;   // cnp[idx*CC] = (n[idx], p[idx]) of this lane's cell
     const double *cnd = snd + cl;
     const double *cns = sns + cl;
     const int q = cell_of(cl);
@@ -281,27 +320,29 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
             const char *gk = reinterpret_cast<const char *>(tK2 + (size_t)i0 * nep);
             const size_t rstride = (size_t)nep * 16;
             __syncwarp();  // the previous round's last tile is no longer being read
+            RingFeed<CC, TJ> feed;
+            feed.start(ring, gk, rstride, cl);
 #pragma unroll
             for (int t = 0; t < NSTAGE - 1; ++t) {
-                if (t < ntile) ring_prefetch<CC, TJ>(ring + t * STAGE_BYTES, gk + (size_t)t * TJ * 16, rstride, cl);
+                feed.load(t < ntile, TJ * 16);
                 cp_async_commit();
             }
+            const char *kt_stage = ring;
             for (int t = 0; t < ntile; ++t) {
                 __syncwarp();
-                const int tn = t + NSTAGE - 1;
-                if (tn < ntile)
-                    ring_prefetch<CC, TJ>(ring + (tn % NSTAGE) * STAGE_BYTES, gk + (size_t)tn * TJ * 16, rstride, cl);
+                feed.load(t + NSTAGE - 1 < ntile, TJ * 16);
                 cp_async_commit();
                 cp_async_wait<NSTAGE - 1>();
                 __syncwarp();
-                const double2 *kt = reinterpret_cast<const double2 *>(ring + (t % NSTAGE) * STAGE_BYTES);
+                const double2 *kt = reinterpret_cast<const double2 *>(kt_stage);
+                kt_stage = kt_stage + STAGE_BYTES == ring + NSTAGE * STAGE_BYTES ? ring : kt_stage + STAGE_BYTES;
                 const int j0 = t * TJ;
                 const int kb = i0 - j0;
-                if (kb >= TJ) qp_tile<CC, SC, RC, 0>(kt, cn, cp, cnd, cns, i0, j0, L, G);
-                else if (kb <= -TI) qp_tile<CC, SC, RC, 1>(kt, cn, cp, cnd, cns, i0, j0, L, G);
-                else if (kb == 0) qp_tile_diag<CC, SC, RC, 0>(kt, cn, cp, cnd, cns, i0, j0, L, G);
-                else if (kb == -TJ) qp_tile_diag<CC, SC, RC, -TJ>(kt, cn, cp, cnd, cns, i0, j0, L, G);
-                else qp_tile<CC, SC, RC, 2>(kt, cn, cp, cnd, cns, i0, j0, L, G);
+                if (kb >= TJ) qp_tile<CC, SC, RC, 0>(kt, cnp, cnd, cns, i0, j0, L, G);
+                else if (kb <= -TI) qp_tile<CC, SC, RC, 1>(kt, cnp, cnd, cns, i0, j0, L, G);
+                else if (kb == 0) qp_tile_diag<CC, SC, RC, 0>(kt, cnp, cnd, cns, i0, j0, L, G);
+                else if (kb == -TJ) qp_tile_diag<CC, SC, RC, -TJ>(kt, cnp, cnd, cns, i0, j0, L, G);
+                else qp_tile<CC, SC, RC, 2>(kt, cnp, cnd, cns, i0, j0, L, G);
             }
             cp_async_wait<0>();
             if (live && work) {
@@ -311,7 +352,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                     const int i = i0 + r;
                     if (i < A.ne) {
                         double *dst = A.xmode == 1 ? exchange_slot(A, i, d) : &A.S[(long long)i * A.ncd + d];
-                        *dst = relax_update(cn[i * CC], cp[i * CC] * G[r], L[r], A.dt);
+                        const double2 v = cnp[i * CC];
+                        *dst = relax_update(v.x, v.y * G[r], L[r], A.dt);
                     }
                 }
             }
@@ -357,32 +399,36 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 const char *gk = reinterpret_cast<const char *>(tKsD + (size_t)k0 * nep + (size_t)t_lo * TJ);
                 const size_t rstride = (size_t)nep * 8;
                 __syncwarp();
+                RingFeed<CC, TJ / 2> feed;
+                feed.start(ring, gk, rstride, cl);
 #pragma unroll
                 for (int t = 0; t < NSTAGE - 1; ++t) {
-                    if (t < mytiles) ring_prefetch<CC, TJ / 2>(ring + t * STAGE_BYTES, gk + (size_t)t * TJ * 8, rstride, cl);
+                    feed.load(t < mytiles, TJ * 8);
                     cp_async_commit();
                 }
+                const char *kt_stage = ring;
                 for (int t = 0; t < ntile; ++t) {
                     __syncwarp();
-                    const int tn = t + NSTAGE - 1;
-                    if (tn < mytiles)
-                        ring_prefetch<CC, TJ / 2>(ring + (tn % NSTAGE) * STAGE_BYTES, gk + (size_t)tn * TJ * 8, rstride, cl);
+                    feed.load(t + NSTAGE - 1 < mytiles, TJ * 8);
                     cp_async_commit();
                     cp_async_wait<NSTAGE - 1>();
                     __syncwarp();
                     if (t >= mytiles) continue;
-                    const double *kt = reinterpret_cast<const double *>(ring + (t % NSTAGE) * STAGE_BYTES);
+                    const double *kt = reinterpret_cast<const double *>(kt_stage);
+                    kt_stage = kt_stage + STAGE_BYTES == ring + NSTAGE * STAGE_BYTES ? ring : kt_stage + STAGE_BYTES;
                     const int j0 = (t_lo + t) * TJ;
                     double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
 #pragma unroll
                     for (int s = 0; s < TJ; ++s) {
-                        nj[s] = cn[(j0 + s) * CC];
-                        pj[s] = cp[(j0 + s) * CC];
+                        const double2 v = cnp[(j0 + s) * CC];
+                        nj[s] = v.x;
+                        pj[s] = v.y;
                     }
 #pragma unroll
                     for (int t2 = 0; t2 < TI + TJ - 1; ++t2) {
-                        nwn[t2] = cn[(j0 + k0 + t2) * CC];
-                        pwn[t2] = cp[(j0 + k0 + t2) * CC];
+                        const double2 v = cnp[(j0 + k0 + t2) * CC];
+                        nwn[t2] = v.x;
+                        pwn[t2] = v.y;
                     }
 #pragma unroll
                     for (int r = 0; r < TI; ++r) {
@@ -462,33 +508,37 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 const char *gk = reinterpret_cast<const char *>(tKrA + (size_t)m0 * nep + jlo);
                 const size_t rstride = (size_t)nep * 8;
                 __syncwarp();
+                RingFeed<CC, TJ / 2> feed;
+                feed.start(ring, gk, rstride, cl);
 #pragma unroll
                 for (int t = 0; t < NSTAGE - 1; ++t) {
-                    if (t < mytiles) ring_prefetch<CC, TJ / 2>(ring + t * STAGE_BYTES, gk + (size_t)t * TJ * 8, rstride, cl);
+                    feed.load(t < mytiles, TJ * 8);
                     cp_async_commit();
                 }
+                const char *kt_stage = ring;
                 for (int t = 0; t < ntile; ++t) {
                     __syncwarp();
-                    const int tn = t + NSTAGE - 1;
-                    if (tn < mytiles)
-                        ring_prefetch<CC, TJ / 2>(ring + (tn % NSTAGE) * STAGE_BYTES, gk + (size_t)tn * TJ * 8, rstride, cl);
+                    feed.load(t + NSTAGE - 1 < mytiles, TJ * 8);
                     cp_async_commit();
                     cp_async_wait<NSTAGE - 1>();
                     __syncwarp();
                     if (t >= mytiles) continue;
-                    const double *kt = reinterpret_cast<const double *>(ring + (t % NSTAGE) * STAGE_BYTES);
+                    const double *kt = reinterpret_cast<const double *>(kt_stage);
+                    kt_stage = kt_stage + STAGE_BYTES == ring + NSTAGE * STAGE_BYTES ? ring : kt_stage + STAGE_BYTES;
                     const int j0 = jlo + t * TJ;
                     double nj[TJ], pj[TJ], nwn[TI + TJ - 1], pwn[TI + TJ - 1];
 #pragma unroll
                     for (int s = 0; s < TJ; ++s) {
-                        nj[s] = cn[(j0 + s) * CC];
-                        pj[s] = cp[(j0 + s) * CC];
+                        const double2 v = cnp[(j0 + s) * CC];
+                        nj[s] = v.x;
+                        pj[s] = v.y;
                     }
                     const int base = m0 - j0 - (TJ - 1);     // index m-j = base + (r - s + TJ-1)
 #pragma unroll
                     for (int t2 = 0; t2 < TI + TJ - 1; ++t2) {
-                        nwn[t2] = cn[(base + t2) * CC];
-                        pwn[t2] = cp[(base + t2) * CC];
+                        const double2 v = cnp[(base + t2) * CC];
+                        nwn[t2] = v.x;
+                        pwn[t2] = v.y;
                     }
 #pragma unroll
                     for (int r = 0; r < TI; ++r) {

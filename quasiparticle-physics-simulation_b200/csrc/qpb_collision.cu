@@ -313,15 +313,26 @@ struct StructCfg {
     // one round of each pass and give each scheduler four warps to hide the FP64 latency with (ncu at 256 bins with
     // 8 warps: 12.5 % warps active, top stall "wait")
     static constexpr int NT = CC >= 16 ? 512 : (CC >= 8 ? 256 : 128);
-    static size_t smem(int nep) {
+    static size_t smem(int nep, int nt = NT) {
         return sizeof(double) * (size_t)CC * (2 * (nep + PADF + PADB) + 3 * nep) +
-               (size_t)(NT / 32) * (32 / CC) * NSTAGE * (TI * TJ * 16);
+               (size_t)(nt / 32) * (32 / CC) * NSTAGE * (TI * TJ * 16);
     }
 };
 
-template <int CC, bool SC, bool RC, bool PH>
+// Energy grids of at most 64 (padded) bins have no more than 8 row blocks: a 512-thread CTA would leave half of its warp
+// slots without a row block in every pass.  They run 256-thread CTAs of 32 cells, two per SM (2 x 105 KB of shared
+// memory at 64 bins), so that one CTA stages its columns while the other one computes.  QPB_COLL_NT=512 restores the
+// wide CTA (A/B runs).
+constexpr int STRUCT_SMALL_NEP = 64;
+constexpr int STRUCT_SMALL_NT = 256;
+static bool struct_small_grid(int nep) {
+    if (nep > STRUCT_SMALL_NEP) return false;
+    const char *e = getenv("QPB_COLL_NT");
+    return !(e && atoi(e) == 512);
+}
+
+template <int CC, int NT, bool SC, bool RC, bool PH>
 static int launch_struct(qpb_ctx *c, const StructArgs &A, size_t smem) {
-    constexpr int NT = StructCfg<CC>::NT;
     auto kern = k_collide_struct<CC, NT, SC, RC, PH>;
     static bool configured = false;
     if (!configured) {
@@ -334,11 +345,19 @@ static int launch_struct(qpb_ctx *c, const StructArgs &A, size_t smem) {
     return QPB_OK;
 }
 
+template <int CC, int NT>
+static int dispatch_struct_nt(qpb_ctx *c, const StructArgs &A, size_t smem, bool sc, bool rc, bool ph) {
+    if (sc && rc) return ph ? launch_struct<CC, NT, true, true, true>(c, A, smem) : launch_struct<CC, NT, true, true, false>(c, A, smem);
+    if (sc) return ph ? launch_struct<CC, NT, true, false, true>(c, A, smem) : launch_struct<CC, NT, true, false, false>(c, A, smem);
+    return ph ? launch_struct<CC, NT, false, true, true>(c, A, smem) : launch_struct<CC, NT, false, true, false>(c, A, smem);
+}
+
 template <int CC>
 static int dispatch_struct(qpb_ctx *c, const StructArgs &A, size_t smem, bool sc, bool rc, bool ph) {
-    if (sc && rc) return ph ? launch_struct<CC, true, true, true>(c, A, smem) : launch_struct<CC, true, true, false>(c, A, smem);
-    if (sc) return ph ? launch_struct<CC, true, false, true>(c, A, smem) : launch_struct<CC, true, false, false>(c, A, smem);
-    return ph ? launch_struct<CC, false, true, true>(c, A, smem) : launch_struct<CC, false, true, false>(c, A, smem);
+    if (CC == 32 && struct_small_grid(A.nep))
+        return dispatch_struct_nt<CC, CC == 32 ? STRUCT_SMALL_NT : StructCfg<CC>::NT>(
+            c, A, StructCfg<CC>::smem(A.nep, STRUCT_SMALL_NT), sc, rc, ph);
+    return dispatch_struct_nt<CC, StructCfg<CC>::NT>(c, A, smem, sc, rc, ph);
 }
 
 template <int CG>
