@@ -384,9 +384,11 @@ def load_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
-def load_profile_traffic(tag):
+def load_profile_traffic(tag, n_coll_cells=None, nbins=None):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures under
-    profiles/ (documentation of an earlier run of the same kernels, not a measurement of this one)."""
+    profiles/ (documentation of an earlier run of the same kernels, not a measurement of this one).  The C3 kernels were
+    captured on a slice of the workload (collision: 37 888 cells of the 256-bin grid; spectral passes: 16 bins of the
+    2048^2 grid): their bytes are scaled to the cells / bins of this rank's launches, and the line says so."""
     out = {}
     for name in ("r2_ncu_kernels.json", "r1_ncu_kernels.json"):
         path = os.path.join(ROOT, "profiles", name)
@@ -395,13 +397,23 @@ def load_profile_traffic(tag):
         with open(path) as f:
             k = json.load(f)
         if tag == "c3":
-            sw = [v["dram_bytes"] for n, v in k.items() if "2048" in n and "sweep" in n]
-            co = []
-        else:
-            sw = [v["dram_bytes"] for n, v in k.items() if n.endswith("[c2_k_pr_resident]")]
-            if not sw:
-                sw = [v["dram_bytes"] for n, v in k.items() if n.endswith("[k_sweep_x_pipe]") or n.endswith("[k_sweep_y_pipe]")]
-            co = [v["dram_bytes"] for n, v in k.items() if n.endswith("[k_collide_struct]")]
+            sw = [v["dram_bytes"] / v["slice"]["bins"] * (nbins or 0) for n, v in k.items()
+                  if n.split("[")[-1] in ("c3_k_dct_forward]", "c3_k_dct_inverse]", "c3_k_thomas_fused]") and "slice" in v]
+            co = [v["dram_bytes"] / v["slice"]["cells"] * (n_coll_cells or 0) for n, v in k.items()
+                  if n.endswith("[c3_k_collide_struct]") and "slice" in v]
+            if len(sw) == 3 and nbins and "sweep" not in out:
+                out["sweep"] = float(np.mean(sw))
+                out["sweep_source"] = ("committed ncu captures of the three spectral passes on 16 bins of this grid "
+                                       "(profiles/r2_ncu_kernels.json), scaled to the bins of this rank; not this run")
+            if co and n_coll_cells and "collide" not in out:
+                out["collide"] = float(co[0])
+                out["collide_source"] = ("committed ncu capture of this kernel on 37 888 cells of this energy grid "
+                                         "(profiles/r2_ncu_kernels.json), scaled to the cells of this rank; not this run")
+            continue
+        sw = [v["dram_bytes"] for n, v in k.items() if n.endswith("[c2_k_pr_resident]")]
+        if not sw:
+            sw = [v["dram_bytes"] for n, v in k.items() if n.endswith("[k_sweep_x_pipe]") or n.endswith("[k_sweep_y_pipe]")]
+        co = [v["dram_bytes"] for n, v in k.items() if n.endswith("k_collide_struct]") and "[c3_" not in n]
         if sw and "sweep" not in out:
             out["sweep"] = float(np.mean(sw))
         if co and "collide" not in out:
@@ -416,7 +428,8 @@ def rooflines(n_sweep_cells, ncd, ne, n_coll_cells, tx, ty, nsweep_launches, bin
     sweep_ms = tx + ty
     rs = {"bound": "hbm", "achieved": 16.0 * n_sweep_cells * bin_sweeps / (sweep_ms * 1e-3) / 1e9 if sweep_ms > 0 else 0.0,
           "peak": peaks["hbm_gbs"], "unit": "GB/s", "traffic": traffic.get("sweep"),
-          "traffic_source": "committed ncu capture (profiles/), not this run" if traffic.get("sweep") else None,
+          "traffic_source": traffic.get("sweep_source", "committed ncu capture (profiles/), not this run")
+          if traffic.get("sweep") else None,
           "kernel": ("k_dct_forward + k_thomas_frozen + k_dct_inverse (direct spectral solve: three passes per bin)"
                      if sweep_path == 4 else
                      "k_pr_resident (bin-resident cluster solve: right-hand side, all line sweeps of the iteration and the "
@@ -444,7 +457,8 @@ def rooflines(n_sweep_cells, ncd, ne, n_coll_cells, tx, ty, nsweep_launches, bin
     flops = 21.0 * ne * ne * n_coll_cells * ncoll
     rc = {"bound": "fp64", "achieved": flops / (tc * 1e-3) / 1e12 if tc > 0 else 0.0, "peak": fp64_peak,
           "unit": "TFLOP/s", "traffic": traffic.get("collide"),
-          "traffic_source": "committed ncu capture (profiles/), not this run" if traffic.get("collide") else None,
+          "traffic_source": traffic.get("collide_source", "committed ncu capture (profiles/), not this run")
+          if traffic.get("collide") else None,
           "kernel": "k_collide_struct", "launches": int(ncoll), "ms_per_launch": tc / max(1, ncoll),
           "peak_source": "measured in this run: DFMA loop on all SMs (qpb_measure_fp64)"}
     rc["frac"] = rc["achieved"] / rc["peak"] if fp64_peak else None
@@ -713,7 +727,9 @@ def run_sharded(args, strong: bool):
     if rank == 0:
         coll_ms, sweep_ms, ser_step = (float(v) for v in parts.tolist())
         roof_sweep, roof_coll = rooflines(n, ny * nx, ne, nloc, tx, ty, nxl + nyl, bin_sweeps, tc, ncl, peaks,
-                                          peak_src, fp64_peak, load_profile_traffic("c3" if strong else "c2"),
+                                          peak_src, fp64_peak,
+                                          load_profile_traffic("c3", nloc, plan.nbins()) if strong
+                                          else load_profile_traffic("c2"),
                                           sweep_path=dd1["sweep_path"])
         roof_coll["scope"] = f"rank 0: {nloc} of {n} cells, all bins"
         roof_sweep["scope"] = f"rank 0: {plan.nbins()} of {ne} bins, all cells"

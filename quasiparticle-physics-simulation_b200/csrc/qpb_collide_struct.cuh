@@ -123,10 +123,11 @@ struct RingFeed {
 };
 
 // quasiparticle tile, one side of the diagonal (SIDE 0: i > j everywhere, 1: i < j everywhere, 2: mixed)
+// cnd2 / cns2: the phonon occupations at |i-j| and i+j, two consecutive indices per 128-bit slot (ph_pair below)
 template <int CC, bool SC, bool RC, int SIDE>
 __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const double2 *__restrict__ cnp,
-                                        const double *__restrict__ cnd,
-                                        const double *__restrict__ cns, int i0, int j0, double (&L)[TI],
+                                        const double2 *__restrict__ cnd2,
+                                        const double2 *__restrict__ cns2, int i0, int j0, double (&L)[TI],
                                         double (&G)[TI]) {
     double nj[TJ], pj[TJ];
 #pragma unroll
@@ -135,16 +136,27 @@ __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const do
         nj[s] = v.x;
         pj[s] = v.y;
     }
-    double nsw[TI + TJ - 1], ndw[TI + TJ - 1];
+    // windows of TI + TJ - 1 = 11 consecutive indices as six 128-bit reads: i0 + j0 is even, the first index of the
+    // |i-j| window is odd (kb is a multiple of TJ), so that one starts a slot earlier (element 0 unused)
+    static_assert((TI + TJ - 1) <= 11 && TI % 2 == 0 && TJ % 2 == 0, "window slots");
+    double nsw[12], ndw[12];
     if (RC) {
 #pragma unroll
-        for (int t = 0; t < TI + TJ - 1; ++t) nsw[t] = cns[(i0 + j0 + t) * CC];
+        for (int t = 0; t < 6; ++t) {
+            const double2 v = cns2[(((i0 + j0) >> 1) + t) * CC];
+            nsw[2 * t] = v.x;
+            nsw[2 * t + 1] = v.y;
+        }
     }
     const int kb = i0 - j0;
     if (SC && SIDE != 2) {
-        const int base = SIDE == 0 ? kb - (TJ - 1) : -kb - (TI - 1);
+        const int base = SIDE == 0 ? kb - (TJ - 1) : -kb - (TI - 1);   // odd
 #pragma unroll
-        for (int t = 0; t < TI + TJ - 1; ++t) ndw[t] = cnd[(base + t) * CC];
+        for (int t = 0; t < 6; ++t) {
+            const double2 v = cnd2[(((base - 1) >> 1) + t) * CC];
+            ndw[2 * t] = v.x;
+            ndw[2 * t + 1] = v.y;
+        }
     }
 #pragma unroll
     for (int r = 0; r < TI; ++r) {
@@ -153,17 +165,19 @@ __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const do
             const double2 kv = kt[r * TJ + s];
             if (SC) {
                 if (SIDE == 0) {
-                    const double e = kv.x * ndw[r - s + TJ - 1];
+                    const double e = kv.x * ndw[r - s + TJ];
                     L[r] = fma(e + kv.x, pj[s], L[r]);   // stimulated + spontaneous emission out of i
                     G[r] = fma(e, nj[s], G[r]);
                 } else if (SIDE == 1) {
-                    const double e = kv.x * ndw[s - r + TI - 1];
+                    const double e = kv.x * ndw[s - r + TI];
                     L[r] = fma(e, pj[s], L[r]);
                     G[r] = fma(e + kv.x, nj[s], G[r]);   // spontaneous emission into i
                 } else {
                     const int k = kb + r - s;
                     if (k != 0) {
-                        const double e = kv.x * cnd[(k > 0 ? k : -k) * CC];
+                        const int ka = k > 0 ? k : -k;
+                        const double2 v = cnd2[(ka >> 1) * CC];
+                        const double e = kv.x * ((ka & 1) ? v.y : v.x);
                         L[r] = fma(k > 0 ? e + kv.x : e, pj[s], L[r]);
                         G[r] = fma(k > 0 ? e : e + kv.x, nj[s], G[r]);
                     }
@@ -182,8 +196,8 @@ __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const do
 // every element's side of the diagonal is known at compile time (the diagonal itself carries Ks = 0)
 template <int CC, bool SC, bool RC, int KB>
 __device__ __forceinline__ void qp_tile_diag(const double2 *__restrict__ kt, const double2 *__restrict__ cnp,
-                                             const double *__restrict__ cnd,
-                                             const double *__restrict__ cns, int i0, int j0, double (&L)[TI],
+                                             const double2 *__restrict__ cnd2,
+                                             const double2 *__restrict__ cns2, int i0, int j0, double (&L)[TI],
                                              double (&G)[TI]) {
     double nj[TJ], pj[TJ];
 #pragma unroll
@@ -192,14 +206,22 @@ __device__ __forceinline__ void qp_tile_diag(const double2 *__restrict__ kt, con
         nj[s] = v.x;
         pj[s] = v.y;
     }
-    double nsw[TI + TJ - 1], nda[TI];   // nda[m] = n_ph at |i-j| = m, m < TI covers both values of KB
+    double nsw[12], nda[TI];   // nda[m] = n_ph at |i-j| = m, m < TI covers both values of KB
     if (RC) {
 #pragma unroll
-        for (int t = 0; t < TI + TJ - 1; ++t) nsw[t] = cns[(i0 + j0 + t) * CC];
+        for (int t = 0; t < 6; ++t) {
+            const double2 v = cns2[(((i0 + j0) >> 1) + t) * CC];
+            nsw[2 * t] = v.x;
+            nsw[2 * t + 1] = v.y;
+        }
     }
     if (SC) {
 #pragma unroll
-        for (int m = 1; m < TI; ++m) nda[m] = cnd[m * CC];
+        for (int m = 0; m < TI; m += 2) {
+            const double2 v = cnd2[(m >> 1) * CC];
+            nda[m] = v.x;
+            nda[m + 1] = v.y;
+        }
     }
 #pragma unroll
     for (int r = 0; r < TI; ++r) {
@@ -284,8 +306,11 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                     om = A.smap[idx - nep];
                 }
             }
-            if (om >= 0) cp_async8(&snd[idx * CC + c_me], &A.P[(long long)om * ncell + q_me]);
-            else snd[idx * CC + c_me] = 0.0;
+            // two consecutive indices of a family share a 128-bit slot: [idx / 2][cell][idx % 2] (nep is even, so the
+            // formula runs through both families)
+            double *slot_ph = &snd[((size_t)(idx >> 1) * CC + c_me) * 2 + (idx & 1)];
+            if (om >= 0) cp_async8(slot_ph, &A.P[(long long)om * ncell + q_me]);
+            else *slot_ph = 0.0;
         }
         cp_async_commit();
         cp_async_wait<0>();
@@ -299,8 +324,8 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
     }
     __syncthreads();
     const double2 *cnp = snp + (size_t)PADF * CC + cl;   // cnp[idx*CC] = (n[idx], p[idx]) of this lane's cell
-    const double *cnd = snd + cl;
-    const double *cns = sns + cl;
+    const double2 *cnd2 = reinterpret_cast<const double2 *>(snd) + cl;   // cnd2[(k / 2) * CC] = n_ph at |i-j| = k, k + 1 (k even)
+    const double2 *cns2 = reinterpret_cast<const double2 *>(sns) + cl;   // cns2[(m / 2) * CC] = n_ph at i+j = m, m + 1 (m even)
     const int q = cell_of(cl);
     const bool live = q >= 0 && q < ncell;
 
@@ -329,20 +354,21 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
             }
             const char *kt_stage = ring;
             for (int t = 0; t < ntile; ++t) {
+                // the lane's own pieces of tile t have landed; after the warp barrier everybody's have, and everybody is
+                // done with tile t - 1, whose stage the next load overwrites
+                cp_async_wait<NSTAGE - 2>();
                 __syncwarp();
                 feed.load(t + NSTAGE - 1 < ntile, TJ * 16);
                 cp_async_commit();
-                cp_async_wait<NSTAGE - 1>();
-                __syncwarp();
                 const double2 *kt = reinterpret_cast<const double2 *>(kt_stage);
                 kt_stage = kt_stage + STAGE_BYTES == ring + NSTAGE * STAGE_BYTES ? ring : kt_stage + STAGE_BYTES;
                 const int j0 = t * TJ;
                 const int kb = i0 - j0;
-                if (kb >= TJ) qp_tile<CC, SC, RC, 0>(kt, cnp, cnd, cns, i0, j0, L, G);
-                else if (kb <= -TI) qp_tile<CC, SC, RC, 1>(kt, cnp, cnd, cns, i0, j0, L, G);
-                else if (kb == 0) qp_tile_diag<CC, SC, RC, 0>(kt, cnp, cnd, cns, i0, j0, L, G);
-                else if (kb == -TJ) qp_tile_diag<CC, SC, RC, -TJ>(kt, cnp, cnd, cns, i0, j0, L, G);
-                else qp_tile<CC, SC, RC, 2>(kt, cnp, cnd, cns, i0, j0, L, G);
+                if (kb >= TJ) qp_tile<CC, SC, RC, 0>(kt, cnp, cnd2, cns2, i0, j0, L, G);
+                else if (kb <= -TI) qp_tile<CC, SC, RC, 1>(kt, cnp, cnd2, cns2, i0, j0, L, G);
+                else if (kb == 0) qp_tile_diag<CC, SC, RC, 0>(kt, cnp, cnd2, cns2, i0, j0, L, G);
+                else if (kb == -TJ) qp_tile_diag<CC, SC, RC, -TJ>(kt, cnp, cnd2, cns2, i0, j0, L, G);
+                else qp_tile<CC, SC, RC, 2>(kt, cnp, cnd2, cns2, i0, j0, L, G);
             }
             cp_async_wait<0>();
             if (live && work) {
@@ -408,11 +434,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 }
                 const char *kt_stage = ring;
                 for (int t = 0; t < ntile; ++t) {
+                    cp_async_wait<NSTAGE - 2>();
                     __syncwarp();
                     feed.load(t + NSTAGE - 1 < mytiles, TJ * 8);
                     cp_async_commit();
-                    cp_async_wait<NSTAGE - 1>();
-                    __syncwarp();
                     if (t >= mytiles) continue;
                     const double *kt = reinterpret_cast<const double *>(kt_stage);
                     kt_stage = kt_stage + STAGE_BYTES == ring + NSTAGE * STAGE_BYTES ? ring : kt_stage + STAGE_BYTES;
@@ -517,11 +542,10 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 }
                 const char *kt_stage = ring;
                 for (int t = 0; t < ntile; ++t) {
+                    cp_async_wait<NSTAGE - 2>();
                     __syncwarp();
                     feed.load(t + NSTAGE - 1 < mytiles, TJ * 8);
                     cp_async_commit();
-                    cp_async_wait<NSTAGE - 1>();
-                    __syncwarp();
                     if (t >= mytiles) continue;
                     const double *kt = reinterpret_cast<const double *>(kt_stage);
                     kt_stage = kt_stage + STAGE_BYTES == ring + NSTAGE * STAGE_BYTES ? ring : kt_stage + STAGE_BYTES;
