@@ -159,19 +159,21 @@ __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const do
         }
     }
 #pragma unroll
-    for (int r = 0; r < TI; ++r) {
+    for (int s = 0; s < TJ; ++s) {
 #pragma unroll
-        for (int s = 0; s < TJ; ++s) {
+        for (int r = 0; r < TI; ++r) {
             const double2 kv = kt[r * TJ + s];
             if (SC) {
                 if (SIDE == 0) {
                     const double e = kv.x * ndw[r - s + TJ];
-                    L[r] = fma(e + kv.x, pj[s], L[r]);   // stimulated + spontaneous emission out of i
+                    L[r] = fma(kv.x, pj[s], L[r]);       // spontaneous emission out of i
+                    L[r] = fma(e, pj[s], L[r]);          // stimulated
                     G[r] = fma(e, nj[s], G[r]);
                 } else if (SIDE == 1) {
                     const double e = kv.x * ndw[s - r + TI];
                     L[r] = fma(e, pj[s], L[r]);
-                    G[r] = fma(e + kv.x, nj[s], G[r]);   // spontaneous emission into i
+                    G[r] = fma(e, nj[s], G[r]);
+                    G[r] = fma(kv.x, nj[s], G[r]);       // spontaneous emission into i
                 } else {
                     const int k = kb + r - s;
                     if (k != 0) {
@@ -185,7 +187,8 @@ __device__ __forceinline__ void qp_tile(const double2 *__restrict__ kt, const do
             }
             if (RC) {
                 const double g = kv.y * nsw[r + s];
-                L[r] = fma(g + kv.y, nj[s], L[r]);
+                L[r] = fma(kv.y, nj[s], L[r]);
+                L[r] = fma(g, nj[s], L[r]);
                 G[r] = fma(g, pj[s], G[r]);
             }
         }
@@ -224,24 +227,27 @@ __device__ __forceinline__ void qp_tile_diag(const double2 *__restrict__ kt, con
         }
     }
 #pragma unroll
-    for (int r = 0; r < TI; ++r) {
+    for (int s = 0; s < TJ; ++s) {
 #pragma unroll
-        for (int s = 0; s < TJ; ++s) {
+        for (int r = 0; r < TI; ++r) {
             const double2 kv = kt[r * TJ + s];
             const int k = KB + r - s;   // compile-time after unrolling
             if (SC && k != 0) {
                 const double e = kv.x * nda[k > 0 ? k : -k];
                 if (k > 0) {
-                    L[r] = fma(e + kv.x, pj[s], L[r]);
+                    L[r] = fma(kv.x, pj[s], L[r]);
+                    L[r] = fma(e, pj[s], L[r]);
                     G[r] = fma(e, nj[s], G[r]);
                 } else {
                     L[r] = fma(e, pj[s], L[r]);
-                    G[r] = fma(e + kv.x, nj[s], G[r]);
+                    G[r] = fma(e, nj[s], G[r]);
+                    G[r] = fma(kv.x, nj[s], G[r]);
                 }
             }
             if (RC) {
                 const double g = kv.y * nsw[r + s];
-                L[r] = fma(g + kv.y, nj[s], L[r]);
+                L[r] = fma(kv.y, nj[s], L[r]);
+                L[r] = fma(g, nj[s], L[r]);
                 G[r] = fma(g, pj[s], G[r]);
             }
         }
