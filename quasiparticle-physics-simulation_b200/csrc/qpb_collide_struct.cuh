@@ -29,7 +29,7 @@ struct StructArgs {
     double *S;
     double *P;
     const int32_t *c2d;
-    const double2 *K2;   // [nep][nep]  (dE*Ks, 2dE*Kr)
+    const double2 *K2;   // [nep][nep]  (dE*Ks, 2dE*Kr)                                  all three stored tile by tile
     const double *KsD;   // [nep][nep]  dE*Ks[j+k][j]
     const double *KrA;   // [2nep][nep] dE*Kr[m-j][j] * (2 if j<m-j, 1 if j==m-j, else 0)
     const double *rho;   // [nep] zero padded
@@ -87,40 +87,41 @@ __device__ __forceinline__ void cp_async16_s(uint32_t sdst, const void *gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sdst), "l"(gsrc) : "memory");
 }
 
-// Feeds a sub-slot's ring with TI-row tiles (UPR 16-byte units per row) that follow each other along a row of the
-// table.  Everything that does not change from tile to tile is formed once per walk: the lane's source pointer (row
-// and unit of its first element), its destination inside a stage, the stride between its elements; a tile then costs
-// one pointer increment and the copies themselves (ncu source page of the 256-bin kernel before this: 68 instructions
-// of 64-bit index arithmetic, a division by the ring depth and the copies per tile, next to the 331 of the tile body).
-template <int CC, int UPR>
+// Feeds a sub-slot's ring with the TI x TJ tiles of a table that follow each other along a row block.  The tables are
+// stored tile by tile (struct_tile_index: a tile is one contiguous run of UNITS 16-byte units, the tiles of a row block
+// follow each other), so a tile is a flat copy: whole 128-byte lines from L2 and few shared-memory write wavefronts
+// (row-major tables: every 32- or 64-byte row piece of a tile arrived as a write of its own, 8-16 wavefronts per copy
+// instruction where 4 are needed).  Everything that does not change from tile to tile is formed once per walk.
+template <int CC, int UNITS>
 struct RingFeed {
-    static constexpr int U = TI * UPR;                 // 16-byte units per tile
-    static constexpr int N = (U + CC - 1) / CC;        // units per lane
+    static constexpr int N = (UNITS + CC - 1) / CC;    // units per lane
     static constexpr int STAGE = TI * TJ * 16;         // bytes per stage (the largest tile)
-    static_assert(CC % UPR == 0 || CC < UPR, "lanes of a sub-slot cover whole rows");
-    const char *src;      // this lane's first element of the next tile to load
-    size_t lane_step;     // bytes between consecutive elements of the lane in the table (whole rows)
-    uint32_t dst0;        // shared address of the lane's first element in stage 0
+    const char *src;      // this lane's first unit of the next tile to load
+    uint32_t dst0;        // shared address of the lane's first unit in stage 0
     uint32_t load_stage;  // stage the next load goes to
     bool mine;            // lane takes part (tiles smaller than the sub-slot)
-    __device__ __forceinline__ void start(char *ring, const char *tile0, size_t row_stride, int cl) {
-        src = tile0 + (size_t)(cl / UPR) * row_stride + (cl % UPR) * 16;
-        lane_step = (size_t)(CC / UPR) * row_stride;
+    __device__ __forceinline__ void start(char *ring, const char *tile0, int cl) {
+        src = tile0 + cl * 16;
         dst0 = (uint32_t)__cvta_generic_to_shared(ring) + cl * 16;
         load_stage = 0;
-        mine = U % CC == 0 || cl < U;
+        mine = UNITS % CC == 0 || cl < UNITS;
     }
     // load the next tile (when there is one) and step to the tile after it
-    __device__ __forceinline__ void load(bool there, int tile_bytes) {
+    __device__ __forceinline__ void load(bool there) {
         if (there && mine) {
             const uint32_t d = dst0 + load_stage * STAGE;
 #pragma unroll
-            for (int n = 0; n < N; ++n) cp_async16_s(d + n * CC * 16, src + n * lane_step);
+            for (int n = 0; n < N; ++n) cp_async16_s(d + n * CC * 16, src + n * CC * 16);
         }
-        src += tile_bytes;
+        src += UNITS * 16;
         load_stage = load_stage + 1 == NSTAGE ? 0 : load_stage + 1;
     }
 };
+
+// Element (row, col) of a table stored tile by tile; ncols = columns of the table (a multiple of TJ), rows in blocks of TI.
+__host__ __device__ __forceinline__ size_t struct_tile_index(int row, int col, int ncols) {
+    return ((size_t)(row / TI) * (ncols / TJ) + col / TJ) * (TI * TJ) + (row % TI) * TJ + col % TJ;
+}
 
 // quasiparticle tile, one side of the diagonal (SIDE 0: i > j everywhere, 1: i < j everywhere, 2: mixed)
 // cnd2 / cns2: the phonon occupations at |i-j| and i+j, two consecutive indices per 128-bit slot (ph_pair below)
@@ -348,14 +349,13 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
             double L[TI], G[TI];
 #pragma unroll
             for (int r = 0; r < TI; ++r) L[r] = G[r] = 0.0;
-            const char *gk = reinterpret_cast<const char *>(tK2 + (size_t)i0 * nep);
-            const size_t rstride = (size_t)nep * 16;
+            const char *gk = reinterpret_cast<const char *>(tK2 + struct_tile_index(i0, 0, nep));
             __syncwarp();  // the previous round's last tile is no longer being read
-            RingFeed<CC, TJ> feed;
-            feed.start(ring, gk, rstride, cl);
+            RingFeed<CC, TI * TJ> feed;
+            feed.start(ring, gk, cl);
 #pragma unroll
             for (int t = 0; t < NSTAGE - 1; ++t) {
-                feed.load(t < ntile, TJ * 16);
+                feed.load(t < ntile);
                 cp_async_commit();
             }
             const char *kt_stage = ring;
@@ -364,7 +364,7 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 // done with tile t - 1, whose stage the next load overwrites
                 cp_async_wait<NSTAGE - 2>();
                 __syncwarp();
-                feed.load(t + NSTAGE - 1 < ntile, TJ * 16);
+                feed.load(t + NSTAGE - 1 < ntile);
                 cp_async_commit();
                 const double2 *kt = reinterpret_cast<const double2 *>(kt_stage);
                 kt_stage = kt_stage + STAGE_BYTES == ring + NSTAGE * STAGE_BYTES ? ring : kt_stage + STAGE_BYTES;
@@ -428,21 +428,20 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 int ntile = mytiles;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ntile = max(ntile, __shfl_xor_sync(0xffffffffu, ntile, o));
-                const char *gk = reinterpret_cast<const char *>(tKsD + (size_t)k0 * nep + (size_t)t_lo * TJ);
-                const size_t rstride = (size_t)nep * 8;
+                const char *gk = reinterpret_cast<const char *>(tKsD + struct_tile_index(k0, t_lo * TJ, nep));
                 __syncwarp();
-                RingFeed<CC, TJ / 2> feed;
-                feed.start(ring, gk, rstride, cl);
+                RingFeed<CC, TI * TJ / 2> feed;
+                feed.start(ring, gk, cl);
 #pragma unroll
                 for (int t = 0; t < NSTAGE - 1; ++t) {
-                    feed.load(t < mytiles, TJ * 8);
+                    feed.load(t < mytiles);
                     cp_async_commit();
                 }
                 const char *kt_stage = ring;
                 for (int t = 0; t < ntile; ++t) {
                     cp_async_wait<NSTAGE - 2>();
                     __syncwarp();
-                    feed.load(t + NSTAGE - 1 < mytiles, TJ * 8);
+                    feed.load(t + NSTAGE - 1 < mytiles);
                     cp_async_commit();
                     if (t >= mytiles) continue;
                     const double *kt = reinterpret_cast<const double *>(kt_stage);
@@ -536,21 +535,20 @@ __global__ void __launch_bounds__(NT, NT <= 256 ? 2 : 1) k_collide_struct(const 
                 int ntile = mytiles;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) ntile = max(ntile, __shfl_xor_sync(0xffffffffu, ntile, o));
-                const char *gk = reinterpret_cast<const char *>(tKrA + (size_t)m0 * nep + jlo);
-                const size_t rstride = (size_t)nep * 8;
+                const char *gk = reinterpret_cast<const char *>(tKrA + struct_tile_index(m0, jlo, nep));
                 __syncwarp();
-                RingFeed<CC, TJ / 2> feed;
-                feed.start(ring, gk, rstride, cl);
+                RingFeed<CC, TI * TJ / 2> feed;
+                feed.start(ring, gk, cl);
 #pragma unroll
                 for (int t = 0; t < NSTAGE - 1; ++t) {
-                    feed.load(t < mytiles, TJ * 8);
+                    feed.load(t < mytiles);
                     cp_async_commit();
                 }
                 const char *kt_stage = ring;
                 for (int t = 0; t < ntile; ++t) {
                     cp_async_wait<NSTAGE - 2>();
                     __syncwarp();
-                    feed.load(t + NSTAGE - 1 < mytiles, TJ * 8);
+                    feed.load(t + NSTAGE - 1 < mytiles);
                     cp_async_commit();
                     if (t >= mytiles) continue;
                     const double *kt = reinterpret_cast<const double *>(kt_stage);

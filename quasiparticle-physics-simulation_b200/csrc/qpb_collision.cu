@@ -283,11 +283,11 @@ int qpbk_collision_setup(qpb_ctx *c) {
         for (int i = 0; i < ne; ++i) {
             rhop[(size_t)g * nep + i] = rho[(size_t)g * ne + i];
             for (int j = 0; j < ne; ++j) {
-                K2[np2 * g + (size_t)i * nep + j] = make_double2(dE * ks[(size_t)i * ne + j], 2.0 * dE * kr[(size_t)i * ne + j]);
-                if (i >= j) KsD[np2 * g + (size_t)(i - j) * nep + j] = dE * ks[(size_t)i * ne + j];
+                K2[np2 * g + struct_tile_index(i, j, nep)] = make_double2(dE * ks[(size_t)i * ne + j], 2.0 * dE * kr[(size_t)i * ne + j]);
+                if (i >= j) KsD[np2 * g + struct_tile_index(i - j, j, nep)] = dE * ks[(size_t)i * ne + j];
                 if (j <= i) {
                     const double wgt = j < i ? 2.0 : 1.0;
-                    KrA[2 * np2 * g + (size_t)(i + j) * nep + j] = wgt * dE * kr[(size_t)i * ne + j];
+                    KrA[2 * np2 * g + struct_tile_index(i + j, j, nep)] = wgt * dE * kr[(size_t)i * ne + j];
                 }
             }
         }
