@@ -99,6 +99,37 @@ def test_collision_kernels_nonuniform_tables(path, ne, n, ngaps, monkeypatch):
     helpers.assert_close(ph.T, p_ref.T, "n_ph", rtol=helpers.RTOL_PHONON)
 
 
+@pytest.mark.parametrize("ne,n", [(24, 700), (64, 1500), (56, 333)])
+def test_collision_cta_shapes_on_small_energy_grids_agree(ne, n, monkeypatch):
+    """Energy grids of at most 64 bins run 256-thread CTAs, two per SM; QPB_COLL_NT=512 keeps the wide CTA the larger
+    grids use.  Same tiles, another split of the diagonals between the warps: both against the oracle (solver.py:703-791)
+    and against each other (the pieces of a diagonal meet through shared-memory atomics, so the last bits may differ)."""
+    rng = np.random.default_rng(11)
+    E, dE = Q.build_energy_grid(cases.GAP, 1.0, 3.0, ne)
+    om, idd, ids, sg = Q.phonon_frequency_map(E)
+    rho = Q.density_of_states(E, cases.GAP, 0.18)
+    Kr = Q.recombination_kernel_base(E, cases.GAP, 440.0, 1.2)
+    Ks = Q.scattering_kernel_base(E, cases.GAP, 440.0, 1.2)
+    state0 = rho[:, None] * rng.uniform(0, 0.4, (ne, n))
+    ph0 = Q.thermal_phonon_occupation(om, 0.3)[:, None] * rng.uniform(0.5, 2, (om.size, n))
+    s_ref, p_ref = state0.copy(), ph0.copy()
+    O.collide(s_ref, p_ref, Kr, Ks, rho, idd, ids, sg, dE, 0.4, recomb=True, scat=True)
+    got = {}
+    for nt in ("", "512"):
+        if nt:
+            monkeypatch.setenv("QPB_COLL_NT", nt)
+        else:
+            monkeypatch.delenv("QPB_COLL_NT", raising=False)
+        s, p = state0.copy(), ph0.copy()
+        Q.apply_collision_step_fischer_catelani_uniform(s, p, Kr, Ks, rho, idd, ids, sg, dE, 0.4,
+                                                        enable_recombination=True, enable_scattering=True)
+        helpers.assert_close(s.T, s_ref.T, f"n (QPB_COLL_NT={nt or 'default'})", rtol=1e-10)
+        helpers.assert_close(p.T, p_ref.T, f"n_ph (QPB_COLL_NT={nt or 'default'})", rtol=helpers.RTOL_PHONON)
+        got[nt] = (s, p)
+    helpers.assert_close(got[""][0].T, got["512"][0].T, "n, narrow against wide CTA", rtol=1e-13)
+    helpers.assert_close(got[""][1].T, got["512"][1].T, "n_ph, narrow against wide CTA", rtol=1e-9)
+
+
 def test_reflective_uniform_field_is_stationary():
     """tests/test_regressions.py:232-252 of the reference: uniform field, reflective walls, mass = 12."""
     mask = np.ones((3, 4), dtype=bool)
