@@ -831,7 +831,9 @@ def run_reference(args):
         "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": w["name"], "cells": n, "energy_bins": ne,
-                   "step": "one pass over a bounded sample of the workload (see cpu_baseline.sample)"},
+                   "step": "one pass over a bounded sample of the workload (see cpu_baseline.sample)",
+                   # value = this / (ms_per_step / 1e3): the cell*bin updates one sampled pass stands for
+                   "updates_per_sampled_step": v * float(np.mean([r["sample_step_s"] for r in runs]))},
         "cpu_baseline": {"kind": last["kind"], "cores": last["cores"], "sample": last["sample"], "value": v,
                          "unit": UNIT, "extrapolated": True, "single_core_value": last["single_core_value"],
                          "spread": [float(r["value"]) for r in runs]},
