@@ -20,7 +20,7 @@ for obj in sorted(glob.glob(os.path.join(ROOT, "quasiparticle-physics-simulation
         if not WANT.search(name):
             continue
         cnt = collections.Counter()
-        for m in re.finditer(r"^\s+/\*[0-9a-f]{4}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", body, re.M):
+        for m in re.finditer(r"^\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", body, re.M):
             op = m.group(1)
             if KEEP.match(op):
                 key = op if op.startswith(("UTMA", "SYNCS", "LDGSTS", "DMMA", "UCGABAR", "STAS", "CCTL", "MEMBAR")) else op.split(".")[0]
