@@ -8,7 +8,11 @@
 //   * a thread owns TI = 8 rows (pass 1), diagonals (pass 2) or anti-diagonals (pass 3) and walks the other index
 //     in register tiles of TJ = 4; its accumulators never leave registers, so there is no cross-thread reduction;
 //   * the kernel-matrix tiles (8 x 4 elements) stream from L2 through a per-warp cp.async ring (3 stages), so the
-//     FP64 pipe does not wait on global loads; operands of a tile are read as 128-bit broadcasts.
+//     FP64 pipe does not wait on global loads; operands of a tile are read as 128-bit broadcasts.  The tables are
+//     stored tile by tile, a ring stage is one flat copy (RingFeed);
+//   * the columns pair what is read together: (n, p) of an energy index, and the phonon occupations of two
+//     consecutive indices of a family, each one 128-bit shared-memory read - 61 % of the kernel's warp instructions
+//     are DFMA / DMUL / DADD (DESIGN.md section 4.2 has the step-by-step record).
 //
 //   pass 1 (rows, quasiparticles)      L_i = sum_j [dE Ks (nd + [i>j]) p_j + 2dE Kr (1 + ns) n_j]
 //                                      G_i = sum_j [dE Ks (nd + [j>i]) n_j + 2dE Kr ns p_j],  gain_i = p_i G_i
