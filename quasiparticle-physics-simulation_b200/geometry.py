@@ -29,6 +29,34 @@ def boundary_face_masks(mask: np.ndarray) -> dict[str, np.ndarray]:
     return {"up": up, "down": down, "left": left, "right": right}
 
 
+def boundary_face_indices(mask: np.ndarray) -> dict[str, np.ndarray]:
+    """Sorted flat (row-major) indices of the cells that have a domain boundary on each side: the same sets as
+    ``flatnonzero`` of :func:`boundary_face_masks`, found through the cells that are not interior (one grid-sized pass
+    and a thin candidate list instead of four grid-sized selections)."""
+    m = np.asarray(mask, dtype=bool)
+    ny, nx = m.shape
+    inner = m.copy()
+    inner[0, :] = inner[-1, :] = False
+    inner[:, 0] = inner[:, -1] = False
+    if ny > 2 and nx > 2:
+        core = inner[1:-1, 1:-1]
+        core &= m[:-2, 1:-1]
+        core &= m[2:, 1:-1]
+        core &= m[1:-1, :-2]
+        core &= m[1:-1, 2:]
+    cand = np.flatnonzero((m & ~inner).ravel())      # mask cells with at least one missing neighbour
+    r, c = np.divmod(cand, nx)
+    flat = m.ravel()
+    out = {}
+    has = np.zeros(cand.size, dtype=bool)
+    for name, ok, nb in (("up", r > 0, cand - nx), ("down", r < ny - 1, cand + nx),
+                         ("left", c > 0, cand - 1), ("right", c < nx - 1, cand + 1)):
+        has[:] = False
+        has[ok] = flat[nb[ok]]
+        out[name] = cand[~has]
+    return out
+
+
 def _runs(sorted_pos: np.ndarray):
     """Split a sorted integer array into maximal runs of consecutive values -> list of (start, end_exclusive)."""
     if sorted_pos.size == 0:
@@ -46,7 +74,8 @@ def extract_edge_segments(mask: np.ndarray) -> list[EdgeSegment]:
     maximal runs of adjacent columns; then vertical faces ordered by x then normal ("left" < "right").
     """
     m = np.asarray(mask, dtype=bool)
-    faces = boundary_face_masks(m)
+    faces = boundary_face_indices(m)
+    nx_grid = m.shape[1]
     out: list[EdgeSegment] = []
 
     def add(normal, line, a, b):
@@ -62,7 +91,7 @@ def extract_edge_segments(mask: np.ndarray) -> list[EdgeSegment]:
 
     groups = []
     for normal in ("down", "up"):
-        rows, cols = np.nonzero(faces[normal])
+        rows, cols = np.divmod(faces[normal], nx_grid)
         line = rows + (1 if normal == "down" else 0)
         for y in np.unique(line):
             groups.append((int(y), normal, np.sort(cols[line == y])))
@@ -71,7 +100,7 @@ def extract_edge_segments(mask: np.ndarray) -> list[EdgeSegment]:
             add(normal, y, a, b)
     groups = []
     for normal in ("left", "right"):
-        rows, cols = np.nonzero(faces[normal])
+        rows, cols = np.divmod(faces[normal], nx_grid)
         line = cols + (1 if normal == "right" else 0)
         for x in np.unique(line):
             groups.append((int(x), normal, np.sort(rows[line == x])))
@@ -127,14 +156,24 @@ def compile_boundaries(mask: np.ndarray, edges, edge_conditions, dx: float):
     ny, nx = m.shape
     inv_dx = 1.0 / dx
     inv_dx2 = inv_dx * inv_dx
-    bcx = np.zeros((ny, nx))
-    bcy = np.zeros((ny, nx))
-    src = np.zeros((ny, nx))
-    covered = {d: np.zeros((ny, nx), dtype=bool) for d in _FACE_DIRS}
+    # The boundary faces are a thin set: everything is kept on their sorted flat indices, one short array per
+    # direction - no grid-sized scratch arrays (at 2048 x 2048 a dozen of them cost more in page faults than the rest).
+    faces = boundary_face_indices(m)
+    covered = {d: np.zeros(faces[d].size, dtype=bool) for d in _FACE_DIRS}
     # later edges overwrite earlier ones for a shared face (dict semantics of solver.py:37-50); accumulate per
     # face first, then add, so a face listed twice is not counted twice
-    face_diag = {d: np.zeros((ny, nx)) for d in _FACE_DIRS}
-    face_src = {d: np.zeros((ny, nx)) for d in _FACE_DIRS}
+    face_diag = {d: np.zeros(faces[d].size) for d in _FACE_DIRS}
+    face_src = {d: np.zeros(faces[d].size) for d in _FACE_DIRS}
+
+    def positions(d, flat):
+        """Index into faces[d] of every flat cell index that is a boundary face of direction d (others dropped)."""
+        fd = faces[d]
+        if fd.size == 0:
+            return np.zeros(0, dtype=np.int64)
+        pos = np.searchsorted(fd, flat)
+        pos[pos == fd.size] = 0
+        return pos[fd[pos] == flat]
+
     for edge in edges:
         bc = edge_conditions.get(edge.edge_id)
         if bc is None:
@@ -162,31 +201,31 @@ def compile_boundaries(mask: np.ndarray, edges, edge_conditions, dx: float):
             continue
         for d, r, c in _face_arrays(edge):
             ok = (r >= 0) & (r < ny) & (c >= 0) & (c < nx)
-            r, c = r[ok], c[ok]
-            covered[d][r, c] = True
-            face_diag[d][r, c] = diag
-            face_src[d][r, c] = s
+            pos = positions(d, r[ok] * nx + c[ok])
+            covered[d][pos] = True
+            face_diag[d][pos] = diag
+            face_src[d][pos] = s
     missing = [e.edge_id for e in edges if e.edge_id not in edge_conditions]
     if missing:
         raise BoundaryAssignmentError(
             f"All edges must be assigned boundary conditions before simulation. Missing: {len(missing)}"
         )
-    need = boundary_face_masks(m)
-    # the boundary faces are a thin set: work on their flat indices, not on grid-sized boolean selections
-    faces = {d: np.flatnonzero(need[d].ravel()) for d in _FACE_DIRS}
-    uncovered = {d: faces[d][~covered[d].ravel()[faces[d]]] for d in _FACE_DIRS}
+    uncovered = {d: faces[d][~covered[d]] for d in _FACE_DIRS}
     if any(u.size for u in uncovered.values()):
         first = min(int(u[0]) for u in uncovered.values() if u.size)   # first offending cell in row-major order
         r, c = divmod(first, nx)
         for d in _FACE_DIRS:
-            if need[d][r, c] and not covered[d][r, c]:
+            if uncovered[d].size and first in uncovered[d]:
                 raise BoundaryAssignmentError(
                     f"Missing boundary condition for face at cell ({r}, {c}) direction '{d}'."
                 )
+    bcx = np.zeros((ny, nx))
+    bcy = np.zeros((ny, nx))
+    src = np.zeros((ny, nx))
     flat_src = src.ravel()
     for d in _FACE_DIRS:
         idx = faces[d]
         tgt = (bcx if d in ("left", "right") else bcy).ravel()
-        tgt[idx] += face_diag[d].ravel()[idx]
-        flat_src[idx] += face_src[d].ravel()[idx]
+        tgt[idx] += face_diag[d]
+        flat_src[idx] += face_src[d]
     return bcx, bcy, src
